@@ -1,0 +1,123 @@
+"""Pins oracle/qlinear_oracle.py against vectors produced by the reference's own Python code
+(tests/golden/make_golden.py). Integer work is bit-exact; float work within stated tolerance."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import qlinear_oracle as O
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("bits", range(2, 9))
+def test_bitstream_codec_matches_reference(golden_dir, bits):
+    d = _load(golden_dir, "codec.npz")
+    q, p = d[f"q{bits}"], d[f"p{bits}"]
+    assert np.array_equal(O.pack_rows(q, bits), p)            # compress_weight.py:46-51
+    assert np.array_equal(O.unpack_rows(p, bits, q.shape[0]), q)   # compress_weight.py:87-92
+
+
+def _gptq_cases(d):
+    i = 0
+    while f"c{i}_meta" in d:
+        yield i
+        i += 1
+
+
+def test_gptq_unpack_and_forward(golden_dir):
+    d = _load(golden_dir, "gptq.npz")
+    for i in _gptq_cases(d):
+        bits, gs, K, N, act = (int(v) for v in d[f"c{i}_meta"])
+        p = f"c{i}_"
+        q, z, s, gi = O.unpack_layer("GPTQ", bits, gs, K, N, d[p + "qweight"], d[p + "qzeros"],
+                                     d[p + "scales"], d[p + "g_idx"])
+        assert np.array_equal(z, d[p + "unpack_z"]), f"case {i}: qzeros unpack"
+        # re-pack is the identity on the reference's bytes
+        assert np.array_equal(O.gptq_pack_qweight(q, bits), d[p + "qweight"])
+        assert np.array_equal(O.gptq_pack_qzeros(z, bits), d[p + "qzeros"])
+        # reference unpack() returns fp16(q*s - z*s)^T in fp32 scales here -> compare in fp32
+        W = O.dequant(q, z, s, gi, "exact")
+        assert np.allclose(W.T, d[p + "unpack_w"], rtol=0, atol=2e-3 * np.abs(W).max())
+        # reference fp32 CPU forward (DequantizeLinearBlockWise + matmul + bias)
+        y = O.matmul_ref(d[p + "x"], W, d[p + "bias"], acc=np.float64)
+        ref = d[p + "y32"]
+        assert np.abs(y - ref).max() <= 1e-3 * np.abs(ref).max(), f"case {i}: forward"
+
+
+def test_autogptq_zero_fixup(golden_dir):
+    d = _load(golden_dir, "gptq.npz")
+    z = d["autogptq_z"]
+    assert np.array_equal(O.gptq_pack_qzeros(z, 4, zero_bias=1), d["autogptq_stored"])
+    assert np.array_equal(O.autogptq_fix_qzeros(d["autogptq_stored"], 4, z.shape[1]), d["autogptq_fixed"])
+    assert np.array_equal(O.gptq_unpack_qzeros(d["autogptq_fixed"], 4, z.shape[1]), z)
+
+
+def test_hqq_forward(golden_dir):
+    d = _load(golden_dir, "hqq.npz")
+    i = 0
+    while f"c{i}_meta" in d:
+        bits, gs, K, N = (int(v) for v in d[f"c{i}_meta"])
+        p = f"c{i}_"
+        y = O.forward("HQQ", bits, gs, K, N, d[p + "x"], d[p + "qweight"], d[p + "qzeros"], d[p + "scales"],
+                      mode="exact", acc=np.float64)
+        ref = d[p + "y32"]
+        assert np.abs(y - ref).max() <= 1e-3 * np.abs(ref).max(), f"case {i}"
+        i += 1
+    assert i == 4
+
+
+def test_awq_layout(golden_dir):
+    d = _load(golden_dir, "awq.npz")
+    for i in range(2):
+        bits, gs, K, N = (int(v) for v in d[f"c{i}_meta"])
+        p = f"c{i}_"
+        q = O.awq_unpack_qweight(d[p + "qweight"])
+        z = O.awq_unpack_qzeros(d[p + "qzeros"])
+        # reference unpack_qweight returns [K, N]; unpack_qzeros returns [G, N]
+        assert np.array_equal(q, d[p + "int_w"])
+        assert np.array_equal(z, d[p + "unpack_z"])
+        assert np.array_equal(O.awq_pack_qweight(q), d[p + "qweight"])
+        assert np.array_equal(O.awq_pack_qzeros(z), d[p + "qzeros"])
+        W = O.dequant(q, z, d[p + "scales"], O.default_g_idx(K, gs), "torch")
+        assert np.array_equal(W.T.astype(np.float32), d[p + "unpack_w"])     # fp16 bit-exact
+
+
+def test_marlin_layout(golden_dir):
+    d = _load(golden_dir, "marlin.npz")
+    for i in range(2):
+        bits, gs, K, N = (int(v) for v in d[f"c{i}_meta"])
+        p = f"c{i}_"
+        qw, sp = O.marlin_pack(d[p + "int_w"], d[p + "nat_scales"], gs)
+        assert np.array_equal(qw, d[p + "qweight"])
+        assert np.array_equal(sp.view(np.uint16), d[p + "scales"].view(np.uint16))
+        q, s = O.marlin_unpack(d[p + "qweight"], d[p + "scales"], gs, K)
+        assert np.array_equal(q, d[p + "int_w"])
+        assert np.array_equal(s.view(np.uint16), d[p + "nat_scales"].view(np.uint16))
+
+
+def test_marlin_closed_form_word00():
+    """SURVEY Appendix A.7 worked example: word [0,0] nibbles = (k,n):
+    (0,0),(8,0),(0,8),(8,8),(1,0),(9,0),(1,8),(9,8)."""
+    K, N = 16, 64
+    q = (np.arange(K)[:, None] * 0 + 0).astype(np.int32) + np.zeros((K, N), np.int32)
+    marks = [(0, 0), (8, 0), (0, 8), (8, 8), (1, 0), (9, 0), (1, 8), (9, 8)]
+    for v, (k, n) in enumerate(marks):
+        q[k, n] = v + 1
+    qw, _ = O.marlin_pack(q, np.ones((1, N), np.float16), K)
+    w = int(qw.view(np.uint32)[0, 0])
+    assert [(w >> (4 * i)) & 0xF for i in range(8)] == list(range(1, 9))
+
+
+@pytest.mark.parametrize("layout,bits", [("GPTQ", 2), ("GPTQ", 3), ("GPTQ", 4), ("GPTQ", 8),
+                                          ("HQQ", 4), ("GEMM", 4), ("MARLIN", 4)])
+def test_make_layer_roundtrip(layout, bits):
+    L = O.make_layer(layout, bits, 64 if layout != "MARLIN" else 128, 256, 256, seed=3,
+                     act_order=(layout == "GPTQ" and bits == 4))
+    q, z, s, gi = O.unpack_layer(layout, bits, L["group_size"], 256, 256, L["qweight"], L["qzeros"],
+                                 L["scales"], L["g_idx"])
+    assert np.array_equal(q, L["q"])
+    assert np.array_equal(np.asarray(z), np.asarray(L["z"]))
+    assert np.array_equal(s.view(np.uint16), L["s"].view(np.uint16))
