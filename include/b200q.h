@@ -1,0 +1,144 @@
+/*
+ * b200q.h -- C ABI of the B200-native fused dequant-matmul engine (libb200q.so).
+ *
+ * This is the drop-in boundary behind QLLM's QuantLinear.forward.  Every entry point below
+ * replaces one (or several) of the reference's native entry points for the hot path; the
+ * reference interface each one stands in for is cited as file:line relative to the reference
+ * tree (wejoncy/QLLM @ df20c15).  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only; every pointer is a CUDA *device* pointer unless stated otherwise;
+ *   - the engine never allocates, frees or synchronises; work is enqueued on `stream`
+ *     (the reference enqueues on at::cuda::getCurrentCUDAStream(): gemm_cuda_gen.cu:1126);
+ *   - return value: B200Q_OK (0) or a negative b200q_status code, never abort()
+ *     (the reference aborts on unsupported bits / launch failure: dq_gemv.cu:156-159,:172-176);
+ *   - all calls are CUDA-graph capturable (no host-side data-dependent control flow);
+ *   - activations and outputs are IEEE fp16, row-major, with explicit row strides.
+ *
+ * Logical math for every layout:
+ *     W[k,n] = scales[g(k),n] * (q[k,n] - z[g(k),n]),   y[m,:] = x[m,:] @ W (+ bias)
+ * with g(k) = g_idx[k] when g_idx != NULL, else k / group_size.
+ */
+#ifndef B200Q_H_
+#define B200Q_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200Q_VERSION 100 /* 0.1.0 */
+
+/* Opaque CUDA stream handle (cudaStream_t) passed as a pointer-sized integer. */
+typedef void* b200q_stream_t;
+
+typedef enum b200q_status {
+  B200Q_OK = 0,
+  B200Q_ERR_NULL = -1,        /* required pointer is NULL */
+  B200Q_ERR_SHAPE = -2,       /* K/N/M/group violate the layout's constraints (cf. ERR_PROB_SHAPE, marlin_cuda_kernel.cu:803) */
+  B200Q_ERR_UNSUPPORTED = -3, /* (layout, bits, group, g_idx) combination has no kernel */
+  B200Q_ERR_ALIGNMENT = -4,   /* pointer / stride not 16-byte aligned where required */
+  B200Q_ERR_WORKSPACE = -5,   /* workspace smaller than b200q_workspace_bytes() */
+  B200Q_ERR_CUDA = -6,        /* a CUDA runtime call failed; see b200q_last_cuda_error() */
+  B200Q_ERR_ARCH = -7         /* device is not sm_100 (tcgen05/TMA kernels cannot run) */
+} b200q_status;
+
+/* Packed-weight layouts ("pack modes", qllm/run.py:58-70; classes in qllm/modeling/q_layers/). */
+typedef enum b200q_layout {
+  B200Q_LAYOUT_GPTQ = 0,     /* QuantLinearGPTQ   quant_linear_gptq.py:92-143  qweight i32 [K*b/32, N], qzeros i32 [G, N*b/32] */
+  B200Q_LAYOUT_AWQ_GEMM = 1, /* WQLinear_GEMM     quant_linear_awq.py:38-153   qweight i32 [K, N/8],   qzeros i32 [G, N/8], nibble order 0,2,4,6,1,3,5,7 */
+  B200Q_LAYOUT_MARLIN = 2,   /* QuantLinearMarlin quant_linear_marlin.py:60-146 qweight i32 [K/16, 2N], scales permuted, z == 8 */
+  B200Q_LAYOUT_HQQ = 3       /* QuantLinearHQQ    quant_linear_hqq.py:48-80    qweight as GPTQ, qzeros fp16 [G, N] */
+} b200q_layout;
+
+/*
+ * One quantised linear layer, exactly as its buffers sit in a QLLM/AutoGPTQ/AutoAWQ checkpoint
+ * after load_state_dict (no repacking).  Mirrors the module attributes of the q_layers classes.
+ */
+typedef struct b200q_layer {
+  int32_t layout;      /* b200q_layout */
+  int32_t bits;        /* 2,3,4,8 fast paths; 5,6,7 generic path (GPTQ/HQQ only); AWQ/MARLIN: 4 */
+  int32_t group_size;  /* >0; per-channel (-1 in the reference) must be passed as K */
+  int32_t K;           /* in_features  */
+  int32_t N;           /* out_features held by this rank (column shard width when sharded) */
+  int32_t zero_bias;   /* added to unpacked integer zeros then masked: the reference's
+                          COMPATIBLE_WITH_AUTOGPTQ env / add_zero_bias arg (ort_ops.cc:63). 0 or 1. */
+  const void* qweight; /* int32, shape per layout */
+  const void* qzeros;  /* int32 packed (GPTQ, AWQ_GEMM) | fp16 [G,N] (HQQ) | NULL (MARLIN) */
+  const void* scales;  /* fp16 [G,N] (MARLIN: in the reference's permuted order) */
+  const int32_t* g_idx;/* int32 [K] act-order group map, or NULL for k / group_size (GPTQ only) */
+  const void* bias;    /* fp16 [N] or NULL */
+} b200q_layer;
+
+/*
+ * y[M, N] = x[M, K] @ dequant(layer) (+ bias).  The single forward entry point: chooses the
+ * decode kernel (M <= b200q_gemv_max_m()) or the tcgen05 tensor-core GEMM.
+ * Replaces, depending on layer->layout:
+ *   awq_inference_engine.gemm_forward_cuda   csrc/awq_cuda/pybind_awq.cpp:16, quantization/gemm_cuda_gen.cu:1102-1161
+ *   awq_inference_engine.mul (Marlin)        csrc/awq_cuda/pybind_awq.cpp:20, quantization/marlin_cuda.cpp:29-74
+ *   ort_ops.gemv                             csrc/ort_cuda/ort_ops.cc:94-140
+ *   ort_ops.dequant + torch.matmul           csrc/ort_cuda/ort_ops.cc:58-92, quant_linear_gptq.py:81-85
+ *   DequantAndUnpack + torch.matmul (HQQ)    qllm/modeling/q_layers/quant_linear_hqq.py:8-38
+ * ldx / ldy are row strides in elements (ldy lets a column shard write into a wider output).
+ * workspace: >= b200q_workspace_bytes(layer, M) bytes, 16-byte aligned, ZERO on first use; the
+ * engine leaves it zeroed again on completion (same contract as Marlin's workspace,
+ * marlin_cuda_kernel.cu:203-210), so one buffer may be reused by successive calls on a stream.
+ */
+int b200q_linear(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy,
+                 void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+
+/* Same contract, forcing the decode (GEMV-class) kernel; M must be <= b200q_gemv_max_m(). */
+int b200q_gemv(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy,
+               void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+
+/* Same contract, forcing the tcgen05 GEMM kernel (any M >= 1). */
+int b200q_gemm(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy,
+               void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+
+/*
+ * Multi-GPU column-sharded forward with the all-gather fused into the epilogue: this rank computes
+ * y[:, n_offset : n_offset + layer->N] and stores the tile into `n_peers` output buffers
+ * (peer_y[r] = rank r's full [M, ldy] output, mapped through NVLink peer access / symmetric memory;
+ * peer_y[self] is the local one).  No reference equivalent (the reference is single-GPU).
+ */
+int b200q_linear_sharded(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx,
+                         void* const* peer_y, int32_t n_peers, int64_t ldy, int64_t n_offset,
+                         void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+
+/*
+ * W_out[K, N] (fp16, row-major, ld = N) = dequant(layer), rounded once: fp16((q - z) * s).
+ * Replaces ort_ops.dequant (csrc/ort_cuda/ort_ops.cc:58-92 -> dq_gemv.cu:696-725) for every
+ * layout and bit width, with or without g_idx.
+ */
+int b200q_dequant(const b200q_layer* layer, void* w_out, b200q_stream_t stream);
+
+/*
+ * Integer unpack (bit-exact gate): q_out int32 [K, N]; z_out int32 [G, N] (may be NULL; for HQQ
+ * zeros are floats and z_out is ignored).  Device restatement of general_unpack_on_row
+ * (compress_weight.py:87-92), WQLinear_GEMM.unpack_qweight/unpack_qzeros (quant_linear_awq.py:76-93)
+ * and of the Marlin inverse permutation the reference lacks (quant_linear_marlin.py:139-140).
+ */
+int b200q_unpack(const b200q_layer* layer, int32_t* q_out, int32_t* z_out, b200q_stream_t stream);
+
+/* Bytes of zero-initialised workspace b200q_linear/gemv/gemm need for this layer at batch M. */
+size_t b200q_workspace_bytes(const b200q_layer* layer, int64_t M);
+
+/* Largest M routed to the decode kernel by b200q_linear. */
+int b200q_gemv_max_m(void);
+
+/* Which kernel b200q_linear would pick: 1 = decode kernel, 2 = tcgen05 GEMM, <0 = status. */
+int b200q_select_kernel(const b200q_layer* layer, int64_t M);
+
+/* Number of kernel launches issued by this process through the library (bench accounting). */
+uint64_t b200q_launch_count(void);
+
+const char* b200q_strerror(int status);
+int b200q_last_cuda_error(void); /* cudaError_t of the most recent failing runtime call */
+int b200q_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H_ */

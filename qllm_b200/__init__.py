@@ -1,0 +1,19 @@
+"""qllm_b200 -- B200-native fused dequant-matmul engine behind QLLM's QuantLinear.forward.
+
+Importing this package loads libb200q.so (hand-written sm_100a CUDA behind a C ABI, include/b200q.h);
+if the library has not been built the import raises: there is no CPU or PyTorch fallback.
+"""
+from ._lib import lib, check, Layer  # noqa: F401  (raises ImportError when the .so is missing)
+from .q_layers import (QuantLinearGPTQ, QuantLinearHQQ, QuantLinearMarlin, WQLinear_GEMM,  # noqa: F401
+                       make_mixbits_quant_linear, select_quant_linear)
+
+__version__ = "0.1.0"
+
+
+def patch_qllm():
+    """Route an installed `qllm` through this engine: replaces the one dispatch function the reference
+    uses to pick its QuantLinear class (qllm/utils/modelutils.py:44).  See INTEGRATION.md."""
+    import qllm.utils.modelutils as mu
+    mu.select_quant_linear = select_quant_linear
+    mu.make_mixbits_quant_linear = make_mixbits_quant_linear
+    return mu

@@ -1,0 +1,70 @@
+"""ctypes binding of libb200q.so (include/b200q.h).  There is no fallback: if the shared library
+is missing the import fails loudly -- the product path is the CUDA engine or nothing."""
+import ctypes
+import os
+
+from ._build import LIB
+
+B200Q_OK = 0
+LAYOUT_GPTQ, LAYOUT_AWQ_GEMM, LAYOUT_MARLIN, LAYOUT_HQQ = 0, 1, 2, 3
+KERNEL_GEMV, KERNEL_GEMM, KERNEL_GENERIC = 1, 2, 3
+
+
+class Layer(ctypes.Structure):
+    """struct b200q_layer"""
+    _fields_ = [("layout", ctypes.c_int32), ("bits", ctypes.c_int32), ("group_size", ctypes.c_int32),
+                ("K", ctypes.c_int32), ("N", ctypes.c_int32), ("zero_bias", ctypes.c_int32),
+                ("qweight", ctypes.c_void_p), ("qzeros", ctypes.c_void_p), ("scales", ctypes.c_void_p),
+                ("g_idx", ctypes.c_void_p), ("bias", ctypes.c_void_p)]
+
+
+EXPORTS = ["b200q_linear", "b200q_gemv", "b200q_gemm", "b200q_linear_sharded", "b200q_dequant", "b200q_unpack",
+           "b200q_workspace_bytes", "b200q_gemv_max_m", "b200q_select_kernel", "b200q_launch_count",
+           "b200q_strerror", "b200q_last_cuda_error", "b200q_version"]
+
+
+def _load():
+    if not os.path.exists(LIB):
+        raise ImportError(
+            f"{LIB} not found: build it with `python -m qllm_b200._build` (nvcc, sm_100a). "
+            "qllm_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB)
+    P, I64, SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
+    LP = ctypes.POINTER(Layer)
+    fwd = [LP, P, I64, I64, P, I64, P, SZ, P]
+    for name in ("b200q_linear", "b200q_gemv", "b200q_gemm"):
+        getattr(lib, name).argtypes = fwd
+        getattr(lib, name).restype = ctypes.c_int
+    lib.b200q_linear_sharded.argtypes = [LP, P, I64, I64, ctypes.POINTER(P), ctypes.c_int32, I64, I64, P, SZ, P]
+    lib.b200q_linear_sharded.restype = ctypes.c_int
+    lib.b200q_dequant.argtypes = [LP, P, P]
+    lib.b200q_dequant.restype = ctypes.c_int
+    lib.b200q_unpack.argtypes = [LP, P, P, P]
+    lib.b200q_unpack.restype = ctypes.c_int
+    lib.b200q_workspace_bytes.argtypes = [LP, I64]
+    lib.b200q_workspace_bytes.restype = SZ
+    lib.b200q_gemv_max_m.restype = ctypes.c_int
+    lib.b200q_select_kernel.argtypes = [LP, I64]
+    lib.b200q_select_kernel.restype = ctypes.c_int
+    lib.b200q_launch_count.restype = ctypes.c_uint64
+    lib.b200q_strerror.argtypes = [ctypes.c_int]
+    lib.b200q_strerror.restype = ctypes.c_char_p
+    lib.b200q_last_cuda_error.restype = ctypes.c_int
+    lib.b200q_version.restype = ctypes.c_int
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int, what: str = "b200q"):
+    """Map status codes to the exception types the reference raises (SURVEY §8b errors row)."""
+    if status == B200Q_OK:
+        return
+    msg = f"{what}: {lib.b200q_strerror(status).decode()} (status {status})"
+    if status == -6:
+        msg += f", cudaError={lib.b200q_last_cuda_error()}"
+        raise RuntimeError(msg)
+    if status in (-2, -3, -4):
+        raise ValueError(msg)
+    raise RuntimeError(msg)

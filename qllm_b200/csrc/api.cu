@@ -1,0 +1,193 @@
+// extern "C" surface of libb200q.so: argument validation, kernel selection, status codes.
+// No torch, no allocation, no synchronisation (include/b200q.h states the contract).
+#include <atomic>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200q {
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_last_cuda{0};
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int cuda_status(cudaError_t e) {
+  if (e == cudaSuccess) return B200Q_OK;
+  g_last_cuda.store((int)e);
+  (void)cudaGetLastError();
+  return B200Q_ERR_CUDA;
+}
+
+static int validate(const b200q_layer* L) {
+  if (!L || !L->qweight || !L->scales) return B200Q_ERR_NULL;
+  if (L->layout != B200Q_LAYOUT_MARLIN && !L->qzeros) return B200Q_ERR_NULL;
+  if (L->K <= 0 || L->N <= 0 || L->group_size <= 0) return B200Q_ERR_SHAPE;
+  if (L->bits < 2 || L->bits > 8) return B200Q_ERR_UNSUPPORTED;
+  if (L->zero_bias != 0 && L->zero_bias != 1) return B200Q_ERR_UNSUPPORTED;
+  if (L->K % L->group_size != 0 && L->g_idx == nullptr) return B200Q_ERR_SHAPE;
+  if (L->N % 8 != 0) return B200Q_ERR_SHAPE;
+  switch (L->layout) {
+    case B200Q_LAYOUT_GPTQ:
+    case B200Q_LAYOUT_HQQ:
+      // bit-stream along K must fill whole words (compress_weight.py:178), qzeros along N likewise
+      if (((int64_t)L->K * L->bits) % 32 != 0) return B200Q_ERR_SHAPE;
+      if (L->layout == B200Q_LAYOUT_GPTQ && ((int64_t)L->N * L->bits) % 32 != 0) return B200Q_ERR_SHAPE;
+      if (L->layout == B200Q_LAYOUT_HQQ && L->g_idx) return B200Q_ERR_UNSUPPORTED;
+      break;
+    case B200Q_LAYOUT_AWQ_GEMM:
+      if (L->bits != 4) return B200Q_ERR_UNSUPPORTED;       // quant_linear_awq.py:42-43
+      if (L->g_idx) return B200Q_ERR_UNSUPPORTED;           // quant_linear_awq.py:96-103
+      break;
+    case B200Q_LAYOUT_MARLIN:
+      if (L->bits != 4 || L->g_idx) return B200Q_ERR_UNSUPPORTED;   // quant_linear_marlin.py:96-99
+      if (L->K % 16 != 0 || L->N % 64 != 0) return B200Q_ERR_SHAPE; // tile permutation granularity
+      break;
+    default:
+      return B200Q_ERR_UNSUPPORTED;
+  }
+  if (((uintptr_t)L->qweight & 3) || ((uintptr_t)L->scales & 1)) return B200Q_ERR_ALIGNMENT;
+  return B200Q_OK;
+}
+
+static constexpr int kGemvMaxM = 8;
+static constexpr int kGenericMaxM = 16;
+
+enum { KERNEL_GEMV_MMA = 1, KERNEL_GEMM_TC = 2, KERNEL_GENERIC = 3 };
+
+static int select(const LayerView& V, int64_t M, const __half* x, int64_t ldx, int force) {
+  if (force == KERNEL_GEMM_TC) return gemm_tc_supported(V, M, x, ldx) ? KERNEL_GEMM_TC : B200Q_ERR_UNSUPPORTED;
+  if (force == KERNEL_GEMV_MMA) {
+    if (M > kGenericMaxM) return B200Q_ERR_SHAPE;
+    return (M <= kGemvMaxM && gemv_mma_supported(V, (int)M, x, ldx)) ? KERNEL_GEMV_MMA : KERNEL_GENERIC;
+  }
+  if (M <= kGemvMaxM && gemv_mma_supported(V, (int)M, x, ldx)) return KERNEL_GEMV_MMA;
+  if (M > kGemvMaxM && gemm_tc_supported(V, M, x, ldx)) return KERNEL_GEMM_TC;
+  if (M <= kGemvMaxM) return KERNEL_GENERIC;
+  if (gemm_tc_supported(V, M, x, ldx)) return KERNEL_GEMM_TC;
+  return KERNEL_GENERIC;   // chunked over 16-row slabs: slow, but no configuration is refused
+}
+
+static size_t workspace_for(const LayerView& V, int64_t M) {
+  size_t w = 0;
+  const int mg = (int)(M < kGenericMaxM ? M : kGenericMaxM);
+  w = gemv_generic_workspace(V, mg);
+  if (M <= kGemvMaxM) { const size_t a = gemv_mma_workspace(V, (int)M); if (a > w) w = a; }
+  const size_t g = gemm_tc_workspace(V, M);
+  if (g > w) w = g;
+  return (w + 255) & ~(size_t)255;
+}
+
+static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, const PeerOut* peers, void* y,
+               int64_t ldy, int64_t n_offset, void* ws, size_t ws_bytes, b200q_stream_t stream, int force) {
+  const int v = validate(layer);
+  if (v != B200Q_OK) return v;
+  if (!x || (!y && !peers)) return B200Q_ERR_NULL;
+  if (M < 1 || ldx < layer->K || ldy < n_offset + layer->N) return B200Q_ERR_SHAPE;
+  const LayerView V = make_view(layer);
+  const int kern = select(V, M, (const __half*)x, ldx, force);
+  if (kern < 0) return kern;
+  const size_t need = workspace_for(V, M);
+  if (need > 0 && (!ws || ws_bytes < need)) return B200Q_ERR_WORKSPACE;
+  if (ws && ((uintptr_t)ws & 15)) return B200Q_ERR_ALIGNMENT;
+  LinearArgs a;
+  a.L = V; a.x = (const __half*)x; a.ldx = ldx; a.M = (int)M; a.y = (__half*)y; a.ldy = ldy; a.n_offset = n_offset;
+  a.workspace = ws; a.workspace_bytes = ws_bytes; a.stream = (cudaStream_t)stream;
+  if (kern == KERNEL_GEMV_MMA) return cuda_status(launch_gemv_mma(a, peers));
+  if (kern == KERNEL_GEMM_TC) return cuda_status(launch_gemm_tc(a, peers));
+  // generic: slabs of <= 16 activation rows
+  for (int64_t m0 = 0; m0 < M; m0 += kGenericMaxM) {
+    LinearArgs s = a;
+    s.M = (int)((M - m0) < kGenericMaxM ? (M - m0) : kGenericMaxM);
+    s.x = a.x + m0 * ldx;
+    PeerOut po;
+    if (peers) { po = *peers; for (int i = 0; i < po.n; ++i) po.y[i] += m0 * ldy; }
+    else { po.n = 1; po.y[0] = a.y + m0 * ldy; }
+    const cudaError_t e = launch_gemv_generic(s, &po);
+    if (e != cudaSuccess) return cuda_status(e);
+  }
+  return B200Q_OK;
+}
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" {
+
+int b200q_linear(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy, void* workspace,
+                 size_t workspace_bytes, b200q_stream_t stream) {
+  return run(layer, x, M, ldx, nullptr, y, ldy, 0, workspace, workspace_bytes, stream, 0);
+}
+
+int b200q_gemv(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy, void* workspace,
+               size_t workspace_bytes, b200q_stream_t stream) {
+  return run(layer, x, M, ldx, nullptr, y, ldy, 0, workspace, workspace_bytes, stream, KERNEL_GEMV_MMA);
+}
+
+int b200q_gemm(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy, void* workspace,
+               size_t workspace_bytes, b200q_stream_t stream) {
+  return run(layer, x, M, ldx, nullptr, y, ldy, 0, workspace, workspace_bytes, stream, KERNEL_GEMM_TC);
+}
+
+int b200q_linear_sharded(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* const* peer_y,
+                         int32_t n_peers, int64_t ldy, int64_t n_offset, void* workspace, size_t workspace_bytes,
+                         b200q_stream_t stream) {
+  if (!peer_y) return B200Q_ERR_NULL;
+  if (n_peers < 1 || n_peers > kMaxPeers || n_offset < 0) return B200Q_ERR_SHAPE;
+  PeerOut po;
+  po.n = n_peers;
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peer_y[i]) return B200Q_ERR_NULL;
+    po.y[i] = (__half*)peer_y[i];
+  }
+  return run(layer, x, M, ldx, &po, nullptr, ldy, n_offset, workspace, workspace_bytes, stream, 0);
+}
+
+int b200q_dequant(const b200q_layer* layer, void* w_out, b200q_stream_t stream) {
+  const int v = validate(layer);
+  if (v != B200Q_OK) return v;
+  if (!w_out) return B200Q_ERR_NULL;
+  if ((uintptr_t)w_out & 15) return B200Q_ERR_ALIGNMENT;
+  return cuda_status(launch_dequant(make_view(layer), (__half*)w_out, (cudaStream_t)stream));
+}
+
+int b200q_unpack(const b200q_layer* layer, int32_t* q_out, int32_t* z_out, b200q_stream_t stream) {
+  const int v = validate(layer);
+  if (v != B200Q_OK) return v;
+  if (!q_out) return B200Q_ERR_NULL;
+  if ((uintptr_t)q_out & 15) return B200Q_ERR_ALIGNMENT;
+  return cuda_status(launch_unpack(make_view(layer), q_out, z_out, (cudaStream_t)stream));
+}
+
+size_t b200q_workspace_bytes(const b200q_layer* layer, int64_t M) {
+  if (validate(layer) != B200Q_OK || M < 1) return 0;
+  return workspace_for(make_view(layer), M);
+}
+
+int b200q_gemv_max_m(void) { return kGemvMaxM; }
+
+int b200q_select_kernel(const b200q_layer* layer, int64_t M) {
+  const int v = validate(layer);
+  if (v != B200Q_OK) return v;
+  // alignment-independent answer: assume a 16-byte aligned, densely strided x
+  return select(make_view(layer), M, (const __half*)nullptr, layer->K, 0);
+}
+
+uint64_t b200q_launch_count(void) { return g_launches.load(); }
+
+const char* b200q_strerror(int status) {
+  switch (status) {
+    case B200Q_OK: return "ok";
+    case B200Q_ERR_NULL: return "required pointer is NULL";
+    case B200Q_ERR_SHAPE: return "shape violates the layout's constraints";
+    case B200Q_ERR_UNSUPPORTED: return "unsupported (layout, bits, group, g_idx) combination";
+    case B200Q_ERR_ALIGNMENT: return "pointer or stride misaligned";
+    case B200Q_ERR_WORKSPACE: return "workspace too small (see b200q_workspace_bytes)";
+    case B200Q_ERR_CUDA: return "CUDA runtime error (see b200q_last_cuda_error)";
+    case B200Q_ERR_ARCH: return "device is not sm_100";
+    default: return "unknown status";
+  }
+}
+
+int b200q_last_cuda_error(void) { return g_last_cuda.load(); }
+int b200q_version(void) { return B200Q_VERSION; }
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// Internal launch interface between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace b200q {
+
+void count_launch(uint64_t n = 1);
+
+struct LinearArgs {
+  LayerView L;
+  const __half* x;
+  int64_t ldx;
+  int M;
+  // output: either a single y, or n_peers replicated destinations (fused all-gather epilogue)
+  __half* y;
+  int64_t ldy;
+  int64_t n_offset;     // column offset of this shard inside the (possibly wider) output rows
+  void* workspace;
+  size_t workspace_bytes;
+  cudaStream_t stream;
+};
+
+static constexpr int kMaxPeers = 8;
+struct PeerOut {
+  __half* y[kMaxPeers];
+  int n;
+};
+
+// unpack.cu
+cudaError_t launch_unpack(const LayerView& L, int32_t* q_out, int32_t* z_out, cudaStream_t st);
+cudaError_t launch_dequant(const LayerView& L, __half* w_out, cudaStream_t st);
+
+// gemv_generic.cu : any layout / bits / group / g_idx, M <= 16, CUDA cores
+size_t gemv_generic_workspace(const LayerView& L, int M);
+cudaError_t launch_gemv_generic(const LinearArgs& a, const PeerOut* peers);
+
+// gemv_mma.cu : fast decode path (bulk-copy pipeline + mma.sync), M <= 8
+bool gemv_mma_supported(const LayerView& L, int M, const __half* x, int64_t ldx);
+size_t gemv_mma_workspace(const LayerView& L, int M);
+cudaError_t launch_gemv_mma(const LinearArgs& a, const PeerOut* peers);
+
+// gemm_tcgen05.cu : tensor-core GEMM (TMA + tcgen05 + TMEM), any M
+bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t ldx);
+size_t gemm_tc_workspace(const LayerView& L, int64_t M);
+cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers);
+
+}  // namespace b200q

@@ -1,0 +1,61 @@
+// Element-wise unpack / dequant kernels for every layout and bit width (HBM-bound streaming).
+//   b200q_unpack  : packed -> int32 q[K,N], z[G,N]   (bit-exact gate vs compress_weight.py:87-92,
+//                   quant_linear_awq.py:76-93; adds the Marlin inverse the reference lacks)
+//   b200q_dequant : packed -> fp16 W[K,N]            (replaces ort_ops.dequant, ort_ops.cc:58-92)
+// One thread produces 8 consecutive columns of one row so that global stores are 16-byte
+// (fp16) / 32-byte (int32) vectors and packed loads along N are coalesced.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200q {
+
+template <bool kDequant>
+__global__ void __launch_bounds__(256) unpack_kernel(LayerView L, int32_t* __restrict__ q_out, __half* __restrict__ w_out) {
+  const int n8 = L.N >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)L.K * n8) return;
+  const int k = (int)(idx / n8);
+  const int n0 = (int)(idx % n8) << 3;
+  const int g = group_of(L, k);
+  if (kDequant) {
+    __align__(16) __half w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = dequant_one(L, load_q(L, k, n0 + i), load_z(L, g, n0 + i), load_s(L, g, n0 + i));
+    *reinterpret_cast<uint4*>(w_out + (size_t)k * L.N + n0) = *reinterpret_cast<const uint4*>(w);
+  } else {
+    __align__(16) int32_t q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = (int32_t)load_q(L, k, n0 + i);
+    int4* dst = reinterpret_cast<int4*>(q_out + (size_t)k * L.N + n0);
+    dst[0] = *reinterpret_cast<const int4*>(q);
+    dst[1] = *reinterpret_cast<const int4*>(q + 4);
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_zeros_kernel(LayerView L, int32_t* __restrict__ z_out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)L.G * L.N) return;
+  const int g = (int)(idx / L.N), n = (int)(idx % L.N);
+  z_out[idx] = (int32_t)load_z(L, g, n);
+}
+
+cudaError_t launch_unpack(const LayerView& L, int32_t* q_out, int32_t* z_out, cudaStream_t st) {
+  const size_t total = (size_t)L.K * (L.N >> 3);
+  unpack_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, q_out, nullptr);
+  count_launch();
+  if (z_out && L.layout != B200Q_LAYOUT_HQQ) {
+    const size_t tz = (size_t)L.G * L.N;
+    unpack_zeros_kernel<<<(unsigned)((tz + 255) / 256), 256, 0, st>>>(L, z_out);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dequant(const LayerView& L, __half* w_out, cudaStream_t st) {
+  const size_t total = (size_t)L.K * (L.N >> 3);
+  unpack_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, nullptr, w_out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace b200q

@@ -1,0 +1,376 @@
+"""Host-side mirror of QLLM's QuantLinear plug-in interface, backed by libb200q.so.
+
+Class names, constructor signatures, attribute and buffer names/shapes/dtypes are those of the
+reference's `qllm/modeling/q_layers/*` (so `load_state_dict` of any GPTQ/AWQ/HQQ/Marlin checkpoint
+fills them unchanged and `make_mixbits_quant_linear` can instantiate them):
+
+    QuantLinearGPTQ    quant_linear_gptq.py:92-143
+    WQLinear_GEMM      quant_linear_awq.py:38-153
+    QuantLinearMarlin  quant_linear_marlin.py:60-146   (+ the `dtype=` kwarg the reference's ctor lacks,
+                                                        SURVEY §3.4, and an `unpack()`)
+    QuantLinearHQQ     quant_linear_hqq.py:48-80
+    select_quant_linear / make_mixbits_quant_linear    utils/modelutils.py:44-68, :161-182
+
+`forward` goes through the C ABI only (include/b200q.h); there is no torch/CPU fallback: calling
+forward on CPU tensors raises, exactly like the reference's AWQ/Marlin layers.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import codec
+from ._lib import (LAYOUT_AWQ_GEMM, LAYOUT_GPTQ, LAYOUT_HQQ, LAYOUT_MARLIN, Layer, check, lib)
+
+_workspaces = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Zero-initialised scratch shared by all layers on (device, current stream); the engine leaves it
+    zeroed after every call (b200q.h), so it is allocated once and only ever grown."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+class _B200QuantLinearBase(nn.Module):
+    """Shared forward plumbing: builds the `b200q_layer` descriptor lazily and calls b200q_linear."""
+    _layout = None
+
+    def _init_common(self, bits, groupsize, infeatures, outfeatures, dtype):
+        self.dtype = torch.get_default_dtype() if dtype is None else dtype
+        self.infeatures = infeatures
+        self.outfeatures = outfeatures
+        self.bits = bits
+        self.groupsize = groupsize if groupsize != -1 else infeatures
+        self.maxq = 2 ** bits - 1
+        self.orig_fp_weight = None
+        self.act_order = None
+        self.zero_bias = 0            # the loader rewrites AutoGPTQ zeros, so kernels always see 0
+        self._desc = None
+        self._desc_key = None
+
+    # -- descriptor ---------------------------------------------------------------------------
+    def _tensors(self):
+        g_idx = self.g_idx if (self.act_order and isinstance(getattr(self, "g_idx", None), torch.Tensor)) else None
+        return self.qweight, getattr(self, "qzeros", None), self.scales, g_idx, self.bias
+
+    def _detect_act_order(self):
+        g = getattr(self, "g_idx", None)
+        if self._layout != LAYOUT_GPTQ or not isinstance(g, torch.Tensor):
+            return False
+        trivial = torch.arange(self.infeatures, device=g.device, dtype=torch.int64) // self.groupsize
+        return bool((g.to(torch.int64) != trivial).any().item())
+
+    def _descriptor(self):
+        if self.act_order is None:
+            self.act_order = self._detect_act_order()
+        qw, qz, sc, gi, bias = self._tensors()
+        key = tuple(0 if t is None else t.data_ptr() for t in (qw, qz, sc, gi, bias))
+        if self._desc is None or key != self._desc_key:
+            if not qw.is_cuda:
+                raise RuntimeError("qllm_b200 QuantLinear.forward needs CUDA buffers (no CPU fallback)")
+            if sc.dtype != torch.float16:
+                # scales arrive in the model dtype; the engine computes in fp16 (as the reference's
+                # kernels do after their bf16->fp16 cast: quant_linear_awq.py:29-36, ort_ops.cc:79-90)
+                self.scales = sc = sc.to(torch.float16)
+            if self._layout == LAYOUT_HQQ and qz.dtype != torch.float16:
+                self.qzeros = qz = qz.to(torch.float16)
+            if bias is not None and bias.dtype != torch.float16:
+                self._bias16 = bias.to(torch.float16)
+            else:
+                self._bias16 = bias
+            for t in (qw, qz, sc, gi, self._bias16):
+                if t is not None and not t.is_contiguous():
+                    raise ValueError("QuantLinear buffers must be contiguous")
+            d = Layer()
+            d.layout, d.bits, d.group_size = self._layout, self.bits, self.groupsize
+            d.K, d.N, d.zero_bias = self.infeatures, self.outfeatures, self.zero_bias
+            d.qweight = qw.data_ptr()
+            d.qzeros = qz.data_ptr() if qz is not None else None
+            d.scales = sc.data_ptr()
+            d.g_idx = gi.data_ptr() if gi is not None else None
+            d.bias = self._bias16.data_ptr() if self._bias16 is not None else None
+            self._desc = d
+            self._desc_key = tuple(0 if t is None else t.data_ptr() for t in self._tensors())
+        return self._desc
+
+    # -- forward ------------------------------------------------------------------------------
+    def forward(self, x):
+        desc = self._descriptor()
+        out_shape = x.shape[:-1] + (self.outfeatures,)
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.dtype != torch.float16:
+            x2 = x2.to(torch.float16)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        y = torch.empty((M, self.outfeatures), dtype=torch.float16, device=x.device)
+        if M > 0:
+            need = lib.b200q_workspace_bytes(ctypes.byref(desc), M)
+            ws = _workspace(x.device, need)
+            st = lib.b200q_linear(ctypes.byref(desc), x2.data_ptr(), M, x2.stride(0), y.data_ptr(), y.stride(0),
+                                  ws.data_ptr(), ws.numel(), torch.cuda.current_stream(x.device).cuda_stream)
+            check(st, type(self).__name__ + ".forward")
+        if y.dtype != x.dtype:
+            y = y.to(x.dtype)
+        return y.reshape(out_shape)
+
+    def dequantize(self) -> torch.Tensor:
+        """fp16 W[K, N] (= nn.Linear.weight.T) straight from the packed buffers (b200q_dequant)."""
+        desc = self._descriptor()
+        w = torch.empty((self.infeatures, self.outfeatures), dtype=torch.float16, device=self.qweight.device)
+        check(lib.b200q_dequant(ctypes.byref(desc), w.data_ptr(), torch.cuda.current_stream(w.device).cuda_stream))
+        return w
+
+    def unpack_int(self):
+        """(q int32 [K,N], z int32 [G,N] or None) via b200q_unpack -- the bit-exact gate."""
+        desc = self._descriptor()
+        dev = self.qweight.device
+        q = torch.empty((self.infeatures, self.outfeatures), dtype=torch.int32, device=dev)
+        G = self.infeatures // self.groupsize
+        z = None if self._layout == LAYOUT_HQQ else torch.empty((G, self.outfeatures), dtype=torch.int32, device=dev)
+        check(lib.b200q_unpack(ctypes.byref(desc), q.data_ptr(), None if z is None else z.data_ptr(),
+                               torch.cuda.current_stream(dev).cuda_stream))
+        return q, z
+
+    def _default_g_idx(self):
+        return (torch.arange(self.infeatures, dtype=torch.int32) // self.groupsize).to(torch.int32)
+
+    def extra_repr(self):
+        return "infeatures={}, outfeatures={}, bias={}, bits={}, groupsize={}, pack_mode={}".format(
+            self.infeatures, self.outfeatures, self.bias is not None, self.bits, self.groupsize, self.pack_mode)
+
+
+def _pack_device():
+    return "cuda" if torch.cuda.is_available() else "cpu"
+
+
+class QuantLinearGPTQ(_B200QuantLinearBase):
+    """pack_mode=GPTQ: qweight i32 [K*b/32, N], qzeros i32 [G, N*b/32], scales [G,N], g_idx i32 [K]."""
+    _layout = LAYOUT_GPTQ
+
+    def __init__(self, bits, groupsize, infeatures, outfeatures, bias, dtype=None):
+        super().__init__()
+        if bits not in [2, 3, 4, 5, 6, 7, 8]:
+            raise NotImplementedError("Only 2,3,4,5,6,7,8 bits are supported.")
+        self._init_common(bits, groupsize, infeatures, outfeatures, dtype)
+        self.pack_mode = "GPTQ"
+        G = math.ceil(infeatures / self.groupsize)
+        self.register_buffer("qweight", torch.zeros((infeatures // 32 * bits, outfeatures), dtype=torch.int32))
+        self.register_buffer("qzeros", torch.zeros((G, outfeatures // 32 * bits), dtype=torch.int32))
+        self.register_buffer("scales", torch.zeros((G, outfeatures), dtype=self.dtype))
+        self.register_buffer("g_idx", self._default_g_idx())
+        if bias:
+            self.register_buffer("bias", torch.zeros((outfeatures), dtype=self.dtype))
+        else:
+            self.bias = None
+
+    def handle_qzeros_for_autogptq(self):
+        """AutoGPTQ stores z-1; rewrite to z once at load (reference: quant_linear_gptq.py:119-134)."""
+        if self.qzeros.numel() == 0:
+            return
+        z = codec.gptq_unpack_qzeros(self.qzeros, self.bits, self.outfeatures, zero_bias=1)
+        self.qzeros = codec.gptq_pack_qzeros(z, self.bits).to(self.qzeros.device)
+        self._desc = None
+
+    def pack(self, linear, scales, zeros, g_idx=None):
+        """scales/zeros are the quantiser's [N, G] tensors (reference contract, compress_weight.py:204-210)."""
+        dev = _pack_device()
+        g = self._default_g_idx() if g_idx is None else g_idx.to(torch.int32).cpu()
+        s_t = scales.t().contiguous().to(dev).float()
+        z_t = zeros.t().contiguous().to(dev).float()
+        q = codec.quantize_weight(linear.weight.data.t().to(dev).float(), s_t, z_t, g.to(dev), self.maxq)
+        self.qweight = codec.pack_rows(q, self.bits).cpu()
+        self.qzeros = codec.gptq_pack_qzeros(z_t.round().to(torch.int32), self.bits).cpu()
+        self.scales = s_t.to(self.dtype).cpu()
+        self.g_idx = g
+        if linear.bias is not None:
+            self.bias = linear.bias.detach().clone().to(self.dtype).cpu()
+        self._desc, self.act_order = None, None
+
+    def unpack(self):
+        """-> (fp16 weight [N, K], scales [G, N], zeros int [G, N]) like CompressWeight.unpack."""
+        q = codec.unpack_rows(self.qweight, self.bits, self.infeatures)
+        z = codec.gptq_unpack_qzeros(self.qzeros, self.bits, self.outfeatures)
+        gi = self.g_idx.long().to(q.device)
+        s = self.scales.float()
+        w = ((q.float() - z.float()[gi]) * s[gi]).to(torch.float16)
+        return w.t().contiguous().cpu(), self.scales.cpu(), z.cpu()
+
+
+class QuantLinearHQQ(_B200QuantLinearBase):
+    """HQQ: qweight as GPTQ, qzeros/scales floating [G, N] (quant_linear_hqq.py:48-80)."""
+    _layout = LAYOUT_HQQ
+
+    def __init__(self, bits, groupsize, infeatures, outfeatures, bias, dtype=None):
+        super().__init__()
+        if bits not in [2, 3, 4, 5, 6, 7, 8]:
+            raise NotImplementedError("Only 2,3,4,5,6,7,8 bits are supported.")
+        self._init_common(bits, groupsize, infeatures, outfeatures, dtype)
+        self.pack_mode = "HQQ"
+        G = math.ceil(infeatures / self.groupsize)
+        self.g_idx = self._default_g_idx()      # plain attribute, not a buffer (quant_linear_hqq.py:60)
+        self.register_buffer("qweight", torch.zeros((infeatures // 32 * bits, outfeatures), dtype=torch.int32))
+        self.register_buffer("qzeros", torch.zeros((G, outfeatures), dtype=self.dtype))
+        self.register_buffer("scales", torch.zeros((G, outfeatures), dtype=self.dtype))
+        if bias:
+            self.register_buffer("bias", torch.zeros((outfeatures), dtype=self.dtype))
+        else:
+            self.bias = None
+
+    def pack(self, linear, scales, zeros, g_idx=None):
+        dev = _pack_device()
+        s_t = scales.t().contiguous().to(dev).float()
+        z_t = zeros.t().contiguous().to(dev).float()
+        q = codec.quantize_weight(linear.weight.data.t().to(dev).float(), s_t, z_t, self._default_g_idx().to(dev), self.maxq)
+        self.qweight = codec.pack_rows(q, self.bits).cpu()
+        self.qzeros = z_t.to(self.dtype).cpu()
+        self.scales = s_t.to(self.dtype).cpu()
+        if linear.bias is not None:
+            self.bias = linear.bias.detach().clone().to(self.dtype).cpu()
+        self._desc = None
+
+    def unpack(self):
+        q = codec.unpack_rows(self.qweight, self.bits, self.infeatures)
+        gi = self._default_g_idx().long().to(q.device)
+        w = ((q.float() - self.qzeros.float()[gi]) * self.scales.float()[gi]).to(torch.float16)
+        return w.t().contiguous().cpu(), self.scales.cpu(), self.qzeros.cpu()
+
+
+class WQLinear_GEMM(_B200QuantLinearBase):
+    """pack_mode=GEMM (AWQ): qweight i32 [K, N/8], qzeros i32 [G, N/8], nibble order 0,2,4,6,1,3,5,7."""
+    _layout = LAYOUT_AWQ_GEMM
+
+    def __init__(self, w_bit, group_size, in_features, out_features, bias, dtype=None):
+        super().__init__()
+        if w_bit not in [4]:
+            raise NotImplementedError("Only 4-bit are supported for now.")
+        self._init_common(w_bit, group_size, in_features, out_features, dtype)
+        self.w_bit = w_bit
+        self.group_size = self.groupsize
+        self.pack_mode = "GEMM"
+        assert in_features % self.group_size == 0
+        assert out_features % (32 // w_bit) == 0
+        self.g_idx = self._default_g_idx()
+        self.register_buffer("qweight", torch.zeros((in_features, out_features // 8), dtype=torch.int32))
+        self.register_buffer("qzeros", torch.zeros((in_features // self.group_size, out_features // 8), dtype=torch.int32))
+        self.register_buffer("scales", torch.zeros((in_features // self.group_size, out_features), dtype=self.dtype))
+        if bias:
+            self.register_buffer("bias", torch.zeros((out_features), dtype=self.dtype))
+        else:
+            self.bias = None
+
+    def pack(self, linear, scales, zeros, g_idx=None):
+        if g_idx is not None:
+            triv = self._default_g_idx()
+            assert torch.equal(g_idx.cpu().to(torch.int32), triv), "AWQ GEMM layout has no act-order"
+        dev = _pack_device()
+        s_t = scales.t().contiguous().to(dev).float()
+        z_t = zeros.t().contiguous().to(dev).float()
+        q = codec.quantize_weight(linear.weight.data.t().to(dev).float(), s_t, z_t, self._default_g_idx().to(dev), self.maxq)
+        self.qweight = codec.awq_pack_qweight(q).cpu()
+        self.qzeros = codec.awq_pack_qzeros(z_t.round().to(torch.int32)).cpu()
+        self.scales = s_t.to(self.dtype).cpu()
+        if linear.bias is not None:
+            self.bias = linear.bias.detach().clone().to(self.dtype).cpu()
+        self._desc = None
+
+    def unpack(self):
+        q = codec.awq_unpack_qweight(self.qweight)
+        z = codec.awq_unpack_qzeros(self.qzeros)
+        gi = self._default_g_idx().long().to(q.device)
+        w = ((q.float() - z.float()[gi]) * self.scales.float()[gi]).to(torch.float16)
+        return w.t().contiguous().cpu(), self.scales.cpu(), z.cpu()
+
+
+class QuantLinearMarlin(_B200QuantLinearBase):
+    """pack_mode=MARLIN: symmetric int4, qweight i32 [K/16, 2N], scales fp16 [G, N] permuted."""
+    _layout = LAYOUT_MARLIN
+
+    def __init__(self, bits, group_size, infeatures, outfeatures, bias, dtype=None):
+        super().__init__()
+        if bits not in [4]:
+            raise NotImplementedError("Only 4 bits are supported.")
+        if infeatures % 128 != 0 or outfeatures % 256 != 0:
+            raise ValueError("`infeatures` must be divisible by 128 and `outfeatures` by 256.")
+        if group_size not in [-1, 128] and group_size != infeatures:
+            raise ValueError("Only group_size -1 and 128 are supported.")
+        self._init_common(bits, group_size, infeatures, outfeatures, dtype)
+        self.group_size = self.groupsize
+        self.pack_mode = "MARLIN"
+        self.register_buffer("qweight", torch.zeros((infeatures // 16, outfeatures * 16 // 8), dtype=torch.int32))
+        self.register_buffer("scales", torch.zeros((infeatures // self.group_size, outfeatures), dtype=torch.float16))
+        # kept for state-dict / attribute compatibility; the engine uses its own shared scratch
+        self.register_buffer("workspace", torch.zeros(outfeatures // 128 * 16, dtype=torch.int32), persistent=False)
+        self.g_idx = None
+        self.qzeros = None
+        if bias:
+            self.register_buffer("bias", torch.zeros((outfeatures), dtype=torch.float16))
+        else:
+            self.bias = None
+
+    def pack(self, linear, scales, zeros, g_idx=None):
+        assert zeros is None or torch.all(zeros == 8), "only symmetric quantisation is supported (z == 8)"
+        dev = _pack_device()
+        s_t = scales.t().contiguous().to(dev).to(torch.float16)                 # [G, N]
+        gi = self._default_g_idx().long().to(dev)
+        w = linear.weight.data.t().to(dev).to(torch.float16)
+        q = torch.clamp(torch.round(w / s_t[gi]).to(torch.int32) + 8, 0, 15)    # fp16 division as the reference
+        qw, sp = codec.marlin_pack(q, s_t, self.group_size)
+        self.qweight = qw.cpu()
+        self.scales = sp.cpu()
+        if linear.bias is not None:
+            self.bias = linear.bias.detach().clone().to(torch.float16).cpu()
+        self._desc = None
+
+    def unpack(self):
+        """The reference raises NotImplementedError here (quant_linear_marlin.py:139-140)."""
+        q, s = codec.marlin_unpack(self.qweight, self.scales, self.group_size, self.infeatures)
+        gi = self._default_g_idx().long().to(q.device)
+        w = ((q.float() - 8.0) * s.float()[gi]).to(torch.float16)
+        return w.t().contiguous().cpu(), s.cpu(), torch.full_like(s, 8, dtype=torch.int32).cpu()
+
+
+def select_quant_linear(pack_mode: str, wbits: int, quant_method: str):
+    """Same decision table as the reference (utils/modelutils.py:44-68), minus the back-ends that are
+    out of scope (VPTQ, ORT); AUTO prefers the AWQ layout for 4-bit as the reference does on sm>=75."""
+    pack_mode = pack_mode.upper()
+    quant_method = quant_method.lower()
+    if quant_method == "vptq" or pack_mode == "ORT":
+        raise NotImplementedError(f"pack_mode={pack_mode}/quant_method={quant_method} is outside the b200q hot path")
+    if quant_method == "hqq":
+        return QuantLinearHQQ
+    if pack_mode == "MARLIN":
+        return QuantLinearMarlin
+    if pack_mode == "GEMM" or (pack_mode == "AUTO" and wbits == 4):
+        return WQLinear_GEMM
+    return QuantLinearGPTQ
+
+
+def _set_op_by_name(layer, name, new_module):
+    levels = name.split(".")
+    mod = layer
+    for lv in levels[:-1]:
+        mod = mod[int(lv)] if lv.isdigit() else getattr(mod, lv)
+    setattr(mod, levels[-1], new_module)
+
+
+def make_mixbits_quant_linear(module, replaced_names, quant_info: dict, name="", target_layer=None):
+    """Swap the named nn.Linear modules for `target_layer` instances (utils/modelutils.py:161-182);
+    per-layer (wbits, groupsize) when `quant_info` is keyed by layer name."""
+    dtype = next(iter(module.parameters())).dtype
+    for module_name, sub in list(module.named_modules()):
+        if module_name not in replaced_names:
+            continue
+        if "groupsize" in quant_info and "wbits" in quant_info:
+            bits, groupsize = quant_info["wbits"], quant_info["groupsize"]
+        else:
+            bits, groupsize = quant_info[module_name]["wbits"], quant_info[module_name]["groupsize"]
+        new = target_layer(bits, groupsize, sub.in_features, sub.out_features, sub.bias is not None, dtype=dtype)
+        new.bias = sub.bias.data if sub.bias is not None else None
+        _set_op_by_name(module, module_name, new)

@@ -1,0 +1,171 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on seeded inputs.
+
+Bars: integer unpack bit-exact; dequantised fp16 weights bit-exact vs the oracle's "engine"
+rounding fp16((q-z)*s); matmul outputs within 1e-3 of max|y| of the float64 oracle (the
+tolerance BASELINE.json's north_star states)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import qlinear_oracle as O
+from tests.util import layer_from_dict, oracle_forward, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+UNPACK_CASES = [("GPTQ", b, 32, 128, 64) for b in range(2, 9)] + [
+    ("GPTQ", 4, 128, 256, 96), ("HQQ", 4, 64, 128, 64), ("HQQ", 3, 32, 64, 32), ("GEMM", 4, 64, 128, 128),
+    ("MARLIN", 4, 128, 256, 256), ("MARLIN", 4, -1, 128, 256)]
+
+
+@pytest.mark.parametrize("layout,bits,gs,K,N", UNPACK_CASES)
+def test_unpack_bit_exact(layout, bits, gs, K, N):
+    L = O.make_layer(layout, bits, gs, K, N, seed=K + N + bits, act_order=(layout == "GPTQ" and bits == 4))
+    layer = layer_from_dict(L)
+    q, z = layer.unpack_int()
+    assert np.array_equal(q.cpu().numpy(), L["q"])
+    if z is not None:
+        assert np.array_equal(z.cpu().numpy(), np.asarray(L["z"]).astype(np.int32))
+    W = layer.dequantize().cpu().numpy()
+    ref = O.dequant(L["q"], L["z"], L["s"], L["g_idx"], "engine")
+    assert np.array_equal(W.view(np.uint16), ref.view(np.uint16))
+
+
+def test_unpack_autogptq_zero_bias():
+    L = O.make_layer("GPTQ", 4, 64, 128, 64, seed=5)
+    L2 = dict(L)
+    L2["qzeros"] = O.gptq_pack_qzeros(L["z"], 4, zero_bias=1)      # AutoGPTQ stores z-1
+    layer = layer_from_dict(L2)
+    layer.zero_bias = 1
+    _, z = layer.unpack_int()
+    assert np.array_equal(z.cpu().numpy(), L["z"])
+    layer2 = layer_from_dict(L2)
+    layer2.handle_qzeros_for_autogptq()                              # loader-style rewrite
+    assert np.array_equal(layer2.qzeros.cpu().numpy(), L["qzeros"])
+
+
+# (layout, bits, group, K, N): shapes chosen to hit partial tiles, several k-splits, several groups
+GEMV_CASES = [
+    ("GPTQ", 4, 128, 1024, 512), ("GPTQ", 4, 32, 512, 96), ("GPTQ", 4, -1, 512, 64), ("GPTQ", 4, 64, 2048, 160),
+    ("GPTQ", 2, 64, 1024, 128), ("GPTQ", 2, 16, 512, 64), ("GPTQ", 8, 128, 512, 128), ("GPTQ", 8, 32, 256, 96),
+    ("HQQ", 4, 64, 1024, 256), ("HQQ", 2, 64, 512, 64), ("HQQ", 8, 128, 512, 64),
+    ("GEMM", 4, 128, 1024, 1024), ("GEMM", 4, 32, 512, 576), ("GEMM", 4, 64, 2048, 64),
+    ("MARLIN", 4, 128, 1024, 512), ("MARLIN", 4, -1, 512, 256), ("MARLIN", 4, 128, 2048, 768),
+]
+
+
+@pytest.mark.parametrize("layout,bits,gs,K,N", GEMV_CASES)
+@pytest.mark.parametrize("M", [1, 3, 8])
+def test_decode_kernel_vs_oracle(layout, bits, gs, K, N, M):
+    import qllm_b200
+    L = O.make_layer(layout, bits, gs, K, N, seed=K * 7 + N + M, bias=(M == 3),
+                     float_zeros=(layout == "HQQ" and bits == 4))
+    layer = layer_from_dict(L)
+    x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+    y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+    ref = oracle_forward(L, x)
+    assert rel_err(y, ref) < TOL
+    # these shapes must take the mma decode kernel, not the generic fallback
+    import ctypes
+    assert qllm_b200.lib.b200q_select_kernel(ctypes.byref(layer._descriptor()), M) == 1
+
+
+GENERIC_CASES = [("GPTQ", 3, 32, 256, 64, False), ("GPTQ", 5, 64, 128, 64, False), ("GPTQ", 6, 32, 128, 32, False),
+                 ("GPTQ", 7, 32, 128, 32, False), ("GPTQ", 4, 32, 256, 64, True), ("GPTQ", 3, 32, 128, 32, True),
+                 ("HQQ", 3, 64, 256, 64, False), ("GPTQ", 8, 64, 128, 64, True)]
+
+
+@pytest.mark.parametrize("layout,bits,gs,K,N,act", GENERIC_CASES)
+@pytest.mark.parametrize("M", [1, 7, 16, 40])
+def test_generic_kernel_vs_oracle(layout, bits, gs, K, N, act, M):
+    L = O.make_layer(layout, bits, gs, K, N, seed=K + N + M + bits, act_order=act, bias=True)
+    layer = layer_from_dict(L)
+    x = np.random.default_rng(M + 1).standard_normal((M, K)).astype(np.float16)
+    y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+    assert rel_err(y, oracle_forward(L, x)) < TOL
+
+
+def test_workspace_left_zeroed_and_reusable():
+    from qllm_b200 import q_layers
+    L = O.make_layer("GEMM", 4, 128, 2048, 512, seed=1)
+    layer = layer_from_dict(L)
+    x = torch.randn(2, 2048, dtype=torch.float16, device="cuda")
+    y1 = layer(x)
+    y2 = layer(x)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)                       # deterministic split-K reduction
+    for ws in q_layers._workspaces.values():
+        assert int(ws[:4096].count_nonzero()) == 0   # arrival counters are reset by the last CTA
+
+
+def test_strided_and_batched_inputs():
+    L = O.make_layer("GPTQ", 4, 128, 512, 256, seed=2)
+    layer = layer_from_dict(L)
+    xb = torch.randn(2, 3, 1024, dtype=torch.float16, device="cuda")
+    x = xb[..., :512]                                  # row stride 1024, not contiguous
+    y = layer(x)
+    assert y.shape == (2, 3, 256)
+    ref = oracle_forward(L, x.reshape(-1, 512).cpu().numpy())
+    assert rel_err(y.reshape(-1, 256).float().cpu().numpy(), ref) < TOL
+    xbf = x.to(torch.bfloat16)                         # bf16 activations: cast to fp16 and back
+    ybf = layer(xbf)
+    assert ybf.dtype == torch.bfloat16
+
+
+def test_error_codes():
+    import ctypes
+    import qllm_b200
+    from qllm_b200._lib import Layer
+    lib = qllm_b200.lib
+    d = Layer()
+    assert lib.b200q_workspace_bytes(ctypes.byref(d), 1) == 0
+    L = O.make_layer("GEMM", 4, 128, 256, 64, seed=3)
+    layer = layer_from_dict(L)
+    desc = layer._descriptor()
+    x = torch.zeros(1, 256, dtype=torch.float16, device="cuda")
+    y = torch.zeros(1, 64, dtype=torch.float16, device="cuda")
+    st = lib.b200q_linear(ctypes.byref(desc), x.data_ptr(), 1, 256, y.data_ptr(), 64, None, 0, None)
+    assert st == -5 and b"workspace" in lib.b200q_strerror(st)
+    st = lib.b200q_linear(ctypes.byref(desc), None, 1, 256, y.data_ptr(), 64, None, 0, None)
+    assert st == -1
+    with pytest.raises(RuntimeError):
+        layer.cpu()(torch.zeros(1, 256, dtype=torch.float16))
+
+
+@pytest.mark.parametrize("layout,K,N", [("GEMM", 4096, 4096), ("GPTQ", 4096, 11008), ("GPTQ", 11008, 4096),
+                                         ("MARLIN", 4096, 4096)])
+def test_full_size_properties(layout, K, N):
+    """BASELINE sizes, where the numpy oracle is too slow: size-independent properties.
+    (1) one-hot activations read back single rows of W bit-exactly (unpack at full size);
+    (2) linearity: f(a*x1 + x2) == a*f(x1) + f(x2) within fp16 rounding;
+    (3) agreement with an fp32 torch matmul over the engine's own dequantised weights."""
+    gs = 128
+    rng = np.random.default_rng(K + N)
+    L = dict(layout=layout, bits=4, group_size=gs, K=K, N=N, bias=None, g_idx=O.default_g_idx(K, gs))
+    if layout == "MARLIN":
+        L["qweight"] = rng.integers(-2**31, 2**31, size=(K // 16, 2 * N), dtype=np.int64).astype(np.int32)
+        L["qzeros"] = None
+    elif layout == "GEMM":
+        L["qweight"] = rng.integers(-2**31, 2**31, size=(K, N // 8), dtype=np.int64).astype(np.int32)
+        L["qzeros"] = rng.integers(-2**31, 2**31, size=(K // gs, N // 8), dtype=np.int64).astype(np.int32)
+    else:
+        L["qweight"] = rng.integers(-2**31, 2**31, size=(K // 8, N), dtype=np.int64).astype(np.int32)
+        L["qzeros"] = rng.integers(-2**31, 2**31, size=(K // gs, N // 8), dtype=np.int64).astype(np.int32)
+    L["scales"] = rng.uniform(0.002, 0.012, size=(K // gs, N)).astype(np.float16)
+    layer = layer_from_dict(L)
+    W = layer.dequantize()
+    rows = [0, 1, 7, gs, K // 2 + 3, K - 1]
+    x = torch.zeros(len(rows), K, dtype=torch.float16, device="cuda")
+    for i, r in enumerate(rows):
+        x[i, r] = 1.0
+    y = layer(x)
+    assert torch.equal(y, W[rows])
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x1 = torch.randn(1, K, dtype=torch.float16, device="cuda", generator=g)
+    x2 = torch.randn(1, K, dtype=torch.float16, device="cuda", generator=g)
+    f1, f2, f3 = layer(x1).float(), layer(x2).float(), layer(2 * x1 + x2).float()
+    assert (f3 - (2 * f1 + f2)).abs().max() <= 4e-3 * f3.abs().max()
+    xm = torch.randn(8, K, dtype=torch.float16, device="cuda", generator=g)
+    ref = xm.double() @ W.double()
+    assert ((layer(xm).double() - ref).abs().max() / ref.abs().max()).item() < TOL
+    assert ((layer(xm[:1]).double() - ref[:1]).abs().max() / ref.abs().max()).item() < TOL
