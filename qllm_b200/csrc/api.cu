@@ -1,6 +1,7 @@
 // extern "C" surface of libb200q.so: argument validation, kernel selection, status codes.
 // No torch, no allocation, no synchronisation (include/b200q.h states the contract).
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -53,13 +54,32 @@ static constexpr int kGenericMaxM = 16;
 
 enum { KERNEL_GEMV_MMA = 1, KERNEL_GEMM_TC = 2, KERNEL_GENERIC = 3 };
 
+// B200Q_GEMV=v1 selects the bulk-copy/mbarrier decode kernel (gemv_mma.cu) instead of the default
+// register-prefetch kernel (gemv_rp.cu); read once. Tuning/diagnostic switch only.
+static int gemv_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200Q_GEMV");
+    v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+    const char* kb = getenv("B200Q_SLICE_KB");
+    gemv_rp_set_smem(e && e[0] == 'v' && e[1] == '3', kb ? atoi(kb) : 0);
+    const char* c = getenv("B200Q_MAX_CLUSTER");
+    if (c) gemv_rp_set_max_cluster(atoi(c));
+  }
+  return v;
+}
+static bool decode_supported(const LayerView& V, int M, const __half* x, int64_t ldx) {
+  if (gemv_variant() == 2 && gemv_rp_supported(V, M, x, ldx)) return true;
+  return gemv_mma_supported(V, M, x, ldx);
+}
+
 static int select(const LayerView& V, int64_t M, const __half* x, int64_t ldx, int force) {
   if (force == KERNEL_GEMM_TC) return gemm_tc_supported(V, M, x, ldx) ? KERNEL_GEMM_TC : B200Q_ERR_UNSUPPORTED;
   if (force == KERNEL_GEMV_MMA) {
     if (M > kGenericMaxM) return B200Q_ERR_SHAPE;
-    return (M <= kGemvMaxM && gemv_mma_supported(V, (int)M, x, ldx)) ? KERNEL_GEMV_MMA : KERNEL_GENERIC;
+    return (M <= kGemvMaxM && decode_supported(V, (int)M, x, ldx)) ? KERNEL_GEMV_MMA : KERNEL_GENERIC;
   }
-  if (M <= kGemvMaxM && gemv_mma_supported(V, (int)M, x, ldx)) return KERNEL_GEMV_MMA;
+  if (M <= kGemvMaxM && decode_supported(V, (int)M, x, ldx)) return KERNEL_GEMV_MMA;
   if (M > kGemvMaxM && gemm_tc_supported(V, M, x, ldx)) return KERNEL_GEMM_TC;
   if (M <= kGemvMaxM) return KERNEL_GENERIC;
   if (gemm_tc_supported(V, M, x, ldx)) return KERNEL_GEMM_TC;
@@ -91,7 +111,10 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   LinearArgs a;
   a.L = V; a.x = (const __half*)x; a.ldx = ldx; a.M = (int)M; a.y = (__half*)y; a.ldy = ldy; a.n_offset = n_offset;
   a.workspace = ws; a.workspace_bytes = ws_bytes; a.stream = (cudaStream_t)stream;
-  if (kern == KERNEL_GEMV_MMA) return cuda_status(launch_gemv_mma(a, peers));
+  if (kern == KERNEL_GEMV_MMA) {
+    if (gemv_variant() == 2 && gemv_rp_supported(V, (int)M, a.x, ldx)) return cuda_status(launch_gemv_rp(a, peers));
+    return cuda_status(launch_gemv_mma(a, peers));
+  }
   if (kern == KERNEL_GEMM_TC) return cuda_status(launch_gemm_tc(a, peers));
   // generic: slabs of <= 16 activation rows
   for (int64_t m0 = 0; m0 < M; m0 += kGenericMaxM) {

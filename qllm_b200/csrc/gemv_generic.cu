@@ -20,7 +20,7 @@ static int generic_ksplit(const LayerView& L) {
 }
 
 size_t gemv_generic_workspace(const LayerView& L, int M) {
-  return (size_t)generic_ksplit(L) * (size_t)M * (size_t)L.N * sizeof(float);
+  return kCounterBytes + (size_t)generic_ksplit(L) * (size_t)M * (size_t)L.N * sizeof(float);
 }
 
 template <int MT>
@@ -72,7 +72,7 @@ cudaError_t launch_gemv_generic(const LinearArgs& a, const PeerOut* peers) {
   int kps = (L.K + ks - 1) / ks;
   kps = (kps + 31) / 32 * 32;
   dim3 grid((L.N + kGenThreads - 1) / kGenThreads, (L.K + kps - 1) / kps);
-  float* partial = (float*)a.workspace;
+  float* partial = (float*)((char*)a.workspace + kCounterBytes);   // never touch the counter region
   PeerOut out;
   if (peers) out = *peers; else { out.n = 1; out.y[0] = a.y; }
 #define B200Q_GEN(MT) gemv_generic_kernel<MT><<<grid, kGenThreads, 0, a.stream>>>(L, a.x, a.ldx, a.M, kps, partial)

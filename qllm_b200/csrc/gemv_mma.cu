@@ -622,7 +622,6 @@ bool gemv_mma_supported(const LayerView& L, int M, const __half* x, int64_t ldx)
   return true;
 }
 
-static constexpr size_t kCounterBytes = 4096;
 
 size_t gemv_mma_workspace(const LayerView& L, int M) {
   Plan pl;

@@ -43,6 +43,15 @@ bool gemv_mma_supported(const LayerView& L, int M, const __half* x, int64_t ldx)
 size_t gemv_mma_workspace(const LayerView& L, int M);
 cudaError_t launch_gemv_mma(const LinearArgs& a, const PeerOut* peers);
 
+// gemv_rp.cu : latency-optimised decode path (register prefetch + cluster split-K), M <= 8
+bool gemv_rp_supported(const LayerView& L, int M, const __half* x, int64_t ldx);
+cudaError_t launch_gemv_rp(const LinearArgs& a, const PeerOut* peers);
+void gemv_rp_set_max_cluster(int c);
+void gemv_rp_set_smem(bool on, int slice_kb);
+
+// first kCounterBytes of every workspace are arrival counters that must stay zero between calls
+static constexpr size_t kCounterBytes = 4096;
+
 // gemm_tcgen05.cu : tensor-core GEMM (TMA + tcgen05 + TMEM), any M
 bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t ldx);
 size_t gemm_tc_workspace(const LayerView& L, int64_t M);
