@@ -1,8 +1,383 @@
-// placeholder until the tcgen05 GEMM lands (same interface)
+// Prefill / batched path: fused dequant + tcgen05 tensor-core GEMM for sm_100a.
+//
+// Orientation: D[n, tok] = W^T[n, k] . X^T[k, tok]  (one CTA = 128 output columns x TT tokens)
+//   * the dequantised weights are the UMMA *A* operand and live in TENSOR MEMORY: the 128 dequant
+//     threads map 1:1 to the 128 TMEM lanes (= output columns n).  A thread reads its column's packed
+//     words from shared memory, unpacks 64 k-values in registers (lop3 + exact fp16 (q-z), one
+//     rounding in *s), and writes them with one tcgen05.st.32x32b.x32 -- no shared-memory round trip
+//     for the fp16 weights, which halves shared-memory traffic vs. staging them for an SS-mode MMA;
+//   * X^T is the B operand, K-major, loaded by TMA with 128-byte swizzle straight from the caller's
+//     [M, K] activation matrix (rows beyond M are zero-filled by TMA);
+//   * accumulators (fp32) stay in TMEM; the epilogue reads them with tcgen05.ld, adds bias, converts
+//     to fp16 and stores y[tok, n] (coalesced along n across the warp).
+// Warp roles (256 threads): w0 TMA producer | w1 MMA issuer (one thread) | w2 TMEM allocator |
+// w4-7 dequant + epilogue.  mbarrier rings: input stages (TMA -> dequant/MMA), A stages in TMEM
+// (dequant -> MMA), accumulator-ready.
+//
+// Replaces: ort_ops.dequant + cuBLAS (quant_linear_gptq.py:81-85), gemm_forward_cuda
+// (gemm_cuda_gen.cu:1102-1161), marlin mul (marlin_cuda.cpp:29-74) at M > 8.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "kernels.h"
+
 namespace b200q {
-bool gemm_tc_supported(const LayerView&, int64_t, const __half*, int64_t) { return false; }
+
+static constexpr int kTcThreads = 256;
+static constexpr int kNS = 4;         // input stages (X tile + packed W tile)
+static constexpr int kNA = 4;         // A stages in TMEM (64 k = 32 columns each)
+static constexpr int kBK = 64;        // k per stage
+static constexpr int kBN = 128;       // output columns per CTA (= UMMA M)
+static constexpr int kTmemCols = 256;
+static constexpr int kAccCol = 0, kACol = 128;
+static constexpr uint32_t kSpinLimit = 4u << 20;
+
+static constexpr uint32_t MAGIC = 0x64006400u, LO4 = 0x000f000fu, HI4 = 0x00f000f0u, H_1_16 = 0x2c002c00u;
+
+struct TcParams {
+  LayerView L;
+  int M;
+  PeerOut out;
+  int64_t ldy, n_offset;
+  int kblocks;
+  int off_x, off_w, off_sc, off_zq, off_bar;
+  int* err;
+};
+
+// ---- small PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, int* err, int code) {
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++n > kSpinLimit) {
+      if (err) atomicExch(err, code);
+      return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (version 1)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GPTQ / HQQ 4-bit producer of A: thread n owns column n; word r of a stage holds k = 8r..8r+7.
+// ------------------------------------------------------------------------------------------------
+template <int TT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const TcParams p) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-byte alignment
+  char* xst = smem + p.off_x;                                      // kNS x [TT][64] fp16, SW128
+  uint32_t* wst = reinterpret_cast<uint32_t*>(smem + p.off_w);     // kNS x [8][128] words
+  __half* sc = reinterpret_cast<__half*>(smem + p.off_sc);         // [G][128]
+  char* zq = smem + p.off_zq;                                      // [G][128] nibbles (64 B) | [G][128] fp16
+  uint64_t* full_in = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* empty_in = full_in + kNS;
+  uint64_t* a_full = empty_in + kNS;
+  uint64_t* a_empty = a_full + kNA;
+  uint64_t* acc_full = a_empty + kNA;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * kBN;
+  const int tok0 = blockIdx.y * TT;
+  const bool fz = (p.L.layout == B200Q_LAYOUT_HQQ);
+  const int zq_row = fz ? kBN * 2 : kBN / 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < kNS; ++s) { mbar_init(&full_in[s], 1); mbar_init(&empty_in[s], 5); }
+    for (int s = 0; s < kNA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // group tables for this CTA's 128 columns (all groups)
+  for (int idx = tid; idx < p.L.G * kBN; idx += kTcThreads) {
+    const int g = idx / kBN, n = idx % kBN;
+    sc[idx] = (n0 + n < p.L.N) ? __ldg(p.L.s + (size_t)g * p.L.N + n0 + n) : __float2half(0.f);
+  }
+  if (fz) {
+    for (int idx = tid; idx < p.L.G * kBN; idx += kTcThreads) {
+      const int g = idx / kBN, n = idx % kBN;
+      reinterpret_cast<__half*>(zq)[idx] =
+          (n0 + n < p.L.N) ? __ldg(reinterpret_cast<const __half*>(p.L.qz) + (size_t)g * p.L.N + n0 + n) : __float2half(0.f);
+    }
+  } else {
+    const size_t zrow = (size_t)p.L.N >> 3;
+    for (int idx = tid; idx < p.L.G * (kBN / 8); idx += kTcThreads) {
+      const int g = idx / (kBN / 8), wv = idx % (kBN / 8);
+      reinterpret_cast<uint32_t*>(zq)[idx] =
+          (n0 + 8 * wv < p.L.N) ? __ldg(reinterpret_cast<const uint32_t*>(p.L.qz) + (size_t)g * zrow + (n0 >> 3) + wv) : 0u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  constexpr uint32_t X_BYTES = TT * kBK * 2, W_BYTES = 8 * kBN * 4;
+  bool ok = true;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < p.kblocks && ok; ++kb) {
+        const int s = kb % kNS;
+        ok = mbar_wait_bounded(&empty_in[s], ((kb / kNS) + 1) & 1, p.err, 1);
+        mbar_expect_tx(&full_in[s], X_BYTES + W_BYTES);
+        tma_load_2d(xst + (size_t)s * X_BYTES, &xmap, &full_in[s], kb * kBK, tok0);
+        tma_load_2d(wst + (size_t)s * (W_BYTES / 4), &wmap, &full_in[s], n0, kb * 8);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=f16, both K-major, N=TT, M=128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(kBN >> 4) << 24);
+      for (int kb = 0; kb < p.kblocks && ok; ++kb) {
+        const int s = kb % kNS, sa = kb % kNA;
+        ok = mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 2);
+        ok = ok && mbar_wait_bounded(&a_full[sa], (kb / kNA) & 1, p.err, 3);
+        tc_fence_after();
+        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(xst + (size_t)s * X_BYTES));
+#pragma unroll
+        for (int j = 0; j < kBK / 16; ++j)
+          tc_mma_ts(tmem + kAccCol, tmem + kACol + sa * 32 + j * 8, bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
+        tc_commit(&empty_in[s]);
+        tc_commit(&a_empty[sa]);
+      }
+      tc_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;                     // TMEM lane quadrant of this warp
+    const int n = q * 32 + lane;                // column within the CTA tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int gcur = -1;
+    uint32_t c_lo = 0, c_hi = 0, s2 = 0, z2 = 0;
+    for (int kb = 0; kb < p.kblocks && ok; ++kb) {
+      const int s = kb % kNS, sa = kb % kNA;
+      ok = __all_sync(0xffffffffu, mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 4));
+      uint32_t w[8];
+      const uint32_t* ws = wst + (size_t)s * (W_BYTES / 4) + n;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) w[r] = ws[r * kBN];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_in[s]);
+      uint32_t a[32];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int gi = (kb * kBK + 8 * r) / p.L.group;
+        if (gi != gcur) {
+          gcur = gi;
+          s2 = dup_half(sc[gi * kBN + n]);
+          if (fz) {
+            z2 = dup_half(reinterpret_cast<const __half*>(zq)[gi * kBN + n]);
+            c_lo = MAGIC; c_hi = 0xD400D400u;
+          } else {
+            const uint32_t zw = reinterpret_cast<const uint32_t*>(zq)[gi * (kBN / 8) + (n >> 3)];
+            const uint32_t z = (((zw >> (4 * (n & 7))) & 0xFu) + (uint32_t)p.L.zero_bias) & 0xFu;
+            c_lo = (0x6400u | z) * 0x00010001u;
+            c_hi = (0xD400u + (z << 4)) * 0x00010001u;
+          }
+        }
+        const uint32_t lo = w[r], hi = w[r] >> 8;
+        uint32_t p0 = hsub2_u(and_or(lo, LO4, MAGIC), c_lo);            // (k0,k4) - z
+        uint32_t p1 = hfma2_u(and_or(lo, HI4, MAGIC), H_1_16, c_hi);    // (k1,k5)
+        uint32_t p2 = hsub2_u(and_or(hi, LO4, MAGIC), c_lo);            // (k2,k6)
+        uint32_t p3 = hfma2_u(and_or(hi, HI4, MAGIC), H_1_16, c_hi);    // (k3,k7)
+        if (fz) { p0 = hsub2_u(p0, z2); p1 = hsub2_u(p1, z2); p2 = hsub2_u(p2, z2); p3 = hsub2_u(p3, z2); }
+        p0 = hmul2_u(p0, s2); p1 = hmul2_u(p1, s2); p2 = hmul2_u(p2, s2); p3 = hmul2_u(p3, s2);
+        a[4 * r + 0] = prmt(p0, p1, 0x5410);    // (k0,k1)
+        a[4 * r + 1] = prmt(p2, p3, 0x5410);    // (k2,k3)
+        a[4 * r + 2] = prmt(p0, p1, 0x7632);    // (k4,k5)
+        a[4 * r + 3] = prmt(p2, p3, 0x7632);    // (k6,k7)
+      }
+      ok = __all_sync(0xffffffffu, ok && mbar_wait_bounded(&a_empty[sa], ((kb / kNA) + 1) & 1, p.err, 5));
+      tc_st32(tmem + lane_addr + kACol + sa * 32, a);
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[sa]);
+    }
+    // ---- epilogue ----
+    ok = __all_sync(0xffffffffu, mbar_wait_bounded(acc_full, 0, p.err, 6) && ok);
+    tc_fence_after();
+    const bool ncol_ok = (n0 + n) < p.L.N;
+    const float bias = (p.L.bias && ncol_ok) ? __half2float(__ldg(p.L.bias + n0 + n)) : 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < TT; c0 += 32) {
+      uint32_t v[32];
+      tc_ld32(tmem + lane_addr + kAccCol + c0, v);
+      tc_wait_ld();
+      if (ncol_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int tok = tok0 + c0 + i;
+          if (tok < p.M) {
+            const __half h = __float2half_rn(__uint_as_float(v[i]) + bias);
+            for (int qd = 0; qd < p.out.n; ++qd) p.out.y[qd][(size_t)tok * p.ldy + p.n_offset + n0 + n] = h;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int* g_err_flag = nullptr;      // device int, lazily allocated (diagnostic only)
+int gemm_tc_last_error() {
+  int v = 0;
+  if (g_err_flag) cudaMemcpy(&v, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  return v;
+}
+
+static int pick_tt(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : 128); }
+
+bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t ldx) {
+  if (!(L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) || L.bits != 4 || L.g_idx) return false;
+  if (L.K % kBK != 0 || L.N % 8 != 0 || L.group % 8 != 0 || L.K % L.group != 0) return false;
+  if (((uintptr_t)x & 15) != 0 || (ldx % 8) != 0 || ((uintptr_t)L.qw & 15) != 0 || (L.N % 4) != 0) return false;
+  const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN / 2;
+  const size_t tables = (size_t)L.G * (kBN * 2 + zq_row);
+  if (tables > 60 * 1024) return false;
+  return get_encode() != nullptr && M >= 1;
+}
+
 size_t gemm_tc_workspace(const LayerView&, int64_t) { return 0; }
-cudaError_t launch_gemm_tc(const LinearArgs&, const PeerOut*) { return cudaErrorNotSupported; }
+
+template <int TT>
+static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
+  const LayerView& L = a.L;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return cudaErrorNotSupported;
+  CUtensorMap xmap, wmap;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)L.K, (cuuint64_t)a.M};
+    cuuint64_t strides[1] = {(cuuint64_t)a.ldx * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)TT};
+    cuuint32_t es[2] = {1, 1};
+    if (enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)a.x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)L.N, (cuuint64_t)(L.K / 8)};
+    cuuint64_t strides[1] = {(cuuint64_t)L.N * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kBN, 8};
+    cuuint32_t es[2] = {1, 1};
+    if (enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)L.qw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  if (!g_err_flag) {
+    if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return cudaErrorMemoryAllocation;
+    cudaMemset(g_err_flag, 0, sizeof(int));
+  }
+  TcParams p;
+  p.L = L; p.M = a.M;
+  if (peers) p.out = *peers; else { p.out.n = 1; p.out.y[0] = a.y; }
+  p.ldy = a.ldy; p.n_offset = a.n_offset;
+  p.kblocks = L.K / kBK;
+  p.err = g_err_flag;
+  const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN / 2;
+  int off = 0;
+  p.off_x = off; off += kNS * TT * kBK * 2;
+  p.off_w = off; off += kNS * 8 * kBN * 4;
+  p.off_sc = off; off += L.G * kBN * 2;
+  off = (off + 15) & ~15;
+  p.off_zq = off; off += L.G * zq_row;
+  off = (off + 15) & ~15;
+  p.off_bar = off; off += 256;
+  const int smem_bytes = off + 1024;   // slack for 1024-byte alignment of the dynamic window
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_gptq4_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  dim3 grid((L.N + kBN - 1) / kBN, (a.M + TT - 1) / TT);
+  count_launch();
+  gemm_tc_gptq4_kernel<TT><<<grid, kTcThreads, smem_bytes, a.stream>>>(xmap, wmap, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers) {
+  // M is chunked so that a.M fits int and grid.y <= 65535
+  switch (pick_tt(a.M)) {
+    case 32: return tc_launch<32>(a, peers);
+    case 64: return tc_launch<64>(a, peers);
+    default: return tc_launch<128>(a, peers);
+  }
+}
+
 }  // namespace b200q

@@ -169,3 +169,77 @@ def test_full_size_properties(layout, K, N):
     ref = xm.double() @ W.double()
     assert ((layer(xm).double() - ref).abs().max() / ref.abs().max()).item() < TOL
     assert ((layer(xm[:1]).double() - ref[:1]).abs().max() / ref.abs().max()).item() < TOL
+
+
+# ---- tcgen05 GEMM (M > 8, or forced) ---------------------------------------------------------
+GEMM_CASES = [("GPTQ", 4, 128, 512, 256), ("GPTQ", 4, 64, 1024, 384), ("GPTQ", 4, 32, 256, 128),
+              ("HQQ", 4, 64, 512, 128), ("GPTQ", 4, -1, 256, 128), ("GPTQ", 4, 128, 2048, 160)]
+
+
+def _dump(name, **arrs):
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.savez_compressed(os.path.join("gpurun_out", name), **arrs)
+
+
+@pytest.mark.parametrize("layout,bits,gs,K,N", GEMM_CASES)
+@pytest.mark.parametrize("M", [9, 33, 64, 100, 128, 257])
+def test_tcgen05_gemm_vs_oracle(layout, bits, gs, K, N, M):
+    import ctypes
+    import qllm_b200
+    L = O.make_layer(layout, bits, gs, K, N, seed=K + 3 * N + M, bias=(M % 2 == 1),
+                     float_zeros=(layout == "HQQ"))
+    layer = layer_from_dict(L)
+    assert qllm_b200.lib.b200q_select_kernel(ctypes.byref(layer._descriptor()), M) == 2
+    x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+    y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+    ref = oracle_forward(L, x)
+    err = rel_err(y, ref)
+    if not err < TOL:
+        _dump(f"gemm_fail_{layout}_{gs}_{K}_{N}_{M}.npz", y=y, ref=ref, x=x, q=L["q"], z=np.asarray(L["z"]), s=L["s"])
+    assert err < TOL
+
+
+def test_tcgen05_gemm_forced_small_m_and_identity():
+    """b200q_gemm at M < 8 (zero-filled token tile) and a one-hot X that reads W back bit-exactly:
+    pins the k order inside the TMEM A operand and the n order of the epilogue."""
+    import ctypes
+    import qllm_b200
+    from qllm_b200 import q_layers
+    K, N = 256, 256
+    L = O.make_layer("GPTQ", 4, 128, K, N, seed=77)
+    layer = layer_from_dict(L)
+    desc = layer._descriptor()
+    W = O.dequant(L["q"], L["z"], L["s"], L["g_idx"], "engine")
+    for M in (1, 5, K):
+        x = torch.zeros(M, K, dtype=torch.float16, device="cuda")
+        rows = list(range(M)) if M == K else [3, 77, 128, 200, 255][:M]
+        for i, r in enumerate(rows):
+            x[i, r] = 1.0
+        y = torch.empty(M, N, dtype=torch.float16, device="cuda")
+        ws = q_layers._workspace(x.device, 1 << 20)
+        st = qllm_b200.lib.b200q_gemm(ctypes.byref(desc), x.data_ptr(), M, K, y.data_ptr(), N, ws.data_ptr(), ws.numel(),
+                                      torch.cuda.current_stream().cuda_stream)
+        qllm_b200.check(st)
+        torch.cuda.synchronize()
+        got = y.cpu().numpy()
+        if not np.array_equal(got.view(np.uint16), W[rows].view(np.uint16)):
+            _dump(f"gemm_identity_fail_M{M}.npz", y=got, W=W, rows=np.array(rows))
+        assert np.array_equal(got.view(np.uint16), W[rows].view(np.uint16))
+
+
+@pytest.mark.parametrize("K,N", [(4096, 4096), (4096, 11008)])
+def test_tcgen05_gemm_full_size(K, N):
+    gs = 128
+    rng = np.random.default_rng(K + N)
+    L = dict(layout="GPTQ", bits=4, group_size=gs, K=K, N=N, bias=None, g_idx=O.default_g_idx(K, gs))
+    L["qweight"] = rng.integers(-2**31, 2**31, size=(K // 8, N), dtype=np.int64).astype(np.int32)
+    L["qzeros"] = rng.integers(-2**31, 2**31, size=(K // gs, N // 8), dtype=np.int64).astype(np.int32)
+    L["scales"] = rng.uniform(0.002, 0.012, size=(K // gs, N)).astype(np.float16)
+    layer = layer_from_dict(L)
+    W = layer.dequantize()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(512, K, dtype=torch.float16, device="cuda", generator=g)
+    y = layer(x)
+    ref = x.double() @ W.double()
+    assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < TOL
