@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- driver contract benchmark for the b200q QuantLinear hot path.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): one decode step
+(batch 1) of a random-init Llama-2-7B, int4 g128, AWQ pack_mode=GEMM -- the 224 QuantLinear calls of
+the 32 decoder blocks (q,k,v,o 4096->4096; gate,up 4096->11008; down 11008->4096), chained by real data
+dependencies, each call going through the C ABI (b200q_linear) exactly as QuantLinear.forward does.
+A "step" = one token through all 224 layers.  3.4 GB of distinct packed weights: far larger than L2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200q|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1: column-sharded)
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIDDEN, INTER, BLOCKS, GROUP, BITS = 4096, 11008, 32, 128, 4
+METRIC = "llama2_7b_int4_g128_quantlinear_decode_tokens_per_s"
+SHAPES = [("q", HIDDEN, HIDDEN), ("k", HIDDEN, HIDDEN), ("v", HIDDEN, HIDDEN), ("o", HIDDEN, HIDDEN),
+          ("gate", HIDDEN, INTER), ("up", HIDDEN, INTER), ("down", INTER, HIDDEN)]
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        p.update(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))))
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+def alg_bytes(K, N, M, layout="GEMM"):
+    G = K // GROUP
+    z = 0 if layout == "MARLIN" else G * N * BITS // 8
+    return K * N * BITS // 8 + G * N * 2 + z + M * K * 2 + M * N * 2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU implementation of the path (torch dequant + matmul,
+    restated in oracle/cpu_baseline.py because /root/reference does not travel), all host threads,
+    each step a bounded sample (one decoder block = 7 QuantLinears) extrapolated to 32 blocks."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import cpu_baseline as C
+    steps, warm = max(1, args.steps), max(1, args.warmup)
+    layers = C.make_block(HIDDEN, INTER, GROUP, BITS, torch.float16)
+    h = torch.randn(1, HIDDEN).to(torch.float16)
+
+    def block():
+        fw = lambda i, x: C.quant_linear_forward(x, layers[i][2], layers[i][3], layers[i][4], GROUP, BITS, layers[i][0])
+        q, k, v = fw(0, h), fw(1, h), fw(2, h)
+        o = fw(3, v)
+        gt, up = fw(4, o), fw(5, o)
+        return fw(6, gt)
+
+    for _ in range(warm):
+        block()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        block()
+    dt = (time.perf_counter() - t0) / steps
+    tok_s = 1.0 / (dt * BLOCKS)
+    cores = torch.get_num_threads()
+    sample = f"1 of {BLOCKS} decoder blocks (7 QuantLinears, M=1, fp16) per step, x{BLOCKS} extrapolated"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt * BLOCKS * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "Llama-2-7B int4 g128 QuantLinear decode, M=1 (reference torch-CPU dequant+matmul, GPTQ layout)",
+                   "layers": 7 * BLOCKS},
+        "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def shard_cols(N, world, rank, gran=32):
+    """Contiguous column shard [c0, c1) of width multiple of `gran` (equal when N % (world*gran) == 0)."""
+    tiles = N // gran
+    t0, t1 = tiles * rank // world, tiles * (rank + 1) // world
+    return t0 * gran, t1 * gran
+
+
+def build_model(dev, rank, world, layout="GEMM"):
+    import torch
+    import qllm_b200
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ri = lambda *s: torch.randint(-2 ** 31, 2 ** 31 - 1, s, dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+    blocks = []
+    for _ in range(BLOCKS):
+        layers = {}
+        for name, K, N in SHAPES:
+            c0, c1 = shard_cols(N, world, rank)
+            n = c1 - c0
+            G = K // GROUP
+            if layout == "GEMM":
+                l = qllm_b200.WQLinear_GEMM(BITS, GROUP, K, n, False, dtype=torch.float16)
+                l.qweight, l.qzeros = ri(K, n // 8), ri(G, n // 8)
+            else:
+                l = qllm_b200.QuantLinearGPTQ(BITS, GROUP, K, n, False, dtype=torch.float16)
+                l.qweight, l.qzeros = ri(K * BITS // 32, n), ri(G, n * BITS // 32)
+                l.g_idx = l.g_idx.to(dev)
+            l.scales = ((torch.rand(G, n, device=dev, generator=g) * 0.4 + 0.8) / (6.5 * K ** 0.5)).to(torch.float16)
+            l = l.to(dev)
+            l.col0, l.full_n = c0, N
+            layers[name] = l
+        blocks.append(layers)
+    return blocks
+
+
+class DecodeStep:
+    """The 224 chained QuantLinear calls of one token, issued through the C ABI."""
+
+    def __init__(self, blocks, dev, M, rank, world):
+        import torch
+        import qllm_b200
+        self.lib, self.blocks, self.M, self.world, self.rank = qllm_b200.lib, blocks, M, world, rank
+        f16 = dict(dtype=torch.float16, device=dev)
+        self.h = torch.zeros(M, HIDDEN, **f16)
+        self.bufs = {n: torch.zeros(M, N, **f16) for n, _, N in SHAPES}
+        self.part = {n: torch.zeros(M, max(shard_cols(N, world, r)[1] - shard_cols(N, world, r)[0] for r in range(world)), **f16)
+                     for n, _, N in SHAPES} if world > 1 else None
+        need = max(self.lib.b200q_workspace_bytes(ctypes.byref(l._descriptor()), M) for l in blocks[0].values())
+        self.ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+        self.torch = torch
+
+    def _call(self, layer, x, name, stream):
+        from qllm_b200 import check
+        desc = layer._descriptor()
+        if self.world == 1:
+            y = self.bufs[name]
+            check(self.lib.b200q_linear(ctypes.byref(desc), x.data_ptr(), self.M, x.stride(0), y.data_ptr(), y.stride(0),
+                                        self.ws.data_ptr(), self.ws.numel(), stream))
+            return y
+        # column shard -> local slice, then one all-gather of the output (equal shards)
+        import torch.distributed as dist
+        part = self.part[name]
+        check(self.lib.b200q_linear(ctypes.byref(desc), x.data_ptr(), self.M, x.stride(0), part.data_ptr(), part.stride(0),
+                                    self.ws.data_ptr(), self.ws.numel(), stream))
+        y = self.bufs[name]
+        if self.M == 1 and part.shape[1] * self.world == y.shape[1]:
+            dist.all_gather_into_tensor(y.view(-1), part.view(-1))
+        else:
+            gathered = [self.torch.empty_like(part) for _ in range(self.world)]
+            dist.all_gather(gathered, part)
+            off = 0
+            for r, t in enumerate(gathered):
+                c0, c1 = shard_cols(y.shape[1], self.world, r)
+                y[:, c0:c1].copy_(t[:, : c1 - c0])
+        return y
+
+    def run(self, stream):
+        h = self.h
+        for b in self.blocks:
+            self._call(b["q"], h, "q", stream)
+            self._call(b["k"], h, "k", stream)
+            v = self._call(b["v"], h, "v", stream)
+            o = self._call(b["o"], v, "o", stream)
+            gt = self._call(b["gate"], o, "gate", stream)
+            self._call(b["up"], o, "up", stream)
+            h = self._call(b["down"], gt, "down", stream)
+        return h
+
+
+def run_b200q(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import qllm_b200
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    P = peaks()
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    blocks = build_model(dev, rank, world, "GEMM")
+    M = 1
+    step = DecodeStep(blocks, dev, M, rank, world)
+    h0 = (torch.randn(M, HIDDEN, generator=torch.Generator().manual_seed(7)) * 1.0).to(torch.float16)
+    h0_pinned = h0.pin_memory()
+    y_pinned = torch.empty(M, HIDDEN, dtype=torch.float16).pin_memory()
+    step.h.copy_(h0)
+
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        out = step.run(s.cuda_stream)                 # eager warm-up (sets kernel attributes)
+    s.synchronize()
+    n0 = qllm_b200.lib.b200q_launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        out = step.run(torch.cuda.current_stream().cuda_stream)
+    launches_per_step = qllm_b200.lib.b200q_launch_count() - n0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warm):
+        graph.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(steps):
+            graph.replay()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # ---- e2e: host pinned x -> device -> 224 C-ABI calls (graph) -> host, every step ----
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step.h.copy_(h0_pinned, non_blocking=True)
+            graph.replay()
+            y_pinned.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = t.tolist()
+    ms_per_step = ms / steps
+    tok_s = 1e3 / ms_per_step
+    finite = bool(torch.isfinite(out.float()).all().item())
+
+    if rank != 0:
+        return
+    total_bytes = BLOCKS * sum(alg_bytes(K, N, M) for _, K, N in SHAPES)
+    n_layers = BLOCKS * len(SHAPES)
+    achieved = total_bytes * world / world / (ms_per_step * 1e-3) / 1e9      # whole-job algorithmic GB/s
+    roofline = {"bound": "hbm", "achieved": achieved / world, "peak": P["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / world / P["hbm_gbs"], "traffic": None, "peak_source": P["source"],
+                "kernel": "gemv_rp_kernel<RpAwq> (decode)", "bytes_per_launch": total_bytes / n_layers,
+                "us_per_launch": ms_per_step * 1e3 / n_layers, "per_gpu": True}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roofline["traffic"] = tr.get("decode_awq_dram_bytes_per_launch")
+    except Exception:
+        pass
+    result = {
+        "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+        "data": "synthetic",
+        "config": {"workload": "Llama-2-7B int4 g128 AWQ pack_mode=GEMM, batch=1 decode: 224 chained QuantLinear calls per step",
+                   "M": M, "layers": n_layers, "parallelism": f"column-shard x{world} + all-gather" if world > 1 else "single GPU",
+                   "l2_policy": "inputs (3.4 GB packed weights) larger than L2", "cuda_graph": True, "pdl": True,
+                   "outputs_finite": finite},
+        "clocks": clk.summary(),
+        "e2e": {"value": steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": M * HIDDEN * 2, "d2h_bytes_per_step": M * HIDDEN * 2},
+        "gpu_launches": int(launches_per_step * steps),
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu:
+        from oracle import cpu_baseline as C
+        t_block = C.time_block(M=1, repeats=3)
+        result["cpu_baseline"] = {"value": 1.0 / (t_block * BLOCKS), "unit": "tokens/s", "cores": torch.get_num_threads(),
+                                  "kind": "port", "sample": f"1 of {BLOCKS} decoder blocks (7 QuantLinears, M=1, fp16 torch-CPU dequant+matmul), best of 3, x{BLOCKS}"}
+    if world == 1 and not args.no_prefill:
+        try:
+            result["prefill"] = prefill_tflops(dev, P)
+        except Exception as e:                       # the decode metric stands on its own
+            result["prefill"] = {"error": str(e)[:200]}
+    print(json.dumps(result), flush=True)
+
+
+def prefill_tflops(dev, P, M=512, iters=20):
+    """configs[2]: GPTQ layout, M=512 rows per call, the 7 shapes of one decoder block (tcgen05 GEMM)."""
+    import torch
+    import qllm_b200
+    from tools.microbench import rand_layer
+    copies = 6                                         # 6 blocks x 101 MB of packed weights > L2
+    layers = [[rand_layer("GPTQ", BITS, GROUP, K, N, dev, 100 * c + i) for i, (_, K, N) in enumerate(SHAPES)] for c in range(copies)]
+    xs = {K: torch.randn(M, K, dtype=torch.float16, device=dev) for K in (HIDDEN, INTER)}
+    for c in range(copies):
+        for l in layers[c]:
+            l(xs[l.infeatures])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(iters):
+        for l in layers[it % copies]:
+            l(xs[l.infeatures])
+    e1.record()
+    torch.cuda.synchronize()
+    flops = iters * sum(2.0 * M * K * N for _, K, N in SHAPES)
+    tf = flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    return {"workload": "Llama-2-7B block, GPTQ int4 g128, M=512 per call (7 GEMMs)", "tflops": tf,
+            "frac_of_bf16_peak": tf / P["bf16_tflops"], "peak": P["bf16_tflops"], "kernel": "gemm_tc_gptq4_kernel (tcgen05)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200q", choices=["b200q", "reference"])
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200q(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -23,13 +23,12 @@
 
 namespace b200q {
 
-static constexpr int kTcThreads = 256;
+static constexpr int kTcThreads = 384;
+static constexpr int kDqWarps = 8;      // dequant + epilogue warps (two per TMEM lane quadrant)
 static constexpr int kNS = 4;         // input stages (X tile + packed W tile)
 static constexpr int kNA = 4;         // A stages in TMEM (64 k = 32 columns each)
 static constexpr int kBK = 64;        // k per stage
 static constexpr int kBN = 128;       // output columns per CTA (= UMMA M)
-static constexpr int kTmemCols = 256;
-static constexpr int kAccCol = 0, kACol = 128;
 static constexpr uint32_t kSpinLimit = 4u << 20;
 
 static constexpr uint32_t MAGIC = 0x64006400u, LO4 = 0x000f000fu, HI4 = 0x00f000f0u, H_1_16 = 0x2c002c00u;
@@ -39,7 +38,7 @@ struct TcParams {
   int M;
   PeerOut out;
   int64_t ldy, n_offset;
-  int kblocks;
+  int kblocks, gshift;
   int off_x, off_w, off_sc, off_zq, off_bar;
   int* err;
 };
@@ -103,8 +102,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// GPTQ / HQQ 4-bit producer of A: thread n owns column n; word r of a stage holds k = 8r..8r+7.
+// GPTQ / HQQ 4-bit producer of A: lane n of quadrant q owns column n; word r of a stage holds
+// k = 8r..8r+7.  Two dequant warps per TMEM lane quadrant split the 8 words of a stage.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 template <int TT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const TcParams p) {
@@ -125,16 +133,15 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   const int n0 = blockIdx.x * kBN;
   const int tok0 = blockIdx.y * TT;
   const bool fz = (p.L.layout == B200Q_LAYOUT_HQQ);
-  const int zq_row = fz ? kBN * 2 : kBN / 2;
 
   if (tid == 0) {
-    for (int s = 0; s < kNS; ++s) { mbar_init(&full_in[s], 1); mbar_init(&empty_in[s], 5); }
-    for (int s = 0; s < kNA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kNS; ++s) { mbar_init(&full_in[s], 1); mbar_init(&empty_in[s], 1 + kDqWarps); }
+    for (int s = 0; s < kNA; ++s) { mbar_init(&a_full[s], kDqWarps); mbar_init(&a_empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TT > 128 ? 512 : 256) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // group tables for this CTA's 128 columns (all groups)
@@ -162,13 +169,13 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   const uint32_t tmem = *tmem_slot;
 
   constexpr uint32_t X_BYTES = TT * kBK * 2, W_BYTES = 8 * kBN * 4;
-  bool ok = true;
+  constexpr int kACol = TT;                        // A stages sit right after the TT accumulator columns
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < p.kblocks && ok; ++kb) {
+      for (int kb = 0; kb < p.kblocks; ++kb) {
         const int s = kb % kNS;
-        ok = mbar_wait_bounded(&empty_in[s], ((kb / kNS) + 1) & 1, p.err, 1);
+        if (!mbar_wait_bounded(&empty_in[s], ((kb / kNS) + 1) & 1, p.err, 1)) break;
         mbar_expect_tx(&full_in[s], X_BYTES + W_BYTES);
         tma_load_2d(xst + (size_t)s * X_BYTES, &xmap, &full_in[s], kb * kBK, tok0);
         tma_load_2d(wst + (size_t)s * (W_BYTES / 4), &wmap, &full_in[s], n0, kb * 8);
@@ -178,39 +185,42 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=f16, both K-major, N=TT, M=128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(kBN >> 4) << 24);
+      bool ok = true;
       for (int kb = 0; kb < p.kblocks && ok; ++kb) {
         const int s = kb % kNS, sa = kb % kNA;
-        ok = mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 2);
-        ok = ok && mbar_wait_bounded(&a_full[sa], (kb / kNA) & 1, p.err, 3);
+        ok = mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 2) && mbar_wait_bounded(&a_full[sa], (kb / kNA) & 1, p.err, 3);
         tc_fence_after();
         const uint64_t bdesc = umma_desc_k_sw128(smem_u32(xst + (size_t)s * X_BYTES));
 #pragma unroll
         for (int j = 0; j < kBK / 16; ++j)
-          tc_mma_ts(tmem + kAccCol, tmem + kACol + sa * 32 + j * 8, bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
+          tc_mma_ts(tmem, tmem + kACol + sa * 32 + j * 8, bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
         tc_commit(&empty_in[s]);
         tc_commit(&a_empty[sa]);
       }
       tc_commit(acc_full);
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;                     // TMEM lane quadrant of this warp
+    const int q = warp & 3;                     // TMEM lane quadrant this warp may access (warp id % 4)
+    const int half = (warp - 4) >> 2;           // which 4 of the 8 words of a stage / which token chunks
     const int n = q * 32 + lane;                // column within the CTA tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int gcur = -1;
     uint32_t c_lo = 0, c_hi = 0, s2 = 0, z2 = 0;
+    bool ok = true;
     for (int kb = 0; kb < p.kblocks && ok; ++kb) {
       const int s = kb % kNS, sa = kb % kNA;
-      ok = __all_sync(0xffffffffu, mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 4));
-      uint32_t w[8];
-      const uint32_t* ws = wst + (size_t)s * (W_BYTES / 4) + n;
+      ok = mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 4);
+      uint32_t w[4];
+      const uint32_t* ws = wst + (size_t)s * (W_BYTES / 4) + (4 * half) * kBN + n;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) w[r] = ws[r * kBN];
+      for (int r = 0; r < 4; ++r) w[r] = ws[r * kBN];
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_in[s]);
-      uint32_t a[32];
+      uint32_t a[16];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int gi = (kb * kBK + 8 * r) / p.L.group;
+      for (int r = 0; r < 4; ++r) {
+        const int k = kb * kBK + 32 * half + 8 * r;
+        const int gi = p.gshift >= 0 ? (k >> p.gshift) : (k / p.L.group);
         if (gi != gcur) {
           gcur = gi;
           s2 = dup_half(sc[gi * kBN + n]);
@@ -236,40 +246,48 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         a[4 * r + 2] = prmt(p0, p1, 0x7632);    // (k4,k5)
         a[4 * r + 3] = prmt(p2, p3, 0x7632);    // (k6,k7)
       }
-      ok = __all_sync(0xffffffffu, ok && mbar_wait_bounded(&a_empty[sa], ((kb / kNA) + 1) & 1, p.err, 5));
-      tc_st32(tmem + lane_addr + kACol + sa * 32, a);
+      ok = ok && mbar_wait_bounded(&a_empty[sa], ((kb / kNA) + 1) & 1, p.err, 5);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      tc_st16(tmem + lane_addr + kACol + sa * 32 + half * 16, a);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[sa]);
     }
-    // ---- epilogue ----
-    ok = __all_sync(0xffffffffu, mbar_wait_bounded(acc_full, 0, p.err, 6) && ok);
+    // ---- epilogue: TMEM -> registers -> fp16 -> shared (transpose) -> 16-byte coalesced stores ----
+    ok = __all_sync(0xffffffffu, ok && mbar_wait_bounded(acc_full, 0, p.err, 6));
     tc_fence_after();
-    const bool ncol_ok = (n0 + n) < p.L.N;
-    const float bias = (p.L.bias && ncol_ok) ? __half2float(__ldg(p.L.bias + n0 + n)) : 0.f;
+    const float bias = (p.L.bias && (n0 + n) < p.L.N) ? __half2float(__ldg(p.L.bias + n0 + n)) : 0.f;
+    __half* stg = reinterpret_cast<__half*>(xst) + (size_t)half * 32 * (kBN + 8);     // [32 tok][128+8 n], X stages are free now
+    const int tih = (warp - 4 - 4 * half) * 32 + lane;                                 // thread index within this half (0..127)
 #pragma unroll 1
-    for (int c0 = 0; c0 < TT; c0 += 32) {
+    for (int c0 = half * 32; c0 < TT && ok; c0 += 64) {
       uint32_t v[32];
-      tc_ld32(tmem + lane_addr + kAccCol + c0, v);
+      tc_ld32(tmem + lane_addr + c0, v);
       tc_wait_ld();
-      if (ncol_ok) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int tok = tok0 + c0 + i;
-          if (tok < p.M) {
-            const __half h = __float2half_rn(__uint_as_float(v[i]) + bias);
-            for (int qd = 0; qd < p.out.n; ++qd) p.out.y[qd][(size_t)tok * p.ldy + p.n_offset + n0 + n] = h;
-          }
+      for (int i = 0; i < 32; ++i) stg[(size_t)i * (kBN + 8) + n] = __float2half_rn(__uint_as_float(v[i]) + bias);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+      // 32 token rows x 256 B: 16 chunks of 16 B per row, 128 threads -> 4 chunks each
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = tih + 128 * j, row = idx >> 4, ch = idx & 15;
+        const int tok = tok0 + c0 + row;
+        if (tok < p.M && n0 + 8 * ch < p.L.N) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + (size_t)row * (kBN + 8) + 8 * ch);
+          for (int qd = 0; qd < p.out.n; ++qd)
+            *reinterpret_cast<uint4*>(p.out.y[qd] + (size_t)tok * p.ldy + p.n_offset + n0 + 8 * ch) = val;
         }
       }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
     }
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TT > 128 ? 512 : 256) : "memory");
   }
 }
 
@@ -299,12 +317,12 @@ int gemm_tc_last_error() {
   return v;
 }
 
-static int pick_tt(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : 128); }
+static int pick_tt(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : 128); }   // TT=256 variant exists for large-M experiments
 
 bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t ldx) {
   if (!(L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) || L.bits != 4 || L.g_idx) return false;
   if (L.K % kBK != 0 || L.N % 8 != 0 || L.group % 8 != 0 || L.K % L.group != 0) return false;
-  if (((uintptr_t)x & 15) != 0 || (ldx % 8) != 0 || ((uintptr_t)L.qw & 15) != 0 || (L.N % 4) != 0) return false;
+  if (((uintptr_t)x & 15) != 0 || (ldx % 8) != 0 || ((uintptr_t)L.qw & 15) != 0 || (L.N % 8) != 0) return false;
   const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN / 2;
   const size_t tables = (size_t)L.G * (kBN * 2 + zq_row);
   if (tables > 60 * 1024) return false;
@@ -346,6 +364,8 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   if (peers) p.out = *peers; else { p.out.n = 1; p.out.y[0] = a.y; }
   p.ldy = a.ldy; p.n_offset = a.n_offset;
   p.kblocks = L.K / kBK;
+  p.gshift = -1;
+  if ((L.group & (L.group - 1)) == 0) { int sh = 0; while ((1 << sh) < L.group) ++sh; p.gshift = sh; }
   p.err = g_err_flag;
   const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN / 2;
   int off = 0;
@@ -365,6 +385,9 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
     if (e != cudaSuccess) return e;
     attr_done[dev & 63] = true;
   }
+  for (int i = 0; i < p.out.n; ++i)
+    if (((uintptr_t)p.out.y[i] & 15) != 0) return cudaErrorInvalidValue;
+  if ((a.ldy % 8) != 0 || (a.n_offset % 8) != 0) return cudaErrorInvalidValue;     // 16-byte epilogue stores
   dim3 grid((L.N + kBN - 1) / kBN, (a.M + TT - 1) / TT);
   count_launch();
   gemm_tc_gptq4_kernel<TT><<<grid, kTcThreads, smem_bytes, a.stream>>>(xmap, wmap, p);

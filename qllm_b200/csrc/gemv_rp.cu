@@ -124,6 +124,7 @@ struct RpGptq {
   static constexpr int P = 32 / BITS;
   static constexpr int NT = 32, KSTEP = 4 * P, MAXSTEPS = 16, N_GRAN = 32;
   static constexpr int ROWS_PER_STEP = 4, ROW_WORDS = 32, RS_WORDS = 40, SM_MIN_BLOCKS = 3;
+  static constexpr int COLS_PER_CHUNK = 4, LANE_COLS = 4;       // columns per 16-byte chunk / per lane-g
   static constexpr int NTOT = 2;                               // output accumulators (sets)
   static constexpr int NACC = (BITS == 4) ? 4 : 2;             // 4-bit: {set} x {LO, HI}
   using Step = uint4;
@@ -139,6 +140,15 @@ struct RpGptq {
   }
   // An MMA mixes the k-slots of all four t-lanes, so a step (4 packed rows) must lie inside one group.
   __device__ static int step_k(int s, int) { return s * KSTEP; }
+  // (scale, zero) of (group g, column n) as fp32
+  __device__ static float2 table_entry(const LayerView& L, int g, int n) {
+    const float sv = __half2float(__ldg(L.s + (size_t)g * L.N + n));
+    if (L.layout == B200Q_LAYOUT_HQQ) return make_float2(sv, __half2float(__ldg((const __half*)L.qz + (size_t)g * L.N + n)));
+    const int bit = n * BITS;
+    const uint32_t zw = __ldg((const uint32_t*)L.qz + (size_t)g * (((size_t)L.N * BITS) >> 5) + (bit >> 5));
+    const uint32_t z = (((zw >> (bit & 31)) & ((1u << BITS) - 1u)) + (uint32_t)L.zero_bias) & ((1u << BITS) - 1u);
+    return make_float2(sv, (float)z);
+  }
 
   __device__ static void compute(const Step& w, int s, const RpCtx& cx, float (&acc)[NACC][4], float (&accS)[4], int lane) {
     const int g = lane >> 2;
@@ -235,8 +245,9 @@ struct RpGptq {
 // (n@k, n@k+1).  MMA j of a word covers columns 2j (rows g) and 2j+1 (rows g+8); odd j carry 16*q.
 // ------------------------------------------------------------------------------------------------
 struct RpAwq {
-  static constexpr int NT = 128, KSTEP = 16, MAXSTEPS = 4, N_GRAN = 128;
+  static constexpr int NT = 128, KSTEP = 16, MAXSTEPS = 4, N_GRAN = 32;
   static constexpr int ROWS_PER_STEP = 16, ROW_WORDS = 16, RS_WORDS = 20, SM_MIN_BLOCKS = 2;
+  static constexpr int COLS_PER_CHUNK = 32, LANE_COLS = 16;
   static constexpr int NTOT = 8, NACC = 8;
   struct Step { uint2 r[4]; };
 
@@ -259,6 +270,13 @@ struct RpAwq {
     w.r[3] = r_lds64(base + 9 * RS_WORDS);
   }
   __device__ static int step_k(int s, int) { return s * KSTEP; }
+  __device__ static float2 table_entry(const LayerView& L, int g, int n) {
+    const float sv = __half2float(__ldg(L.s + (size_t)g * L.N + n));
+    const uint32_t zw = __ldg((const uint32_t*)L.qz + (size_t)g * (L.N >> 3) + (n >> 3));
+    const int i = n & 7, nib = (i >> 1) + ((i & 1) << 2);
+    const uint32_t z = (((zw >> (4 * nib)) & 0xFu) + (uint32_t)L.zero_bias) & 0xFu;
+    return make_float2(sv, (float)z);
+  }
 
   __device__ static void compute(const Step& w, int s, const RpCtx& cx, float (&acc)[NACC][4], float (&accS)[4], int lane) {
     const int g = lane >> 2, t = lane & 3;
@@ -314,6 +332,7 @@ struct RpAwq {
 struct RpMarlin {
   static constexpr int NT = 64, KSTEP = 16, MAXSTEPS = 16, N_GRAN = 64;
   static constexpr int ROWS_PER_STEP = 1, ROW_WORDS = 128, RS_WORDS = 128, SM_MIN_BLOCKS = 3;
+  static constexpr int COLS_PER_CHUNK = 64, LANE_COLS = 0;      // tiles are always whole (N % 64 == 0)
   static constexpr int NTOT = 4, NACC = 8;
   using Step = uint4;
 
@@ -323,6 +342,9 @@ struct RpMarlin {
   __device__ static size_t src_word(const LayerView& L, int row, int n0) { return (size_t)row * (2 * (size_t)L.N) + 2 * n0; }
   __device__ static void load_smem(Step& w, const uint32_t* tile, int ls, int lane) { w = r_lds128(tile + (size_t)ls * RS_WORDS + 4 * lane); }
   __device__ static int step_k(int s, int) { return s * KSTEP; }
+  __device__ static float2 table_entry(const LayerView& L, int g, int n) {
+    return make_float2(__half2float(__ldg(L.s + (size_t)g * L.N + marlin_scale_index(n, L.group == L.K))), 8.0f);
+  }
 
   __device__ static void compute(const Step& w, int s, const RpCtx& cx, float (&acc)[NACC][4], float (&accS)[4], int lane) {
     const int g = lane >> 2, t = lane & 3;
@@ -384,6 +406,7 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
   const int rank = (int)cluster_ctarank();
   const int n_tile = blockIdx.x / cs;
   const int n0 = n_tile * T::NT;
+  const int ncols = min(T::NT, p.L.N - n0);             // last tile may be partial (multiple of N_GRAN)
   const int U = cs * kWarps;
   const int S = p.steps_total;
   const int unit = rank * kWarps + warp;
@@ -401,6 +424,11 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
 
   // ---- 1. weights -> shared / registers, group table -> shared (independent of the upstream kernel) ----
   typename T::Step w[SM ? 1 : T::MAXSTEPS];
+  const bool lane_ok = (lane >> 2) * T::LANE_COLS < ncols;      // REGS variant: this lane's columns exist
+  if (!SM) {
+#pragma unroll
+    for (int i = 0; i < (SM ? 1 : T::MAXSTEPS); ++i) w[i] = typename T::Step{};
+  }
   const uint32_t* wtile = reinterpret_cast<const uint32_t*>(smem + p.off_w);
   if (SM) {
     constexpr int CPR = T::ROW_WORDS / 4;                       // 16-byte chunks per packed row
@@ -408,17 +436,19 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
     char* wt = smem + p.off_w;
     for (int idx = tid; idx < nrows * CPR; idx += kRpThreads) {
       const int r = idx / CPR, cc = idx % CPR;
-      cp_async16(wt + ((size_t)r * T::RS_WORDS + 4 * cc) * 4, p.L.qw + T::src_word(p.L, row0 + r, n0) + 4 * cc);
+      if (cc * T::COLS_PER_CHUNK < ncols)
+        cp_async16(wt + ((size_t)r * T::RS_WORDS + 4 * cc) * 4, p.L.qw + T::src_word(p.L, row0 + r, n0) + 4 * cc);
     }
     cp_async_commit();
   } else {
 #pragma unroll
     for (int i = 0; i < (SM ? 1 : T::MAXSTEPS); ++i)
-      if (s_begin + i < s_end) T::load(w[i], p.L, s_begin + i, n0, lane);
+      if (s_begin + i < s_end && lane_ok) T::load(w[i], p.L, s_begin + i, n0, lane);
   }
+  // columns past N get scale 0 (whatever bits sit in their shared-memory slots then contribute 0)
   for (int idx = tid; idx < g_count * T::NT; idx += kRpThreads) {
     const int gl = idx / T::NT, n = idx % T::NT;
-    tab[idx] = make_float2(load_s(p.L, cx.g_first + gl, n0 + n), load_z(p.L, cx.g_first + gl, n0 + n));
+    tab[idx] = (n < ncols) ? T::table_entry(p.L, cx.g_first + gl, n0 + n) : make_float2(0.f, 0.f);
   }
 
   // ---- 2. activations (produced by the upstream kernel) ----
@@ -463,7 +493,7 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
     for (int sb = s_begin + T::MAXSTEPS; sb < s_end; sb += T::MAXSTEPS) {
 #pragma unroll
       for (int i = 0; i < (SM ? 1 : T::MAXSTEPS); ++i)
-        if (sb + i < s_end) T::load(w[i], p.L, sb + i, n0, lane);
+        if (sb + i < s_end && lane_ok) T::load(w[i], p.L, sb + i, n0, lane);
 #pragma unroll
       for (int i = 0; i < (SM ? 1 : T::MAXSTEPS); ++i)
         if (sb + i < s_end) do_step(w[i], sb + i);
@@ -476,7 +506,7 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
   T::store_tot(red + (size_t)warp * T::NT * ms, ms, tot, lane, p.M);
   __syncthreads();
   const int total = T::NT * p.M;          // idx = n * M + m
-  constexpr int NV = (T::NT * kMB + kRpThreads - 1) / kRpThreads;
+  constexpr int NV = (T::NT * (MC == 1 ? 1 : kMB) + kRpThreads - 1) / kRpThreads;   // MC == 1 <=> M == 1
   float v[NV];
 #pragma unroll
   for (int r = 0; r < NV; ++r) {
@@ -508,7 +538,7 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
 #pragma unroll
   for (int r = 0; r < NV; ++r) {
     const int idx = tid + r * kRpThreads;
-    if (idx < total) {
+    if (idx < total && idx / p.M < ncols) {
       const int n = idx / p.M, m = idx % p.M;
       float o = v[r];
       if (p.L.bias) o += __half2float(__ldg(p.L.bias + n0 + n));
@@ -556,7 +586,7 @@ static bool rp_plan(const LayerView& L, int M, RpPlan& pl) {
   if (L.K % pl.KSTEP != 0 || L.N % pl.n_gran != 0 || L.K % L.group != 0) { pl.kind = 0; return false; }
   pl.group_shift = -1;
   if ((L.group & (L.group - 1)) == 0) { int s = 0; while ((1 << s) < L.group) ++s; pl.group_shift = s; }
-  pl.n_tiles = L.N / pl.NT;
+  pl.n_tiles = (L.N + pl.NT - 1) / pl.NT;
   pl.steps_total = L.K / pl.KSTEP;
   int cs = 1;
   if (pl.sm) {
