@@ -134,6 +134,11 @@ int b200q_select_kernel(const b200q_layer* layer, int64_t M);
 /* Number of kernel launches issued by this process through the library (bench accounting). */
 uint64_t b200q_launch_count(void);
 
+/* Diagnostic only: when device_buf != NULL every decode-kernel CTA records 8 x u64 %globaltimer phase
+ * stamps (start, prefetch issued, upstream done, operands in smem, math done, cluster reduced, stored, -)
+ * appended launch after launch until `bytes` are used.  NULL (default) disables. */
+void b200q_debug_set_timeline(void* device_buf, size_t bytes);
+
 const char* b200q_strerror(int status);
 int b200q_last_cuda_error(void); /* cudaError_t of the most recent failing runtime call */
 int b200q_version(void);

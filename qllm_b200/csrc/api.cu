@@ -63,6 +63,10 @@ static int gemv_variant() {
     v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
     const char* kb = getenv("B200Q_SLICE_KB");
     gemv_rp_set_smem(e && e[0] == 'v' && e[1] == '3', kb ? atoi(kb) : 0);
+    const char* ms = getenv("B200Q_MIN_STEPS");
+    if (ms) gemv_rp_set_min_steps(atoi(ms));
+    const char* t = getenv("B200Q_TT256_MIN_M");
+    if (t) gemm_tc_set_tt256_min_m(atoi(t));
     const char* c = getenv("B200Q_MAX_CLUSTER");
     if (c) gemv_rp_set_max_cluster(atoi(c));
   }
@@ -211,6 +215,8 @@ const char* b200q_strerror(int status) {
 }
 
 int b200q_last_cuda_error(void) { return g_last_cuda.load(); }
+/* diagnostic: per-CTA phase timestamps of the decode kernel (8 x u64 per CTA); NULL disables */
+void b200q_debug_set_timeline(void* device_buf, size_t bytes) { gemv_variant(); gemv_rp_set_debug((unsigned long long*)device_buf, bytes / 8); }
 int b200q_version(void) { return B200Q_VERSION; }
 
 }  // extern "C"

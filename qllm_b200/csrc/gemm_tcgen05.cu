@@ -38,12 +38,13 @@ struct TcParams {
   int M;
   PeerOut out;
   int64_t ldy, n_offset;
-  int kblocks, gshift;
+  int kblocks, gshift, group32;
   int off_x, off_w, off_sc, off_zq, off_bar;
   int* err;
 };
 
 // ---- small PTX wrappers -----------------------------------------------------------------------
+#ifdef B200Q_BOUNDED_WAITS     // bring-up aid: every wait gives up after kSpinLimit polls and records a code
 __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, int* err, int code) {
   uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -54,6 +55,20 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity
   }
   return true;
 }
+#else
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, int*, int) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return true;
+}
+#endif
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                    smem_u32(dst)),
@@ -219,9 +234,9 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
       uint32_t a[16];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const int k = kb * kBK + 32 * half + 8 * r;
+        const int k = kb * kBK + 32 * half + (p.group32 ? 0 : 8 * r);     // group32: 32 consecutive k share a group
         const int gi = p.gshift >= 0 ? (k >> p.gshift) : (k / p.L.group);
-        if (gi != gcur) {
+        if ((r == 0 || !p.group32) && gi != gcur) {
           gcur = gi;
           s2 = dup_half(sc[gi * kBN + n]);
           if (fz) {
@@ -317,7 +332,9 @@ int gemm_tc_last_error() {
   return v;
 }
 
-static int pick_tt(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : 128); }   // TT=256 variant exists for large-M experiments
+static int g_tc_tt256_min_m = 1024;
+void gemm_tc_set_tt256_min_m(int m) { g_tc_tt256_min_m = m; }
+static int pick_tt(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : (M >= g_tc_tt256_min_m ? 256 : 128)); }
 
 bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t ldx) {
   if (!(L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) || L.bits != 4 || L.g_idx) return false;
@@ -365,6 +382,7 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   p.ldy = a.ldy; p.n_offset = a.n_offset;
   p.kblocks = L.K / kBK;
   p.gshift = -1;
+  p.group32 = (L.group % 32 == 0) ? 1 : 0;
   if ((L.group & (L.group - 1)) == 0) { int sh = 0; while ((1 << sh) < L.group) ++sh; p.gshift = sh; }
   p.err = g_err_flag;
   const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN / 2;
@@ -399,6 +417,7 @@ cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers) {
   switch (pick_tt(a.M)) {
     case 32: return tc_launch<32>(a, peers);
     case 64: return tc_launch<64>(a, peers);
+    case 256: return tc_launch<256>(a, peers);
     default: return tc_launch<128>(a, peers);
   }
 }

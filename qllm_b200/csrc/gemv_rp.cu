@@ -48,6 +48,7 @@ struct RpParams {
   int n_tiles, cluster, steps_total, group_shift;
   int x_stride;                   // bytes
   int off_x, off_tab, off_red, off_rbuf, off_w;
+  unsigned long long* dbg;        // optional per-CTA phase timestamps (diagnostic; nullptr in production)
 };
 
 __device__ __forceinline__ uint4 ldg128_stream(const void* p) {
@@ -88,6 +89,13 @@ __device__ __forceinline__ void mma_1688(float (&d)[4], uint32_t a0, uint32_t a1
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(b0));
 }
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define RP_STAMP(i) do { if (p.dbg && tid == 0) p.dbg[(size_t)blockIdx.x * 8 + (i)] = gtime(); } while (0)
 
 struct RpCtx {
   int M, k_cta0, g_first, x_stride, group, gshift;
@@ -140,7 +148,29 @@ struct RpGptq {
   }
   // An MMA mixes the k-slots of all four t-lanes, so a step (4 packed rows) must lie inside one group.
   __device__ static int step_k(int s, int) { return s * KSTEP; }
-  // (scale, zero) of (group g, column n) as fp32
+  // (scale, zero) of 8 adjacent columns n..n+7 of group g, as fp32 (n % 8 == 0)
+  __device__ static void table_entries8(const LayerView& L, int g, int n, float2 (&e)[8]) {
+    const uint4 sv = __ldg(reinterpret_cast<const uint4*>(L.s + (size_t)g * L.N + n));
+    const __half* sh = reinterpret_cast<const __half*>(&sv);
+    if (L.layout == B200Q_LAYOUT_HQQ) {
+      const uint4 zv = __ldg(reinterpret_cast<const uint4*>((const __half*)L.qz + (size_t)g * L.N + n));
+      const __half* zh = reinterpret_cast<const __half*>(&zv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = make_float2(__half2float(sh[i]), __half2float(zh[i]));
+      return;
+    }
+    const uint32_t* zrow = (const uint32_t*)L.qz + (size_t)g * (((size_t)L.N * BITS) >> 5);
+    const int bit0 = n * BITS;                                  // 8 columns = 8*BITS bits: one word (two for 8-bit)
+    const uint32_t w0 = __ldg(zrow + (bit0 >> 5));
+    const uint32_t w1 = (BITS == 8) ? __ldg(zrow + (bit0 >> 5) + 1) : 0u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int b = (bit0 & 31) + i * BITS;
+      const uint32_t raw = (b < 32) ? (w0 >> b) : (w1 >> (b - 32));
+      const uint32_t z = ((raw & ((1u << BITS) - 1u)) + (uint32_t)L.zero_bias) & ((1u << BITS) - 1u);
+      e[i] = make_float2(__half2float(sh[i]), (float)z);
+    }
+  }
   __device__ static float2 table_entry(const LayerView& L, int g, int n) {
     const float sv = __half2float(__ldg(L.s + (size_t)g * L.N + n));
     if (L.layout == B200Q_LAYOUT_HQQ) return make_float2(sv, __half2float(__ldg((const __half*)L.qz + (size_t)g * L.N + n)));
@@ -270,6 +300,16 @@ struct RpAwq {
     w.r[3] = r_lds64(base + 9 * RS_WORDS);
   }
   __device__ static int step_k(int s, int) { return s * KSTEP; }
+  __device__ static void table_entries8(const LayerView& L, int g, int n, float2 (&e)[8]) {
+    const uint4 sv = __ldg(reinterpret_cast<const uint4*>(L.s + (size_t)g * L.N + n));
+    const __half* sh = reinterpret_cast<const __half*>(&sv);
+    const uint32_t zw = __ldg((const uint32_t*)L.qz + (size_t)g * (L.N >> 3) + (n >> 3));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int nib = (i >> 1) + ((i & 1) << 2);
+      e[i] = make_float2(__half2float(sh[i]), (float)((((zw >> (4 * nib)) & 0xFu) + (uint32_t)L.zero_bias) & 0xFu));
+    }
+  }
   __device__ static float2 table_entry(const LayerView& L, int g, int n) {
     const float sv = __half2float(__ldg(L.s + (size_t)g * L.N + n));
     const uint32_t zw = __ldg((const uint32_t*)L.qz + (size_t)g * (L.N >> 3) + (n >> 3));
@@ -344,6 +384,10 @@ struct RpMarlin {
   __device__ static int step_k(int s, int) { return s * KSTEP; }
   __device__ static float2 table_entry(const LayerView& L, int g, int n) {
     return make_float2(__half2float(__ldg(L.s + (size_t)g * L.N + marlin_scale_index(n, L.group == L.K))), 8.0f);
+  }
+  __device__ static void table_entries8(const LayerView& L, int g, int n, float2 (&e)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = table_entry(L, g, n + i);
   }
 
   __device__ static void compute(const Step& w, int s, const RpCtx& cx, float (&acc)[NACC][4], float (&accS)[4], int lane) {
@@ -420,6 +464,7 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
   cx.g_first = group_of_k(cx, k_cta0);
   const int g_count = kslice > 0 ? group_of_k(cx, k_cta1 - 1) - cx.g_first + 1 : 0;
 
+  RP_STAMP(0);
   pdl_launch_dependents();
 
   // ---- 1. weights -> shared / registers, group table -> shared (independent of the upstream kernel) ----
@@ -434,10 +479,18 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
     constexpr int CPR = T::ROW_WORDS / 4;                       // 16-byte chunks per packed row
     const int row0 = cta_s0 * T::ROWS_PER_STEP, nrows = (cta_s1 - cta_s0) * T::ROWS_PER_STEP;
     char* wt = smem + p.off_w;
-    for (int idx = tid; idx < nrows * CPR; idx += kRpThreads) {
-      const int r = idx / CPR, cc = idx % CPR;
-      if (cc * T::COLS_PER_CHUNK < ncols)
-        cp_async16(wt + ((size_t)r * T::RS_WORDS + 4 * cc) * 4, p.L.qw + T::src_word(p.L, row0 + r, n0) + 4 * cc);
+    static_assert(kRpThreads % CPR == 0, "chunk column is fixed per thread");
+    constexpr int RSTEP = kRpThreads / CPR;
+    const int cc = tid % CPR, r0 = tid / CPR;
+    if (cc * T::COLS_PER_CHUNK < ncols) {
+      const uint32_t* src = p.L.qw + T::src_word(p.L, row0 + r0, n0) + 4 * cc;
+      const size_t sstep = (T::src_word(p.L, 1, 0) - T::src_word(p.L, 0, 0)) * RSTEP;
+      char* dst = wt + ((size_t)r0 * T::RS_WORDS + 4 * cc) * 4;
+      for (int r = r0; r < nrows; r += RSTEP) {
+        cp_async16(dst, src);
+        src += sstep;
+        dst += (size_t)RSTEP * T::RS_WORDS * 4;
+      }
     }
     cp_async_commit();
   } else {
@@ -446,13 +499,23 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
       if (s_begin + i < s_end && lane_ok) T::load(w[i], p.L, s_begin + i, n0, lane);
   }
   // columns past N get scale 0 (whatever bits sit in their shared-memory slots then contribute 0)
-  for (int idx = tid; idx < g_count * T::NT; idx += kRpThreads) {
-    const int gl = idx / T::NT, n = idx % T::NT;
-    tab[idx] = (n < ncols) ? T::table_entry(p.L, cx.g_first + gl, n0 + n) : make_float2(0.f, 0.f);
+  for (int item = tid; item < g_count * (T::NT / 8); item += kRpThreads) {
+    const int gl = item / (T::NT / 8), c8 = (item % (T::NT / 8)) * 8;
+    float2 e[8];
+    if (c8 < ncols) T::table_entries8(p.L, cx.g_first + gl, n0 + c8, e);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
+    }
+    float4* dst = reinterpret_cast<float4*>(tab + (size_t)gl * T::NT + c8);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = make_float4(e[2 * i].x, e[2 * i].y, e[2 * i + 1].x, e[2 * i + 1].y);
   }
+  RP_STAMP(1);
 
   // ---- 2. activations (produced by the upstream kernel) ----
   pdl_wait();
+  RP_STAMP(2);
   {
     const int vec_per_row = kslice >> 3;
     for (int idx = tid; idx < p.M * vec_per_row; idx += kRpThreads) {
@@ -463,6 +526,7 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
   }
   if (SM) cp_async_wait_all();
   __syncthreads();
+  RP_STAMP(3);
 
   float tot[T::NTOT][4], acc[T::NACC][4], accS[4] = {0.f, 0.f, 0.f, 0.f};
   zero4(tot);
@@ -500,6 +564,7 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
     }
   }
   if (s_begin < s_end) T::template group_end<MC>(tot, acc, accS, cx, gcur - cx.g_first, lane);
+  RP_STAMP(4);
 
   // ---- 3. reduce: warps -> CTA (shared), CTAs of the cluster -> rank 0 (distributed shared) ----
   const int ms = p.M;
@@ -527,6 +592,7 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
       }
     }
     cluster_sync_all();
+    RP_STAMP(5);
     if (rank != 0) return;
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
@@ -546,6 +612,7 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
       for (int q = 0; q < p.out.n; ++q) p.out.y[q][(size_t)m * p.ldy + p.n_offset + n0 + n] = h;
     }
   }
+  RP_STAMP(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -565,6 +632,9 @@ static void rp_fill(RpPlan& pl) {
 static int g_rp_max_cluster = 8;
 static bool g_rp_smem = true;
 static int g_rp_slice_kb = 40;
+static int g_rp_min_steps = 8;
+static unsigned long long* g_rp_dbg = nullptr;
+static size_t g_rp_dbg_cap = 0, g_rp_dbg_pos = 0;   // in u64 entries; consecutive launches append
 
 static bool rp_plan(const LayerView& L, int M, RpPlan& pl) {
   pl.kind = 0;
@@ -596,6 +666,7 @@ static bool rp_plan(const LayerView& L, int M, RpPlan& pl) {
     while (cs < g_rp_max_cluster && (pl.steps_total + cs * kWarps - 1) / (cs * kWarps) > pl.MAXSTEPS) cs *= 2;
   }
   while (cs < g_rp_max_cluster && pl.n_tiles * cs < 148 && pl.steps_total / (2 * cs * kWarps) >= 2) cs *= 2;
+  while (cs > 1 && pl.steps_total / (cs * kWarps) < g_rp_min_steps && pl.n_tiles * (cs / 2) >= 96) cs /= 2;
   pl.cluster = cs;
   const int kslice = ((pl.steps_total + cs - 1) / cs + kWarps) * pl.KSTEP;   // upper bound of a CTA's k-range
   pl.x_stride = kslice * 2;
@@ -626,6 +697,8 @@ bool gemv_rp_supported(const LayerView& L, int M, const __half* x, int64_t ldx) 
 
 void gemv_rp_set_max_cluster(int c) { g_rp_max_cluster = c < 1 ? 1 : (c > 8 ? 8 : c); }
 void gemv_rp_set_smem(bool on, int slice_kb) { g_rp_smem = on; if (slice_kb > 0) g_rp_slice_kb = slice_kb; }
+void gemv_rp_set_min_steps(int n) { g_rp_min_steps = n; }
+void gemv_rp_set_debug(unsigned long long* buf, size_t cap_entries) { g_rp_dbg = buf; g_rp_dbg_cap = cap_entries; g_rp_dbg_pos = 0; }
 
 template <class T, bool SM, int MC>
 static cudaError_t rp_launch_k(const RpParams& p, const RpPlan& pl, cudaStream_t st) {
@@ -671,6 +744,11 @@ cudaError_t launch_gemv_rp(const LinearArgs& a, const PeerOut* peers) {
   p.n_tiles = pl.n_tiles; p.cluster = pl.cluster; p.steps_total = pl.steps_total; p.x_stride = pl.x_stride;
   p.group_shift = pl.group_shift;
   p.off_x = pl.off_x; p.off_tab = pl.off_tab; p.off_red = pl.off_red; p.off_rbuf = pl.off_rbuf; p.off_w = pl.off_w;
+  p.dbg = nullptr;
+  if (g_rp_dbg) {
+    const size_t need = (size_t)pl.n_tiles * pl.cluster * 8;
+    if (g_rp_dbg_pos + need <= g_rp_dbg_cap) { p.dbg = g_rp_dbg + g_rp_dbg_pos; g_rp_dbg_pos += need; }
+  }
   switch (pl.kind) {
     case 1: return rp_launch_t<RpGptq<2>>(p, pl, a.stream);
     case 2: return rp_launch_t<RpGptq<4>>(p, pl, a.stream);

@@ -48,6 +48,8 @@ bool gemv_rp_supported(const LayerView& L, int M, const __half* x, int64_t ldx);
 cudaError_t launch_gemv_rp(const LinearArgs& a, const PeerOut* peers);
 void gemv_rp_set_max_cluster(int c);
 void gemv_rp_set_smem(bool on, int slice_kb);
+void gemv_rp_set_min_steps(int n);
+void gemv_rp_set_debug(unsigned long long* buf, size_t cap_entries);
 
 // first kCounterBytes of every workspace are arrival counters that must stay zero between calls
 static constexpr size_t kCounterBytes = 4096;
@@ -56,5 +58,6 @@ static constexpr size_t kCounterBytes = 4096;
 bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t ldx);
 size_t gemm_tc_workspace(const LayerView& L, int64_t M);
 cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers);
+void gemm_tc_set_tt256_min_m(int m);
 
 }  // namespace b200q
