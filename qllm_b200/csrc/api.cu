@@ -54,15 +54,15 @@ static constexpr int kGenericMaxM = 16;
 
 enum { KERNEL_GEMV_MMA = 1, KERNEL_GEMM_TC = 2, KERNEL_GENERIC = 3 };
 
-// B200Q_GEMV=v1 selects the bulk-copy/mbarrier decode kernel (gemv_mma.cu) instead of the default
-// register-prefetch kernel (gemv_rp.cu); read once. Tuning/diagnostic switch only.
+// Tuning/diagnostic switches, read once: B200Q_GEMV=v1 selects the bulk-copy/mbarrier decode kernel
+// (gemv_mma.cu), =v2 the register-prefetch variant of gemv_rp.cu; default is its cp.async/smem variant.
 static int gemv_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200Q_GEMV");
     v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
     const char* kb = getenv("B200Q_SLICE_KB");
-    gemv_rp_set_smem(e && e[0] == 'v' && e[1] == '3', kb ? atoi(kb) : 0);
+    gemv_rp_set_smem(!(e && e[0] == 'v' && e[1] == '2'), kb ? atoi(kb) : 0);   // v2 = register prefetch, default = smem
     const char* ms = getenv("B200Q_MIN_STEPS");
     if (ms) gemv_rp_set_min_steps(atoi(ms));
     const char* t = getenv("B200Q_TT256_MIN_M");
