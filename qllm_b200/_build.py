@@ -5,7 +5,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libb200q.so")
-SOURCES = ["api.cu", "unpack.cu", "gemv_generic.cu", "gemv_mma.cu", "gemv_rp.cu", "gemm_tcgen05.cu"]
+SOURCES = ["api.cu", "unpack.cu", "gemv_generic.cu", "gemv_mma.cu", "gemv_rp.cu", "gemv_fma.cu", "gemm_tcgen05.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--compiler-options", "-fPIC", "-shared"]
 

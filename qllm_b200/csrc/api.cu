@@ -61,6 +61,9 @@ static int gemv_variant() {
   if (v < 0) {
     const char* e = getenv("B200Q_GEMV");
     v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+    if (e && e[0] == 'v') gemv_fma_set_max_m(0);        // any explicit B200Q_GEMV=v* disables the FMA kernel
+    const char* fm = getenv("B200Q_FMA_MAX_M");
+    if (fm) gemv_fma_set_max_m(atoi(fm));
     const char* kb = getenv("B200Q_SLICE_KB");
     gemv_rp_set_smem(!(e && e[0] == 'v' && e[1] == '2'), kb ? atoi(kb) : 0);   // v2 = register prefetch, default = smem
     const char* ms = getenv("B200Q_MIN_STEPS");
@@ -73,7 +76,7 @@ static int gemv_variant() {
   return v;
 }
 static bool decode_supported(const LayerView& V, int M, const __half* x, int64_t ldx) {
-  if (gemv_variant() == 2 && gemv_rp_supported(V, M, x, ldx)) return true;
+  if (gemv_variant() == 2 && (gemv_fma_supported(V, M, x, ldx) || gemv_rp_supported(V, M, x, ldx))) return true;
   return gemv_mma_supported(V, M, x, ldx);
 }
 
@@ -116,6 +119,7 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   a.L = V; a.x = (const __half*)x; a.ldx = ldx; a.M = (int)M; a.y = (__half*)y; a.ldy = ldy; a.n_offset = n_offset;
   a.workspace = ws; a.workspace_bytes = ws_bytes; a.stream = (cudaStream_t)stream;
   if (kern == KERNEL_GEMV_MMA) {
+    if (gemv_variant() == 2 && gemv_fma_supported(V, (int)M, a.x, ldx)) return cuda_status(launch_gemv_fma(a, peers));
     if (gemv_variant() == 2 && gemv_rp_supported(V, (int)M, a.x, ldx)) return cuda_status(launch_gemv_rp(a, peers));
     return cuda_status(launch_gemv_mma(a, peers));
   }

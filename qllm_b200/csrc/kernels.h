@@ -51,6 +51,11 @@ void gemv_rp_set_smem(bool on, int slice_kb);
 void gemv_rp_set_min_steps(int n);
 void gemv_rp_set_debug(unsigned long long* buf, size_t cap_entries);
 
+// gemv_fma.cu : M <= 2 decode path (CUDA-core fp16x2 FMA, register prefetch, cluster split-K)
+bool gemv_fma_supported(const LayerView& L, int M, const __half* x, int64_t ldx);
+cudaError_t launch_gemv_fma(const LinearArgs& a, const PeerOut* peers);
+void gemv_fma_set_max_m(int m);
+
 // first kCounterBytes of every workspace are arrival counters that must stay zero between calls
 static constexpr size_t kCounterBytes = 4096;
 
