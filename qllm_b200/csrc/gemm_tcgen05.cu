@@ -60,11 +60,11 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"      // %2: suspend-time hint (ns)
       "@p bra DONE;\n\t"
       "bra LAB_WAIT;\n\t"
       "DONE:\n\t}"
-      ::"r"(smem_u32(bar)), "r"(parity)
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return true;
 }
@@ -74,6 +74,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
                    smem_u32(dst)),
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
+}
+// one arrival per warp, issued by lane 0 under a predicate (no divergent branch)
+__device__ __forceinline__ void mbar_arrive_lane0(uint64_t* bar, int lane) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(lane)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -129,7 +137,7 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
 }
 
 template <int TT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, TT <= 128 ? 2 : 1)
 gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const TcParams p) {
   extern __shared__ __align__(1024) char smem_raw[];
   char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-byte alignment
@@ -222,15 +230,18 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     int gcur = -1;
     uint32_t c_lo = 0, c_hi = 0, s2 = 0, z2 = 0;
     bool ok = true;
-    for (int kb = 0; kb < p.kblocks && ok; ++kb) {
+    const uint32_t* ws_lane = wst + (4 * half) * kBN + n;
+    const uint32_t a_dst = tmem + lane_addr + kACol + half * 16;
+    int pending_sa = -1;                             // A stage whose tcgen05.st has been issued but not yet published
+    for (int kb = 0; kb < p.kblocks; ++kb) {
       const int s = kb % kNS, sa = kb % kNA;
-      ok = mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 4);
+      mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 4);
       uint32_t w[4];
-      const uint32_t* ws = wst + (size_t)s * (W_BYTES / 4) + (4 * half) * kBN + n;
+      const uint32_t* ws = ws_lane + (size_t)s * (W_BYTES / 4);
 #pragma unroll
       for (int r = 0; r < 4; ++r) w[r] = ws[r * kBN];
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_in[s]);
+      mbar_arrive_lane0(&empty_in[s], lane);
       uint32_t a[16];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -261,14 +272,22 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         a[4 * r + 2] = prmt(p0, p1, 0x7632);    // (k4,k5)
         a[4 * r + 3] = prmt(p2, p3, 0x7632);    // (k6,k7)
       }
-      ok = ok && mbar_wait_bounded(&a_empty[sa], ((kb / kNA) + 1) & 1, p.err, 5);
-      ok = __all_sync(0xffffffffu, ok);
-      if (!ok) break;
-      tc_st16(tmem + lane_addr + kACol + sa * 32 + half * 16, a);
+      // publish the previous stage only now: its TMEM store has had this k-block's ALU work to complete
+      if (pending_sa >= 0) {
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        mbar_arrive_lane0(&a_full[pending_sa], lane);
+      }
+      mbar_wait_bounded(&a_empty[sa], ((kb / kNA) + 1) & 1, p.err, 5);
+      tc_st16(a_dst + sa * 32, a);
+      pending_sa = sa;
+    }
+    if (pending_sa >= 0) {
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[sa]);
+      mbar_arrive_lane0(&a_full[pending_sa], lane);
     }
     // ---- epilogue: TMEM -> registers -> fp16 -> shared (transpose) -> 16-byte coalesced stores ----
     ok = __all_sync(0xffffffffu, ok && mbar_wait_bounded(acc_full, 0, p.err, 6));

@@ -9,3 +9,5 @@ echo "== timelines (rp smem variant)"; B200Q_GEMV=v3 timeout 120 python tools/ti
 B200Q_GEMV=v3 timeout 120 python tools/timeline.py --layout GPTQ --shape 4096x4096 --launches 5 2>&1 | tee -a $O/timeline2.log
 echo "== bench.py"; timeout 900 python bench.py --steps 30 --warmup 5 --no-prefill 2>&1 | tail -1 | tee $O/bench5.log | cut -c1-200
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemv_fma -s 10 -c 2 -o $O/ncu5_fma -f python tools/microbench.py --m 1 --iters 8 --layouts GEMM --shapes 4096x4096 > $O/ncu5_fma.log 2>&1
+echo "== gemm microbench (deferred publish)"; timeout 300 python tools/microbench.py --m 64,512,2048,8192 --iters 30 --layouts GPTQ --shapes 4096x4096,4096x11008 2>&1 | tee $O/mb5_gemm.log
+timeout 300 python -m pytest tests -m gpu -q -k tcgen05 2>&1 | tail -3
