@@ -122,6 +122,16 @@ int b200q_dequant(const b200q_layer* layer, void* w_out, b200q_stream_t stream);
  */
 int b200q_unpack(const b200q_layer* layer, int32_t* q_out, int32_t* z_out, b200q_stream_t stream);
 
+/*
+ * One-time exact integer re-layout of a 4-bit AWQ-GEMM or Marlin layer into the K-packed GPTQ layout
+ * (qweight i32 [K/8, N], qzeros i32 [G, N/8] holding z with bias 0, scales fp16 [G, N] natural order).
+ * Used by the host shim to give the tcgen05 GEMM a K-packed copy of layouts whose native GEMM producer is
+ * not written yet; the decode kernels always read the checkpoint bytes in place.  Device restatement of
+ * the unpack -> pack round trip of repack_to_new_mode (qllm/auto_model_quantization.py:115-147) without
+ * the fp16 dequant/requant in the middle.
+ */
+int b200q_repack_gptq4(const b200q_layer* layer, void* qweight_out, void* qzeros_out, void* scales_out, b200q_stream_t stream);
+
 /* Bytes of zero-initialised workspace b200q_linear/gemv/gemm need for this layer at batch M. */
 size_t b200q_workspace_bytes(const b200q_layer* layer, int64_t M);
 

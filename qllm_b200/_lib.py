@@ -20,7 +20,7 @@ class Layer(ctypes.Structure):
 
 EXPORTS = ["b200q_linear", "b200q_gemv", "b200q_gemm", "b200q_linear_sharded", "b200q_dequant", "b200q_unpack",
            "b200q_workspace_bytes", "b200q_gemv_max_m", "b200q_select_kernel", "b200q_launch_count",
-           "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline"]
+           "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4"]
 
 
 def _load():
@@ -41,6 +41,8 @@ def _load():
     lib.b200q_dequant.restype = ctypes.c_int
     lib.b200q_unpack.argtypes = [LP, P, P, P]
     lib.b200q_unpack.restype = ctypes.c_int
+    lib.b200q_repack_gptq4.argtypes = [LP, P, P, P, P]
+    lib.b200q_repack_gptq4.restype = ctypes.c_int
     lib.b200q_workspace_bytes.argtypes = [LP, I64]
     lib.b200q_workspace_bytes.restype = SZ
     lib.b200q_gemv_max_m.restype = ctypes.c_int

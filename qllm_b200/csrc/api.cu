@@ -188,6 +188,15 @@ int b200q_unpack(const b200q_layer* layer, int32_t* q_out, int32_t* z_out, b200q
   return cuda_status(launch_unpack(make_view(layer), q_out, z_out, (cudaStream_t)stream));
 }
 
+int b200q_repack_gptq4(const b200q_layer* layer, void* qweight_out, void* qzeros_out, void* scales_out, b200q_stream_t stream) {
+  const int v = validate(layer);
+  if (v != B200Q_OK) return v;
+  if (!qweight_out || !qzeros_out || !scales_out) return B200Q_ERR_NULL;
+  if (layer->bits != 4 || layer->g_idx || layer->layout == B200Q_LAYOUT_HQQ || layer->K % 8 != 0) return B200Q_ERR_UNSUPPORTED;
+  return cuda_status(launch_repack_gptq4(make_view(layer), (uint32_t*)qweight_out, (uint32_t*)qzeros_out, (__half*)scales_out,
+                                         (cudaStream_t)stream));
+}
+
 size_t b200q_workspace_bytes(const b200q_layer* layer, int64_t M) {
   if (validate(layer) != B200Q_OK || M < 1) return 0;
   return workspace_for(make_view(layer), M);

@@ -33,6 +33,7 @@ struct PeerOut {
 // unpack.cu
 cudaError_t launch_unpack(const LayerView& L, int32_t* q_out, int32_t* z_out, cudaStream_t st);
 cudaError_t launch_dequant(const LayerView& L, __half* w_out, cudaStream_t st);
+cudaError_t launch_repack_gptq4(const LayerView& L, uint32_t* qw_out, uint32_t* qz_out, __half* s_out, cudaStream_t st);
 
 // gemv_generic.cu : any layout / bits / group / g_idx, M <= 16, CUDA cores
 size_t gemv_generic_workspace(const LayerView& L, int M);

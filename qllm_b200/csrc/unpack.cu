@@ -39,6 +39,40 @@ __global__ void __launch_bounds__(256) unpack_zeros_kernel(LayerView L, int32_t*
   z_out[idx] = (int32_t)load_z(L, g, n);
 }
 
+// One-time integer re-layout (exact): any 4-bit layout -> K-packed GPTQ words (8 k per word, N-contiguous),
+// GPTQ qzeros (8 columns per word) and natural-order fp16 scales.  One thread per output word.
+__global__ void __launch_bounds__(256) repack_gptq4_kernel(LayerView L, uint32_t* __restrict__ qw_out, uint32_t* __restrict__ qz_out,
+                                                           __half* __restrict__ s_out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nw = (size_t)(L.K >> 3) * L.N;
+  if (idx < nw) {
+    const int kw = (int)(idx / L.N), n = (int)(idx % L.N);
+    uint32_t w = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w |= (load_q(L, 8 * kw + i, n) & 0xFu) << (4 * i);
+    qw_out[idx] = w;
+  }
+  const size_t nz = (size_t)L.G * (L.N >> 3);
+  if (idx < nz) {
+    const int g = (int)(idx / (L.N >> 3)), c = (int)(idx % (L.N >> 3));
+    uint32_t w = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w |= ((uint32_t)load_z(L, g, 8 * c + i) & 0xFu) << (4 * i);
+    qz_out[idx] = w;
+  }
+  const size_t ns = (size_t)L.G * L.N;
+  if (idx < ns) s_out[idx] = __float2half_rn(load_s(L, (int)(idx / L.N), (int)(idx % L.N)));
+}
+
+cudaError_t launch_repack_gptq4(const LayerView& L, uint32_t* qw_out, uint32_t* qz_out, __half* s_out, cudaStream_t st) {
+  const size_t total = (size_t)(L.K >> 3) * L.N;      // >= G*N/8; scales G*N <= total when group >= 8
+  const size_t ns = (size_t)L.G * L.N;
+  const size_t m = total > ns ? total : ns;
+  repack_gptq4_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(L, qw_out, qz_out, s_out);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_unpack(const LayerView& L, int32_t* q_out, int32_t* z_out, cudaStream_t st) {
   const size_t total = (size_t)L.K * (L.N >> 3);
   unpack_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, q_out, nullptr);

@@ -99,6 +99,28 @@ class _B200QuantLinearBase(nn.Module):
             self._desc_key = tuple(0 if t is None else t.data_ptr() for t in self._tensors())
         return self._desc
 
+    # -- K-packed shadow for the tensor-core GEMM (AWQ / Marlin until their native producers exist) --
+    def _gemm_descriptor(self):
+        """b200q_layer the tcgen05 GEMM can take.  GPTQ/HQQ: the checkpoint buffers themselves.  AWQ/Marlin:
+        a one-time exact integer re-layout (b200q_repack_gptq4) kept beside the native buffers."""
+        desc = self._descriptor()
+        if self._layout not in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN):
+            return desc
+        key = self._desc_key
+        if getattr(self, "_shadow_key", None) != key:
+            dev = self.qweight.device
+            K, N, G = self.infeatures, self.outfeatures, self.infeatures // self.groupsize
+            qw = torch.empty((K // 8, N), dtype=torch.int32, device=dev)
+            qz = torch.empty((G, N // 8), dtype=torch.int32, device=dev)
+            sc = torch.empty((G, N), dtype=torch.float16, device=dev)
+            check(lib.b200q_repack_gptq4(ctypes.byref(desc), qw.data_ptr(), qz.data_ptr(), sc.data_ptr(),
+                                         torch.cuda.current_stream(dev).cuda_stream), "b200q_repack_gptq4")
+            d = Layer()
+            d.layout, d.bits, d.group_size, d.K, d.N, d.zero_bias = LAYOUT_GPTQ, 4, self.groupsize, K, N, 0
+            d.qweight, d.qzeros, d.scales, d.g_idx, d.bias = qw.data_ptr(), qz.data_ptr(), sc.data_ptr(), None, desc.bias
+            self._shadow, self._shadow_desc, self._shadow_key = (qw, qz, sc), d, key
+        return self._shadow_desc
+
     # -- forward ------------------------------------------------------------------------------
     def forward(self, x):
         desc = self._descriptor()
@@ -111,6 +133,8 @@ class _B200QuantLinearBase(nn.Module):
         M = x2.shape[0]
         y = torch.empty((M, self.outfeatures), dtype=torch.float16, device=x.device)
         if M > 0:
+            if M > lib.b200q_gemv_max_m() and lib.b200q_select_kernel(ctypes.byref(desc), M) != 2:
+                desc = self._gemm_descriptor()
             need = lib.b200q_workspace_bytes(ctypes.byref(desc), M)
             ws = _workspace(x.device, need)
             st = lib.b200q_linear(ctypes.byref(desc), x2.data_ptr(), M, x2.stride(0), y.data_ptr(), y.stride(0),

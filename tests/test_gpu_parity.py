@@ -243,3 +243,20 @@ def test_tcgen05_gemm_full_size(K, N):
     y = layer(x)
     ref = x.double() @ W.double()
     assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < TOL
+
+
+@pytest.mark.parametrize("layout,gs,K,N", [("GEMM", 128, 512, 256), ("GEMM", 64, 1024, 384), ("MARLIN", 128, 512, 256),
+                                            ("MARLIN", -1, 256, 256)])
+@pytest.mark.parametrize("M", [17, 128, 300])
+def test_awq_marlin_prefill_through_exact_repack(layout, gs, K, N, M):
+    """M > 8 on AWQ/Marlin layers: one-time integer re-layout (bit-exact) + tcgen05 GEMM."""
+    L = O.make_layer(layout, 4, gs, K, N, seed=K + N + M, bias=True)
+    layer = layer_from_dict(L)
+    x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+    y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+    assert rel_err(y, oracle_forward(L, x)) < TOL
+    qw, qz, sc = layer._shadow
+    q = O.gptq_unpack_qweight(qw.cpu().numpy(), 4, K)
+    z = O.gptq_unpack_qzeros(qz.cpu().numpy(), 4, N)
+    assert np.array_equal(q, L["q"]) and np.array_equal(z, np.asarray(L["z"]).astype(np.int32))
+    assert np.array_equal(sc.cpu().numpy().view(np.uint16), L["s"].view(np.uint16))
