@@ -136,13 +136,13 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
       : "memory");
 }
 
-template <int TT>
+template <int TT, int BITS>
 __global__ void __launch_bounds__(kTcThreads, TT <= 128 ? 2 : 1)
-gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const TcParams p) {
+gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const TcParams p) {
   extern __shared__ __align__(1024) char smem_raw[];
   char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-byte alignment
   char* xst = smem + p.off_x;                                      // kNS x [TT][64] fp16, SW128
-  uint32_t* wst = reinterpret_cast<uint32_t*>(smem + p.off_w);     // kNS x [8][128] words
+  uint32_t* wst = reinterpret_cast<uint32_t*>(smem + p.off_w);     // kNS x [64*BITS/32][128] words
   __half* sc = reinterpret_cast<__half*>(smem + p.off_sc);         // [G][128]
   char* zq = smem + p.off_zq;                                      // [G][128] nibbles (64 B) | [G][128] fp16
   uint64_t* full_in = reinterpret_cast<uint64_t*>(smem + p.off_bar);
@@ -179,11 +179,12 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
           (n0 + n < p.L.N) ? __ldg(reinterpret_cast<const __half*>(p.L.qz) + (size_t)g * p.L.N + n0 + n) : __float2half(0.f);
     }
   } else {
-    const size_t zrow = (size_t)p.L.N >> 3;
-    for (int idx = tid; idx < p.L.G * (kBN / 8); idx += kTcThreads) {
-      const int g = idx / (kBN / 8), wv = idx % (kBN / 8);
+    constexpr int ZW = kBN * BITS / 32;                                 // packed zero words of this tile per group
+    const size_t zrow = ((size_t)p.L.N * BITS) >> 5;
+    for (int idx = tid; idx < p.L.G * ZW; idx += kTcThreads) {
+      const int g = idx / ZW, wv = idx % ZW;
       reinterpret_cast<uint32_t*>(zq)[idx] =
-          (n0 + 8 * wv < p.L.N) ? __ldg(reinterpret_cast<const uint32_t*>(p.L.qz) + (size_t)g * zrow + (n0 >> 3) + wv) : 0u;
+          ((n0 * BITS) / 32 + wv < (int)zrow) ? __ldg(reinterpret_cast<const uint32_t*>(p.L.qz) + (size_t)g * zrow + (n0 * BITS) / 32 + wv) : 0u;
     }
   }
   tc_fence_before();
@@ -191,7 +192,10 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  constexpr uint32_t X_BYTES = TT * kBK * 2, W_BYTES = 8 * kBN * 4;
+  constexpr int P = 32 / BITS;                     // k values per packed word
+  constexpr int RS = kBK / P;                      // packed rows per stage
+  constexpr int WH = RS / 2;                       // words per column per half-stage (32 k)
+  constexpr uint32_t X_BYTES = TT * kBK * 2, W_BYTES = RS * kBN * 4;
   constexpr int kACol = TT;                        // A stages sit right after the TT accumulator columns
 
   if (warp == 0) {
@@ -201,7 +205,7 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         if (!mbar_wait_bounded(&empty_in[s], ((kb / kNS) + 1) & 1, p.err, 1)) break;
         mbar_expect_tx(&full_in[s], X_BYTES + W_BYTES);
         tma_load_2d(xst + (size_t)s * X_BYTES, &xmap, &full_in[s], kb * kBK, tok0);
-        tma_load_2d(wst + (size_t)s * (W_BYTES / 4), &wmap, &full_in[s], n0, kb * 8);
+        tma_load_2d(wst + (size_t)s * (W_BYTES / 4), &wmap, &full_in[s], n0, kb * RS);
       }
     }
   } else if (warp == 1) {
@@ -230,22 +234,26 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     int gcur = -1;
     uint32_t c_lo = 0, c_hi = 0, s2 = 0, z2 = 0;
     bool ok = true;
-    const uint32_t* ws_lane = wst + (4 * half) * kBN + n;
+    const uint32_t* ws_lane = wst + (WH * half) * kBN + n;
     const uint32_t a_dst = tmem + lane_addr + kACol + half * 16;
     int pending_sa = -1;                             // A stage whose tcgen05.st has been issued but not yet published
+    constexpr uint32_t ZMASK = (1u << BITS) - 1u;
+    // (h - (1024+z)) * s   [h = 1024+q]   or, for float zeros, ((h - 1024) - z) * s
+    auto fin_lo = [&](uint32_t h) { uint32_t d = hsub2_u(h, c_lo); if (fz) d = hsub2_u(d, z2); return hmul2_u(d, s2); };
+    auto fin_hi = [&](uint32_t h) { uint32_t d = hfma2_u(h, H_1_16, c_hi); if (fz) d = hsub2_u(d, z2); return hmul2_u(d, s2); };
     for (int kb = 0; kb < p.kblocks; ++kb) {
       const int s = kb % kNS, sa = kb % kNA;
       mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 4);
-      uint32_t w[4];
+      uint32_t w[WH];
       const uint32_t* ws = ws_lane + (size_t)s * (W_BYTES / 4);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) w[r] = ws[r * kBN];
+      for (int r = 0; r < WH; ++r) w[r] = ws[r * kBN];
       __syncwarp();
       mbar_arrive_lane0(&empty_in[s], lane);
       uint32_t a[16];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int k = kb * kBK + 32 * half + (p.group32 ? 0 : 8 * r);     // group32: 32 consecutive k share a group
+      for (int r = 0; r < WH; ++r) {
+        const int k = kb * kBK + 32 * half + (p.group32 ? 0 : P * r);     // group32: 32 consecutive k share a group
         const int gi = p.gshift >= 0 ? (k >> p.gshift) : (k / p.L.group);
         if ((r == 0 || !p.group32) && gi != gcur) {
           gcur = gi;
@@ -254,23 +262,36 @@ gemm_tc_gptq4_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_cons
             z2 = dup_half(reinterpret_cast<const __half*>(zq)[gi * kBN + n]);
             c_lo = MAGIC; c_hi = 0xD400D400u;
           } else {
-            const uint32_t zw = reinterpret_cast<const uint32_t*>(zq)[gi * (kBN / 8) + (n >> 3)];
-            const uint32_t z = (((zw >> (4 * (n & 7))) & 0xFu) + (uint32_t)p.L.zero_bias) & 0xFu;
+            const int bit = n * BITS;
+            const uint32_t zw = reinterpret_cast<const uint32_t*>(zq)[gi * (kBN * BITS / 32) + (bit >> 5)];
+            const uint32_t z = (((zw >> (bit & 31)) & ZMASK) + (uint32_t)p.L.zero_bias) & ZMASK;
             c_lo = (0x6400u | z) * 0x00010001u;
             c_hi = (0xD400u + (z << 4)) * 0x00010001u;
           }
         }
-        const uint32_t lo = w[r], hi = w[r] >> 8;
-        uint32_t p0 = hsub2_u(and_or(lo, LO4, MAGIC), c_lo);            // (k0,k4) - z
-        uint32_t p1 = hfma2_u(and_or(lo, HI4, MAGIC), H_1_16, c_hi);    // (k1,k5)
-        uint32_t p2 = hsub2_u(and_or(hi, LO4, MAGIC), c_lo);            // (k2,k6)
-        uint32_t p3 = hfma2_u(and_or(hi, HI4, MAGIC), H_1_16, c_hi);    // (k3,k7)
-        if (fz) { p0 = hsub2_u(p0, z2); p1 = hsub2_u(p1, z2); p2 = hsub2_u(p2, z2); p3 = hsub2_u(p3, z2); }
-        p0 = hmul2_u(p0, s2); p1 = hmul2_u(p1, s2); p2 = hmul2_u(p2, s2); p3 = hmul2_u(p3, s2);
-        a[4 * r + 0] = prmt(p0, p1, 0x5410);    // (k0,k1)
-        a[4 * r + 1] = prmt(p2, p3, 0x5410);    // (k2,k3)
-        a[4 * r + 2] = prmt(p0, p1, 0x7632);    // (k4,k5)
-        a[4 * r + 3] = prmt(p2, p3, 0x7632);    // (k6,k7)
+        if (BITS == 4) {
+          const uint32_t lo = w[r], hi = w[r] >> 8;
+          const uint32_t p0 = fin_lo(and_or(lo, LO4, MAGIC));             // (k0,k4)
+          const uint32_t p1 = fin_hi(and_or(lo, HI4, MAGIC));             // (k1,k5)
+          const uint32_t p2 = fin_lo(and_or(hi, LO4, MAGIC));             // (k2,k6)
+          const uint32_t p3 = fin_hi(and_or(hi, HI4, MAGIC));             // (k3,k7)
+          a[4 * r + 0] = prmt(p0, p1, 0x5410);    // (k0,k1)
+          a[4 * r + 1] = prmt(p2, p3, 0x5410);    // (k2,k3)
+          a[4 * r + 2] = prmt(p0, p1, 0x7632);    // (k4,k5)
+          a[4 * r + 3] = prmt(p2, p3, 0x7632);    // (k6,k7)
+        } else if (BITS == 8) {
+          a[2 * r + 0] = fin_lo(prmt(w[r], MAGIC, 0x5150));               // (k0,k1): bytes -> 1024+q
+          a[2 * r + 1] = fin_lo(prmt(w[r], MAGIC, 0x5352));               // (k2,k3)
+        } else {                                                           // 2-bit: E_i = (k_i, k_{i+8})
+          uint32_t e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = fin_lo(and_or(w[r] >> (2 * i), 0x00030003u, MAGIC));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a[8 * r + j] = prmt(e[2 * j], e[2 * j + 1], 0x5410);           // (k_2j, k_2j+1)
+            a[8 * r + 4 + j] = prmt(e[2 * j], e[2 * j + 1], 0x7632);       // (k_8+2j, k_9+2j)
+          }
+        }
       }
       // publish the previous stage only now: its TMEM store has had this k-block's ALU work to complete
       if (pending_sa >= 0) {
@@ -356,10 +377,12 @@ void gemm_tc_set_tt256_min_m(int m) { g_tc_tt256_min_m = m; }
 static int pick_tt(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : (M >= g_tc_tt256_min_m ? 256 : 128)); }
 
 bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t ldx) {
-  if (!(L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) || L.bits != 4 || L.g_idx) return false;
+  if (!(L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) || L.g_idx) return false;
+  if (L.bits != 2 && L.bits != 4 && L.bits != 8) return false;
+  if (L.group % (32 / L.bits) != 0) return false;                         // a packed word never straddles two groups
   if (L.K % kBK != 0 || L.N % 8 != 0 || L.group % 8 != 0 || L.K % L.group != 0) return false;
   if (((uintptr_t)x & 15) != 0 || (ldx % 8) != 0 || ((uintptr_t)L.qw & 15) != 0 || (L.N % 8) != 0) return false;
-  const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN / 2;
+  const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN * L.bits / 8;
   const size_t tables = (size_t)L.G * (kBN * 2 + zq_row);
   if (tables > 60 * 1024) return false;
   return get_encode() != nullptr && M >= 1;
@@ -367,7 +390,7 @@ bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t l
 
 size_t gemm_tc_workspace(const LayerView&, int64_t) { return 0; }
 
-template <int TT>
+template <int TT, int BITS>
 static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   const LayerView& L = a.L;
   EncodeTiledFn enc = get_encode();
@@ -383,9 +406,9 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
       return cudaErrorInvalidValue;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)L.N, (cuuint64_t)(L.K / 8)};
+    cuuint64_t dims[2] = {(cuuint64_t)L.N, (cuuint64_t)(L.K * BITS / 32)};
     cuuint64_t strides[1] = {(cuuint64_t)L.N * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kBN, 8};
+    cuuint32_t box[2] = {(cuuint32_t)kBN, (cuuint32_t)(kBK * BITS / 32)};
     cuuint32_t es[2] = {1, 1};
     if (enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)L.qw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -404,10 +427,10 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   p.group32 = (L.group % 32 == 0) ? 1 : 0;
   if ((L.group & (L.group - 1)) == 0) { int sh = 0; while ((1 << sh) < L.group) ++sh; p.gshift = sh; }
   p.err = g_err_flag;
-  const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN / 2;
+  const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN * BITS / 8;
   int off = 0;
   p.off_x = off; off += kNS * TT * kBK * 2;
-  p.off_w = off; off += kNS * 8 * kBN * 4;
+  p.off_w = off; off += kNS * (kBK * BITS / 32) * kBN * 4;
   p.off_sc = off; off += L.G * kBN * 2;
   off = (off + 15) & ~15;
   p.off_zq = off; off += L.G * zq_row;
@@ -418,7 +441,7 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_gptq4_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_gptq_kernel<TT, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
     attr_done[dev & 63] = true;
   }
@@ -427,18 +450,23 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   if ((a.ldy % 8) != 0 || (a.n_offset % 8) != 0) return cudaErrorInvalidValue;     // 16-byte epilogue stores
   dim3 grid((L.N + kBN - 1) / kBN, (a.M + TT - 1) / TT);
   count_launch();
-  gemm_tc_gptq4_kernel<TT><<<grid, kTcThreads, smem_bytes, a.stream>>>(xmap, wmap, p);
+  gemm_tc_gptq_kernel<TT, BITS><<<grid, kTcThreads, smem_bytes, a.stream>>>(xmap, wmap, p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers) {
   // M is chunked so that a.M fits int and grid.y <= 65535
-  switch (pick_tt(a.M)) {
-    case 32: return tc_launch<32>(a, peers);
-    case 64: return tc_launch<64>(a, peers);
-    case 256: return tc_launch<256>(a, peers);
-    default: return tc_launch<128>(a, peers);
+#define B200Q_TC_DISPATCH(BITS)                                  \
+  switch (pick_tt(a.M)) {                                       \
+    case 32: return tc_launch<32, BITS>(a, peers);              \
+    case 64: return tc_launch<64, BITS>(a, peers);              \
+    case 256: return tc_launch<256, BITS>(a, peers);            \
+    default: return tc_launch<128, BITS>(a, peers);             \
   }
+  if (a.L.bits == 2) { B200Q_TC_DISPATCH(2) }
+  if (a.L.bits == 8) { B200Q_TC_DISPATCH(8) }
+  B200Q_TC_DISPATCH(4)
+#undef B200Q_TC_DISPATCH
 }
 
 }  // namespace b200q

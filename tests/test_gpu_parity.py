@@ -260,3 +260,17 @@ def test_awq_marlin_prefill_through_exact_repack(layout, gs, K, N, M):
     z = O.gptq_unpack_qzeros(qz.cpu().numpy(), 4, N)
     assert np.array_equal(q, L["q"]) and np.array_equal(z, np.asarray(L["z"]).astype(np.int32))
     assert np.array_equal(sc.cpu().numpy().view(np.uint16), L["s"].view(np.uint16))
+
+
+@pytest.mark.parametrize("layout,bits,gs,K,N", [("GPTQ", 8, 128, 512, 256), ("GPTQ", 2, 64, 512, 128), ("GPTQ", 2, 16, 256, 128),
+                                                ("HQQ", 8, 128, 256, 128), ("HQQ", 2, 64, 512, 256), ("GPTQ", 8, 32, 256, 160)])
+@pytest.mark.parametrize("M", [20, 128, 260])
+def test_tcgen05_gemm_2bit_8bit(layout, bits, gs, K, N, M):
+    import ctypes
+    import qllm_b200
+    L = O.make_layer(layout, bits, gs, K, N, seed=K + N + M + bits, bias=True, float_zeros=(layout == "HQQ" and bits == 8))
+    layer = layer_from_dict(L)
+    assert qllm_b200.lib.b200q_select_kernel(ctypes.byref(layer._descriptor()), M) == 2
+    x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+    y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+    assert rel_err(y, oracle_forward(L, x)) < TOL
