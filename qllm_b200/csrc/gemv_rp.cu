@@ -372,7 +372,7 @@ struct RpAwq {
 struct RpMarlin {
   static constexpr int NT = 64, KSTEP = 16, MAXSTEPS = 16, N_GRAN = 64;
   static constexpr int ROWS_PER_STEP = 1, ROW_WORDS = 128, RS_WORDS = 128, SM_MIN_BLOCKS = 3;
-  static constexpr int COLS_PER_CHUNK = 64, LANE_COLS = 0;      // tiles are always whole (N % 64 == 0)
+  static constexpr int COLS_PER_CHUNK = 2, LANE_COLS = 0;       // 4 words = 2 columns per chunk; tiles are always whole
   static constexpr int NTOT = 4, NACC = 8;
   using Step = uint4;
 
