@@ -25,7 +25,8 @@ namespace b200q {
 
 static constexpr int kTcThreads = 384;
 static constexpr int kDqWarps = 8;      // dequant + epilogue warps (two per TMEM lane quadrant)
-static constexpr int kNS = 4;         // input stages (X tile + packed W tile)
+static constexpr int kNSMax = 8;      // input stages (X tile + packed W tile): 8 for TT <= 128, 5 for TT = 256
+__host__ __device__ constexpr int tc_stages(int tt) { return tt <= 128 ? 8 : 5; }
 static constexpr int kNA = 4;         // A stages in TMEM (64 k = 32 columns each)
 static constexpr int kBK = 64;        // k per stage
 static constexpr int kBN = 128;       // output columns per CTA (= UMMA M)
@@ -38,7 +39,7 @@ struct TcParams {
   int M;
   PeerOut out;
   int64_t ldy, n_offset;
-  int kblocks, gshift, group32;
+  int kblocks, gshift, group32, ns;   // ns: input stages actually used (<= kNSMax, sized to fit shared memory)
   int off_x, off_w, off_sc, off_zq, off_bar;
   int* err;
 };
@@ -137,7 +138,7 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
 }
 
 template <int TT, int BITS>
-__global__ void __launch_bounds__(kTcThreads, TT <= 128 ? 2 : 1)
+__global__ void __launch_bounds__(kTcThreads, TT <= 64 ? 2 : 1)
 gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const TcParams p) {
   extern __shared__ __align__(1024) char smem_raw[];
   char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-byte alignment
@@ -146,8 +147,9 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   __half* sc = reinterpret_cast<__half*>(smem + p.off_sc);         // [G][128]
   char* zq = smem + p.off_zq;                                      // [G][128] nibbles (64 B) | [G][128] fp16
   uint64_t* full_in = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-  uint64_t* empty_in = full_in + kNS;
-  uint64_t* a_full = empty_in + kNS;
+  const int kNS = p.ns;
+  uint64_t* empty_in = full_in + kNSMax;
+  uint64_t* a_full = empty_in + kNSMax;
   uint64_t* a_empty = a_full + kNA;
   uint64_t* acc_full = a_empty + kNA;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -158,7 +160,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   const bool fz = (p.L.layout == B200Q_LAYOUT_HQQ);
 
   if (tid == 0) {
-    for (int s = 0; s < kNS; ++s) { mbar_init(&full_in[s], 1); mbar_init(&empty_in[s], 1 + kDqWarps); }
+    for (int s = 0; s < kNSMax; ++s) { mbar_init(&full_in[s], 1); mbar_init(&empty_in[s], 1 + kDqWarps); }
     for (int s = 0; s < kNA; ++s) { mbar_init(&a_full[s], kDqWarps); mbar_init(&a_empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
@@ -200,12 +202,14 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < p.kblocks; ++kb) {
-        const int s = kb % kNS;
-        if (!mbar_wait_bounded(&empty_in[s], ((kb / kNS) + 1) & 1, p.err, 1)) break;
+        if (!mbar_wait_bounded(&empty_in[s], ph ^ 1u, p.err, 1)) break;
         mbar_expect_tx(&full_in[s], X_BYTES + W_BYTES);
         tma_load_2d(xst + (size_t)s * X_BYTES, &xmap, &full_in[s], kb * kBK, tok0);
         tma_load_2d(wst + (size_t)s * (W_BYTES / 4), &wmap, &full_in[s], n0, kb * RS);
+        if (++s == kNS) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -213,9 +217,11 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       // instruction descriptor: D=f32, A=B=f16, both K-major, N=TT, M=128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(kBN >> 4) << 24);
       bool ok = true;
+      int s = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < p.kblocks && ok; ++kb) {
-        const int s = kb % kNS, sa = kb % kNA;
-        ok = mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 2) && mbar_wait_bounded(&a_full[sa], (kb / kNA) & 1, p.err, 3);
+        const int sa = kb % kNA;
+        ok = mbar_wait_bounded(&full_in[s], ph, p.err, 2) && mbar_wait_bounded(&a_full[sa], (kb / kNA) & 1, p.err, 3);
         tc_fence_after();
         const uint64_t bdesc = umma_desc_k_sw128(smem_u32(xst + (size_t)s * X_BYTES));
 #pragma unroll
@@ -223,6 +229,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
           tc_mma_ts(tmem, tmem + kACol + sa * 32 + j * 8, bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
         tc_commit(&empty_in[s]);
         tc_commit(&a_empty[sa]);
+        if (++s == kNS) { s = 0; ph ^= 1u; }
       }
       tc_commit(acc_full);
     }
@@ -241,9 +248,11 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     // (h - (1024+z)) * s   [h = 1024+q]   or, for float zeros, ((h - 1024) - z) * s
     auto fin_lo = [&](uint32_t h) { uint32_t d = hsub2_u(h, c_lo); if (fz) d = hsub2_u(d, z2); return hmul2_u(d, s2); };
     auto fin_hi = [&](uint32_t h) { uint32_t d = hfma2_u(h, H_1_16, c_hi); if (fz) d = hsub2_u(d, z2); return hmul2_u(d, s2); };
+    int s = 0;
+    uint32_t ph = 0;
     for (int kb = 0; kb < p.kblocks; ++kb) {
-      const int s = kb % kNS, sa = kb % kNA;
-      mbar_wait_bounded(&full_in[s], (kb / kNS) & 1, p.err, 4);
+      const int sa = kb % kNA;
+      mbar_wait_bounded(&full_in[s], ph, p.err, 4);
       uint32_t w[WH];
       const uint32_t* ws = ws_lane + (size_t)s * (W_BYTES / 4);
 #pragma unroll
@@ -303,6 +312,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       mbar_wait_bounded(&a_empty[sa], ((kb / kNA) + 1) & 1, p.err, 5);
       tc_st16(a_dst + sa * 32, a);
       pending_sa = sa;
+      if (++s == kNS) { s = 0; ph ^= 1u; }
     }
     if (pending_sa >= 0) {
       tc_wait_st();
@@ -429,8 +439,14 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   p.err = g_err_flag;
   const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN * BITS / 8;
   int off = 0;
-  p.off_x = off; off += kNS * TT * kBK * 2;
-  p.off_w = off; off += kNS * (kBK * BITS / 32) * kBN * 4;
+  const int stage_bytes = TT * kBK * 2 + (kBK * BITS / 32) * kBN * 4;
+  const int fixed_bytes = L.G * (kBN * 2 + zq_row) + 64 + 256 + 1024;
+  int ns = tc_stages(TT);
+  while (ns > 2 && ns * stage_bytes + fixed_bytes > 220 * 1024) --ns;
+  if (ns * stage_bytes + fixed_bytes > 220 * 1024) return cudaErrorInvalidValue;
+  p.ns = ns;
+  p.off_x = off; off += ns * TT * kBK * 2;
+  p.off_w = off; off += ns * (kBK * BITS / 32) * kBN * 4;
   p.off_sc = off; off += L.G * kBN * 2;
   off = (off + 15) & ~15;
   p.off_zq = off; off += L.G * zq_row;
