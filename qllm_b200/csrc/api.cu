@@ -56,6 +56,7 @@ enum { KERNEL_GEMV_MMA = 1, KERNEL_GEMM_TC = 2, KERNEL_GENERIC = 3 };
 
 // Tuning/diagnostic switches, read once: B200Q_GEMV=v1 selects the bulk-copy/mbarrier decode kernel
 // (gemv_mma.cu), =v2 the register-prefetch variant of gemv_rp.cu; default is its cp.async/smem variant.
+static bool g_force_fma = false;
 static int gemv_variant() {
   static int v = -1;
   if (v < 0) {
@@ -64,6 +65,7 @@ static int gemv_variant() {
     if (e && e[0] == 'v') gemv_fma_set_max_m(0);        // any explicit B200Q_GEMV=v* disables the FMA kernel
     const char* fm = getenv("B200Q_FMA_MAX_M");
     if (fm) gemv_fma_set_max_m(atoi(fm));
+    g_force_fma = getenv("B200Q_FORCE_FMA") != nullptr;
     const char* kb = getenv("B200Q_SLICE_KB");
     gemv_rp_set_smem(!(e && e[0] == 'v' && e[1] == '2'), kb ? atoi(kb) : 0);   // v2 = register prefetch, default = smem
     const char* ms = getenv("B200Q_MIN_STEPS");
@@ -119,8 +121,16 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   a.L = V; a.x = (const __half*)x; a.ldx = ldx; a.M = (int)M; a.y = (__half*)y; a.ldy = ldy; a.n_offset = n_offset;
   a.workspace = ws; a.workspace_bytes = ws_bytes; a.stream = (cudaStream_t)stream;
   if (kern == KERNEL_GEMV_MMA) {
-    if (gemv_variant() == 2 && gemv_fma_supported(V, (int)M, a.x, ldx)) return cuda_status(launch_gemv_fma(a, peers));
-    if (gemv_variant() == 2 && gemv_rp_supported(V, (int)M, a.x, ldx)) return cuda_status(launch_gemv_rp(a, peers));
+    if (gemv_variant() == 2) {
+      // Measured on B200 (profiles/README.md): the MMA kernel with the packed slice staged in shared memory wins
+      // while its slice leaves >= 2 CTAs per SM; for long-K layers (slice > 96 KB) the register-prefetch FMA
+      // kernel wins at M <= 2.
+      const bool rp_ok = gemv_rp_supported(V, (int)M, a.x, ldx);
+      const bool fma_ok = gemv_fma_supported(V, (int)M, a.x, ldx);
+      const bool prefer_fma = fma_ok && (!rp_ok || g_force_fma || gemv_rp_smem_bytes(V, (int)M) > 96 * 1024);
+      if (prefer_fma) return cuda_status(launch_gemv_fma(a, peers));
+      if (rp_ok) return cuda_status(launch_gemv_rp(a, peers));
+    }
     return cuda_status(launch_gemv_mma(a, peers));
   }
   if (kern == KERNEL_GEMM_TC) return cuda_status(launch_gemm_tc(a, peers));

@@ -695,6 +695,12 @@ bool gemv_rp_supported(const LayerView& L, int M, const __half* x, int64_t ldx) 
   return true;
 }
 
+// shared-memory footprint of the plan (0 if unsupported): lets the dispatcher avoid >1-wave configurations
+int gemv_rp_smem_bytes(const LayerView& L, int M) {
+  RpPlan pl;
+  return rp_plan(L, M, pl) ? pl.smem_bytes : 0;
+}
+
 void gemv_rp_set_max_cluster(int c) { g_rp_max_cluster = c < 1 ? 1 : (c > 8 ? 8 : c); }
 void gemv_rp_set_smem(bool on, int slice_kb) { g_rp_smem = on; if (slice_kb > 0) g_rp_slice_kb = slice_kb; }
 void gemv_rp_set_min_steps(int n) { g_rp_min_steps = n; }

@@ -48,6 +48,7 @@ cudaError_t launch_gemv_mma(const LinearArgs& a, const PeerOut* peers);
 bool gemv_rp_supported(const LayerView& L, int M, const __half* x, int64_t ldx);
 cudaError_t launch_gemv_rp(const LinearArgs& a, const PeerOut* peers);
 void gemv_rp_set_max_cluster(int c);
+int gemv_rp_smem_bytes(const LayerView& L, int M);
 void gemv_rp_set_smem(bool on, int slice_kb);
 void gemv_rp_set_min_steps(int n);
 void gemv_rp_set_debug(unsigned long long* buf, size_t cap_entries);
