@@ -239,7 +239,11 @@ const char* b200q_strerror(int status) {
 
 int b200q_last_cuda_error(void) { return g_last_cuda.load(); }
 /* diagnostic: per-CTA phase timestamps of the decode kernel (8 x u64 per CTA); NULL disables */
-void b200q_debug_set_timeline(void* device_buf, size_t bytes) { gemv_variant(); gemv_rp_set_debug((unsigned long long*)device_buf, bytes / 8); }
+void b200q_debug_set_timeline(void* device_buf, size_t bytes) {
+  gemv_variant();
+  gemv_rp_set_debug((unsigned long long*)device_buf, bytes / 8);
+  gemm_tc_set_debug(bytes >= 64 * 1024 ? (unsigned long long*)device_buf : nullptr);   // GEMM: CTA(0,0), 8 stamps per k-block
+}
 int b200q_version(void) { return B200Q_VERSION; }
 
 }  // extern "C"

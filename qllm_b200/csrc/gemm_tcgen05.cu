@@ -42,7 +42,16 @@ struct TcParams {
   int kblocks, gshift, group32, ns;   // ns: input stages actually used (<= kNSMax, sized to fit shared memory)
   int off_x, off_w, off_sc, off_zq, off_bar;
   int* err;
+  unsigned long long* dbg;   // diagnostic: CTA (0,0) records per-k-block phase stamps (nullptr in production)
 };
+
+__device__ __forceinline__ unsigned long long tc_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// stamps: [kb][0..3] dequant warp 4 (inputs landed, ALU done, A stage free, TMEM store issued), [kb][4..5] MMA thread
+#define TC_STAMP(kb, i) do { if (dbg_on) p.dbg[(size_t)(kb) * 8 + (i)] = tc_gtime(); } while (0)
 
 // ---- small PTX wrappers -----------------------------------------------------------------------
 #ifdef B200Q_BOUNDED_WAITS     // bring-up aid: every wait gives up after kSpinLimit polls and records a code
@@ -158,6 +167,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   const int n0 = blockIdx.x * kBN;
   const int tok0 = blockIdx.y * TT;
   const bool fz = (p.L.layout == B200Q_LAYOUT_HQQ);
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (tid == 0) {
     for (int s = 0; s < kNSMax; ++s) { mbar_init(&full_in[s], 1); mbar_init(&empty_in[s], 1 + kDqWarps); }
@@ -222,6 +232,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       for (int kb = 0; kb < p.kblocks && ok; ++kb) {
         const int sa = kb % kNA;
         ok = mbar_wait_bounded(&full_in[s], ph, p.err, 2) && mbar_wait_bounded(&a_full[sa], (kb / kNA) & 1, p.err, 3);
+        TC_STAMP(kb, 4);
         tc_fence_after();
         const uint64_t bdesc = umma_desc_k_sw128(smem_u32(xst + (size_t)s * X_BYTES));
 #pragma unroll
@@ -229,6 +240,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
           tc_mma_ts(tmem, tmem + kACol + sa * 32 + j * 8, bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
         tc_commit(&empty_in[s]);
         tc_commit(&a_empty[sa]);
+        TC_STAMP(kb, 5);
         if (++s == kNS) { s = 0; ph ^= 1u; }
       }
       tc_commit(acc_full);
@@ -253,6 +265,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     for (int kb = 0; kb < p.kblocks; ++kb) {
       const int sa = kb % kNA;
       mbar_wait_bounded(&full_in[s], ph, p.err, 4);
+      if (warp == 4 && lane == 0) TC_STAMP(kb, 0);
       uint32_t w[WH];
       const uint32_t* ws = ws_lane + (size_t)s * (W_BYTES / 4);
 #pragma unroll
@@ -302,6 +315,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
           }
         }
       }
+      if (warp == 4 && lane == 0) TC_STAMP(kb, 1);
       // publish the previous stage only now: its TMEM store has had this k-block's ALU work to complete
       if (pending_sa >= 0) {
         tc_wait_st();
@@ -310,7 +324,9 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         mbar_arrive_lane0(&a_full[pending_sa], lane);
       }
       mbar_wait_bounded(&a_empty[sa], ((kb / kNA) + 1) & 1, p.err, 5);
+      if (warp == 4 && lane == 0) TC_STAMP(kb, 2);
       tc_st16(a_dst + sa * 32, a);
+      if (warp == 4 && lane == 0) TC_STAMP(kb, 3);
       pending_sa = sa;
       if (++s == kNS) { s = 0; ph ^= 1u; }
     }
@@ -375,6 +391,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+static unsigned long long* g_tc_dbg = nullptr;
+void gemm_tc_set_debug(unsigned long long* buf) { g_tc_dbg = buf; }
 static int* g_err_flag = nullptr;      // device int, lazily allocated (diagnostic only)
 int gemm_tc_last_error() {
   int v = 0;
@@ -437,6 +455,7 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   p.group32 = (L.group % 32 == 0) ? 1 : 0;
   if ((L.group & (L.group - 1)) == 0) { int sh = 0; while ((1 << sh) < L.group) ++sh; p.gshift = sh; }
   p.err = g_err_flag;
+  p.dbg = g_tc_dbg;
   const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN * BITS / 8;
   int off = 0;
   const int stage_bytes = TT * kBK * 2 + (kBK * BITS / 32) * kBN * 4;

@@ -545,10 +545,15 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
   };
 
   if (SM) {
+    // software pipeline: the next step's packed words are read from shared memory before this step's math
+    typename T::Step wn;
+    if (s_begin < s_end) T::load_smem(w[0], wtile, s_begin - cta_s0, lane);
 #pragma unroll 2
     for (int s = s_begin; s < s_end; ++s) {
-      T::load_smem(w[0], wtile, s - cta_s0, lane);
+      wn = w[0];
+      if (s + 1 < s_end) T::load_smem(wn, wtile, s + 1 - cta_s0, lane);
       do_step(w[0], s);
+      w[0] = wn;
     }
   } else {
 #pragma unroll

@@ -39,7 +39,7 @@ def main():
             x = torch.randn(M, K, dtype=torch.float16, device=dev)
             la = [rand_layer("GEMM", 4, 128, K, N, dev, s) for s in range(copies)]
             lg = [rand_layer("GPTQ", 4, 128, K, N, dev, s) for s in range(copies)]
-            lm = [rand_layer("MARLIN", 4, 128, K, N, dev, s) for s in range(copies)] if N % 256 == 0 else None
+            lm = None
             it = [0]
 
             def nxt(ls):
@@ -53,7 +53,7 @@ def main():
             else:
                 r["ref_ort_dequant_matmul_us"] = timeit(lambda: (lambda l: torch.matmul(x, ort.dequant(l.qweight, l.scales, l.qzeros, None, 128, 4, K, 0)))(nxt(lg)))
             r["b200q_gptq_us"] = timeit(lambda: nxt(lg)(x))
-            if lm and M <= 16:          # the reference Marlin kernel hits an illegal instruction on sm_100 for M > 16
+            if False and lm:            # the reference Marlin kernel raises cudaErrorIllegalInstruction on B200 (sm_100)
                 ws = torch.zeros(N // 128 * 16, dtype=torch.int32, device=dev)
                 C = torch.empty(M, N, dtype=torch.float16, device=dev)
                 r["ref_marlin_us"] = timeit(lambda: (lambda l: awq.mul(x, l.qweight, C, l.scales, ws, -1, -1, -1, 16))(nxt(lm)))
