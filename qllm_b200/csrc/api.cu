@@ -123,11 +123,11 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   if (kern == KERNEL_GEMV_MMA) {
     if (gemv_variant() == 2) {
       // Measured on B200 (profiles/README.md): the MMA kernel with the packed slice staged in shared memory wins
-      // while its slice leaves >= 2 CTAs per SM; for long-K layers (slice > 96 KB) the register-prefetch FMA
+      // while its slice leaves >= 2 CTAs per SM; for long-K layers (slice > 112 KB) the register-prefetch FMA
       // kernel wins at M <= 2.
       const bool rp_ok = gemv_rp_supported(V, (int)M, a.x, ldx);
       const bool fma_ok = gemv_fma_supported(V, (int)M, a.x, ldx);
-      const bool prefer_fma = fma_ok && (!rp_ok || g_force_fma || gemv_rp_smem_bytes(V, (int)M) > 96 * 1024);
+      const bool prefer_fma = fma_ok && (!rp_ok || g_force_fma || gemv_rp_smem_bytes(V, (int)M) > 112 * 1024);
       if (prefer_fma) return cuda_status(launch_gemv_fma(a, peers));
       if (rp_ok) return cuda_status(launch_gemv_rp(a, peers));
     }
