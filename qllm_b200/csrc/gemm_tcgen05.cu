@@ -23,11 +23,13 @@
 
 namespace b200q {
 
-static constexpr int kTcThreads = 384;
-static constexpr int kDqWarps = 8;      // dequant + epilogue warps (two per TMEM lane quadrant)
-static constexpr int kNSMax = 8;      // input stages (X tile + packed W tile): 8 for TT <= 128, 5 for TT = 256
+static constexpr int kDqWarps = 8;      // dequant warps that cooperate on one k-block (two per TMEM lane quadrant)
+static constexpr int kDqPar = 3;        // k-blocks dequantised concurrently: team p takes k-blocks p, p+kDqPar, ...
+static constexpr int kTcThreads = (4 + kDqWarps * kDqPar) * 32;   // 896
+static constexpr int kNSXMax = 8;     // X-tile stages (TMA -> MMA):      8 for TT <= 128, 5 for TT = 256
+static constexpr int kNSWMax = 16;    // packed-W stages (TMA -> dequant): sized to what shared memory leaves
 __host__ __device__ constexpr int tc_stages(int tt) { return tt <= 128 ? 8 : 5; }
-static constexpr int kNA = 4;         // A stages in TMEM (64 k = 32 columns each)
+static constexpr int kNA = 8;         // A stages in TMEM (64 k = 32 columns each)
 static constexpr int kBK = 64;        // k per stage
 static constexpr int kBN = 128;       // output columns per CTA (= UMMA M)
 static constexpr uint32_t kSpinLimit = 4u << 20;
@@ -39,7 +41,8 @@ struct TcParams {
   int M;
   PeerOut out;
   int64_t ldy, n_offset;
-  int kblocks, gshift, group32, ns;   // ns: input stages actually used (<= kNSMax, sized to fit shared memory)
+  int kblocks, gshift, group32, nsx, nsw;   // nsx / nsw: X and W ring depths actually used
+  float inv_group;   // ns: input stages actually used (<= kNSMax, sized to fit shared memory)
   int off_x, off_w, off_sc, off_zq, off_bar;
   int* err;
   unsigned long long* dbg;   // diagnostic: CTA (0,0) records per-k-block phase stamps (nullptr in production)
@@ -51,7 +54,7 @@ __device__ __forceinline__ unsigned long long tc_gtime() {
   return t;
 }
 // stamps: [kb][0..3] dequant warp 4 (inputs landed, ALU done, A stage free, TMEM store issued), [kb][4..5] MMA thread
-#define TC_STAMP(kb, i) do { if (dbg_on) p.dbg[(size_t)(kb) * 8 + (i)] = tc_gtime(); } while (0)
+#define TC_STAMP(kb, i) do { if (DBG && dbg_on) p.dbg[(size_t)(kb) * 8 + (i)] = tc_gtime(); } while (0)
 
 // ---- small PTX wrappers -----------------------------------------------------------------------
 #ifdef B200Q_BOUNDED_WAITS     // bring-up aid: every wait gives up after kSpinLimit polls and records a code
@@ -146,8 +149,8 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
       : "memory");
 }
 
-template <int TT, int BITS>
-__global__ void __launch_bounds__(kTcThreads, TT <= 64 ? 2 : 1)
+template <int TT, int BITS, bool FZ, bool DBG>
+__global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap, const TcParams p) {
   extern __shared__ __align__(1024) char smem_raw[];
   char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SW128 tiles need 1024-byte alignment
@@ -155,10 +158,11 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   uint32_t* wst = reinterpret_cast<uint32_t*>(smem + p.off_w);     // kNS x [64*BITS/32][128] words
   __half* sc = reinterpret_cast<__half*>(smem + p.off_sc);         // [G][128]
   char* zq = smem + p.off_zq;                                      // [G][128] nibbles (64 B) | [G][128] fp16
-  uint64_t* full_in = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-  const int kNS = p.ns;
-  uint64_t* empty_in = full_in + kNSMax;
-  uint64_t* a_full = empty_in + kNSMax;
+  uint64_t* full_x = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* empty_x = full_x + kNSXMax;
+  uint64_t* full_w = empty_x + kNSXMax;
+  uint64_t* empty_w = full_w + kNSWMax;
+  uint64_t* a_full = empty_w + kNSWMax;
   uint64_t* a_empty = a_full + kNA;
   uint64_t* acc_full = a_empty + kNA;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -166,17 +170,17 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * kBN;
   const int tok0 = blockIdx.y * TT;
-  const bool fz = (p.L.layout == B200Q_LAYOUT_HQQ);
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (tid == 0) {
-    for (int s = 0; s < kNSMax; ++s) { mbar_init(&full_in[s], 1); mbar_init(&empty_in[s], 1 + kDqWarps); }
+    for (int s = 0; s < kNSXMax; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
+    for (int s = 0; s < kNSWMax; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], kDqWarps); }
     for (int s = 0; s < kNA; ++s) { mbar_init(&a_full[s], kDqWarps); mbar_init(&a_empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TT > 128 ? 512 : 256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // group tables for this CTA's 128 columns (all groups)
@@ -184,7 +188,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     const int g = idx / kBN, n = idx % kBN;
     sc[idx] = (n0 + n < p.L.N) ? __ldg(p.L.s + (size_t)g * p.L.N + n0 + n) : __float2half(0.f);
   }
-  if (fz) {
+  if (FZ) {
     for (int idx = tid; idx < p.L.G * kBN; idx += kTcThreads) {
       const int g = idx / kBN, n = idx % kBN;
       reinterpret_cast<__half*>(zq)[idx] =
@@ -210,16 +214,26 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   constexpr uint32_t X_BYTES = TT * kBK * 2, W_BYTES = RS * kBN * 4;
   constexpr int kACol = TT;                        // A stages sit right after the TT accumulator columns
 
-  if (warp == 0) {
+  if (warp == 0) {                         // X producer: the ring only spans TMA latency + MMA lag
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < p.kblocks; ++kb) {
-        if (!mbar_wait_bounded(&empty_in[s], ph ^ 1u, p.err, 1)) break;
-        mbar_expect_tx(&full_in[s], X_BYTES + W_BYTES);
-        tma_load_2d(xst + (size_t)s * X_BYTES, &xmap, &full_in[s], kb * kBK, tok0);
-        tma_load_2d(wst + (size_t)s * (W_BYTES / 4), &wmap, &full_in[s], n0, kb * RS);
-        if (++s == kNS) { s = 0; ph ^= 1u; }
+        if (!mbar_wait_bounded(&empty_x[s], ph ^ 1u, p.err, 1)) break;
+        mbar_expect_tx(&full_x[s], X_BYTES);
+        tma_load_2d(xst + (size_t)s * X_BYTES, &xmap, &full_x[s], kb * kBK, tok0);
+        if (++s == p.nsx) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 3) {                  // packed-W producer: runs far ahead (HBM latency + dequant + A ring)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        if (!mbar_wait_bounded(&empty_w[s], ph ^ 1u, p.err, 7)) break;
+        mbar_expect_tx(&full_w[s], W_BYTES);
+        tma_load_2d(wst + (size_t)s * (W_BYTES / 4), &wmap, &full_w[s], n0, kb * RS);
+        if (++s == p.nsw) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -231,23 +245,25 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       uint32_t ph = 0;
       for (int kb = 0; kb < p.kblocks && ok; ++kb) {
         const int sa = kb % kNA;
-        ok = mbar_wait_bounded(&full_in[s], ph, p.err, 2) && mbar_wait_bounded(&a_full[sa], (kb / kNA) & 1, p.err, 3);
+        ok = mbar_wait_bounded(&full_x[s], ph, p.err, 2) && mbar_wait_bounded(&a_full[sa], (kb / kNA) & 1, p.err, 3);
         TC_STAMP(kb, 4);
         tc_fence_after();
         const uint64_t bdesc = umma_desc_k_sw128(smem_u32(xst + (size_t)s * X_BYTES));
 #pragma unroll
         for (int j = 0; j < kBK / 16; ++j)
           tc_mma_ts(tmem, tmem + kACol + sa * 32 + j * 8, bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
-        tc_commit(&empty_in[s]);
+        tc_commit(&empty_x[s]);
         tc_commit(&a_empty[sa]);
         TC_STAMP(kb, 5);
-        if (++s == kNS) { s = 0; ph ^= 1u; }
+        if (++s == p.nsx) { s = 0; ph ^= 1u; }
       }
       tc_commit(acc_full);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;                     // TMEM lane quadrant this warp may access (warp id % 4)
-    const int half = (warp - 4) >> 2;           // which 4 of the 8 words of a stage / which token chunks
+    const int half = ((warp - 4) >> 2) & 1;     // which half (32 k) of a stage
+    const int par = (warp - 4) >> 3;            // team: k-blocks par, par + kDqPar, ...
+    const int eidx = (warp - 4) >> 2;           // epilogue slot 0 .. 2*kDqPar-1 (token chunks eidx, eidx + 2*kDqPar, ...)
     const int n = q * 32 + lane;                // column within the CTA tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int gcur = -1;
@@ -255,101 +271,106 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     bool ok = true;
     const uint32_t* ws_lane = wst + (WH * half) * kBN + n;
     const uint32_t a_dst = tmem + lane_addr + kACol + half * 16;
-    int pending_sa = -1;                             // A stage whose tcgen05.st has been issued but not yet published
     constexpr uint32_t ZMASK = (1u << BITS) - 1u;
-    // (h - (1024+z)) * s   [h = 1024+q]   or, for float zeros, ((h - 1024) - z) * s
-    auto fin_lo = [&](uint32_t h) { uint32_t d = hsub2_u(h, c_lo); if (fz) d = hsub2_u(d, z2); return hmul2_u(d, s2); };
-    auto fin_hi = [&](uint32_t h) { uint32_t d = hfma2_u(h, H_1_16, c_hi); if (fz) d = hsub2_u(d, z2); return hmul2_u(d, s2); };
-    int s = 0;
-    uint32_t ph = 0;
-    for (int kb = 0; kb < p.kblocks; ++kb) {
+    const int zbit = n * BITS;
+    const uint32_t* zq_lane = reinterpret_cast<const uint32_t*>(zq) + (zbit >> 5);
+    // group constants of this lane's column: s2 = (s,s); integer zeros folded into the magic constants,
+    // (h - (1024+z)) * s  [h = 1024+q];  float zeros (HQQ): ((h - 1024) - z) * s
+    auto load_group = [&](int gi) {
+      s2 = dup_half(sc[gi * kBN + n]);
+      if (FZ) {
+        z2 = dup_half(reinterpret_cast<const __half*>(zq)[gi * kBN + n]);
+        c_lo = MAGIC; c_hi = 0xD400D400u;
+      } else {
+        const uint32_t z = (((zq_lane[gi * (kBN * BITS / 32)] >> (zbit & 31)) & ZMASK) + (uint32_t)p.L.zero_bias) & ZMASK;
+        c_lo = (0x6400u | z) * 0x00010001u;
+        c_hi = (0xD400u + (z << 4)) * 0x00010001u;
+      }
+    };
+    auto fin_lo = [&](uint32_t h) { uint32_t d = hsub2_u(h, c_lo); if (FZ) d = hsub2_u(d, z2); return hmul2_u(d, s2); };
+    auto fin_hi = [&](uint32_t h) { uint32_t d = hfma2_u(h, H_1_16, c_hi); if (FZ) d = hsub2_u(d, z2); return hmul2_u(d, s2); };
+    // one packed word -> 16/BITS... fp16 pairs in MMA k order, written to a[r * (P/2) ...]
+    auto dq_word = [&](uint32_t wv, uint32_t* o) {
+      if (BITS == 4) {
+        const uint32_t hi = wv >> 8;
+        const uint32_t p0 = fin_lo(and_or(wv, LO4, MAGIC));             // (k0,k4)
+        const uint32_t p1 = fin_hi(and_or(wv, HI4, MAGIC));             // (k1,k5)
+        const uint32_t p2 = fin_lo(and_or(hi, LO4, MAGIC));             // (k2,k6)
+        const uint32_t p3 = fin_hi(and_or(hi, HI4, MAGIC));             // (k3,k7)
+        o[0] = prmt(p0, p1, 0x5410);    // (k0,k1)
+        o[1] = prmt(p2, p3, 0x5410);    // (k2,k3)
+        o[2] = prmt(p0, p1, 0x7632);    // (k4,k5)
+        o[3] = prmt(p2, p3, 0x7632);    // (k6,k7)
+      } else if (BITS == 8) {
+        o[0] = fin_lo(prmt(wv, MAGIC, 0x5150));                         // (k0,k1): bytes -> 1024+q
+        o[1] = fin_lo(prmt(wv, MAGIC, 0x5352));                         // (k2,k3)
+      } else {                                                           // 2-bit: E_i = (k_i, k_{i+8})
+        uint32_t e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = fin_lo(and_or(wv >> (2 * i), 0x00030003u, MAGIC));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o[j] = prmt(e[2 * j], e[2 * j + 1], 0x5410);                   // (k_2j, k_2j+1)
+          o[4 + j] = prmt(e[2 * j], e[2 * j + 1], 0x7632);               // (k_8+2j, k_9+2j)
+        }
+      }
+    };
+    auto group_at = [&](int k) { return p.gshift >= 0 ? (k >> p.gshift) : (int)(((float)k + 0.5f) * p.inv_group); };
+    const int kNS = p.nsw;
+    int s = par % kNS;
+    uint32_t ph = (uint32_t)((par / kNS) & 1);
+    for (int kb = par; kb < p.kblocks; kb += kDqPar) {
       const int sa = kb % kNA;
-      mbar_wait_bounded(&full_in[s], ph, p.err, 4);
+      mbar_wait_bounded(&full_w[s], ph, p.err, 4);
       if (warp == 4 && lane == 0) TC_STAMP(kb, 0);
       uint32_t w[WH];
       const uint32_t* ws = ws_lane + (size_t)s * (W_BYTES / 4);
 #pragma unroll
       for (int r = 0; r < WH; ++r) w[r] = ws[r * kBN];
       __syncwarp();
-      mbar_arrive_lane0(&empty_in[s], lane);
+      mbar_arrive_lane0(&empty_w[s], lane);
       uint32_t a[16];
+      const int k0 = kb * kBK + 32 * half;
+      if (p.group32) {                                   // the 32 k of this half-stage share one group (warp-uniform)
+        const int gi = group_at(k0);
+        if (gi != gcur) { gcur = gi; load_group(gi); }
 #pragma unroll
-      for (int r = 0; r < WH; ++r) {
-        const int k = kb * kBK + 32 * half + (p.group32 ? 0 : P * r);     // group32: 32 consecutive k share a group
-        const int gi = p.gshift >= 0 ? (k >> p.gshift) : (k / p.L.group);
-        if ((r == 0 || !p.group32) && gi != gcur) {
-          gcur = gi;
-          s2 = dup_half(sc[gi * kBN + n]);
-          if (fz) {
-            z2 = dup_half(reinterpret_cast<const __half*>(zq)[gi * kBN + n]);
-            c_lo = MAGIC; c_hi = 0xD400D400u;
-          } else {
-            const int bit = n * BITS;
-            const uint32_t zw = reinterpret_cast<const uint32_t*>(zq)[gi * (kBN * BITS / 32) + (bit >> 5)];
-            const uint32_t z = (((zw >> (bit & 31)) & ZMASK) + (uint32_t)p.L.zero_bias) & ZMASK;
-            c_lo = (0x6400u | z) * 0x00010001u;
-            c_hi = (0xD400u + (z << 4)) * 0x00010001u;
-          }
-        }
-        if (BITS == 4) {
-          const uint32_t lo = w[r], hi = w[r] >> 8;
-          const uint32_t p0 = fin_lo(and_or(lo, LO4, MAGIC));             // (k0,k4)
-          const uint32_t p1 = fin_hi(and_or(lo, HI4, MAGIC));             // (k1,k5)
-          const uint32_t p2 = fin_lo(and_or(hi, LO4, MAGIC));             // (k2,k6)
-          const uint32_t p3 = fin_hi(and_or(hi, HI4, MAGIC));             // (k3,k7)
-          a[4 * r + 0] = prmt(p0, p1, 0x5410);    // (k0,k1)
-          a[4 * r + 1] = prmt(p2, p3, 0x5410);    // (k2,k3)
-          a[4 * r + 2] = prmt(p0, p1, 0x7632);    // (k4,k5)
-          a[4 * r + 3] = prmt(p2, p3, 0x7632);    // (k6,k7)
-        } else if (BITS == 8) {
-          a[2 * r + 0] = fin_lo(prmt(w[r], MAGIC, 0x5150));               // (k0,k1): bytes -> 1024+q
-          a[2 * r + 1] = fin_lo(prmt(w[r], MAGIC, 0x5352));               // (k2,k3)
-        } else {                                                           // 2-bit: E_i = (k_i, k_{i+8})
-          uint32_t e[8];
+        for (int r = 0; r < WH; ++r) dq_word(w[r], a + r * (P / 2));
+      } else {                                           // small groups: resolve per packed word
 #pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = fin_lo(and_or(w[r] >> (2 * i), 0x00030003u, MAGIC));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            a[8 * r + j] = prmt(e[2 * j], e[2 * j + 1], 0x5410);           // (k_2j, k_2j+1)
-            a[8 * r + 4 + j] = prmt(e[2 * j], e[2 * j + 1], 0x7632);       // (k_8+2j, k_9+2j)
-          }
+        for (int r = 0; r < WH; ++r) {
+          const int gi = group_at(k0 + P * r);
+          if (gi != gcur) { gcur = gi; load_group(gi); }
+          dq_word(w[r], a + r * (P / 2));
         }
       }
       if (warp == 4 && lane == 0) TC_STAMP(kb, 1);
-      // publish the previous stage only now: its TMEM store has had this k-block's ALU work to complete
-      if (pending_sa >= 0) {
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        mbar_arrive_lane0(&a_full[pending_sa], lane);
-      }
       mbar_wait_bounded(&a_empty[sa], ((kb / kNA) + 1) & 1, p.err, 5);
       if (warp == 4 && lane == 0) TC_STAMP(kb, 2);
+      tc_fence_after();
       tc_st16(a_dst + sa * 32, a);
-      if (warp == 4 && lane == 0) TC_STAMP(kb, 3);
-      pending_sa = sa;
-      if (++s == kNS) { s = 0; ph ^= 1u; }
-    }
-    if (pending_sa >= 0) {
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      mbar_arrive_lane0(&a_full[pending_sa], lane);
+      mbar_arrive_lane0(&a_full[sa], lane);
+      if (warp == 4 && lane == 0) TC_STAMP(kb, 3);
+      s += kDqPar;
+      while (s >= kNS) { s -= kNS; ph ^= 1u; }
     }
     // ---- epilogue: TMEM -> registers -> fp16 -> shared (transpose) -> 16-byte coalesced stores ----
     ok = __all_sync(0xffffffffu, ok && mbar_wait_bounded(acc_full, 0, p.err, 6));
     tc_fence_after();
     const float bias = (p.L.bias && (n0 + n) < p.L.N) ? __half2float(__ldg(p.L.bias + n0 + n)) : 0.f;
-    __half* stg = reinterpret_cast<__half*>(xst) + (size_t)half * 32 * (kBN + 8);     // [32 tok][128+8 n], X stages are free now
-    const int tih = (warp - 4 - 4 * half) * 32 + lane;                                 // thread index within this half (0..127)
+    __half* stg = reinterpret_cast<__half*>(xst) + (size_t)eidx * 32 * (kBN + 8);     // [32 tok][128+8 n], X stages are free now
+    const int tih = q * 32 + lane;                                                     // thread index within this slot's 4 warps
 #pragma unroll 1
-    for (int c0 = half * 32; c0 < TT && ok; c0 += 64) {
+    for (int c0 = eidx * 32; c0 < TT && ok; c0 += 64 * kDqPar) {
       uint32_t v[32];
       tc_ld32(tmem + lane_addr + c0, v);
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 32; ++i) stg[(size_t)i * (kBN + 8) + n] = __float2half_rn(__uint_as_float(v[i]) + bias);
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + eidx) : "memory");
       // 32 token rows x 256 B: 16 chunks of 16 B per row, 128 threads -> 4 chunks each
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -361,14 +382,14 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             *reinterpret_cast<uint4*>(p.out.y[qd] + (size_t)tok * p.ldy + p.n_offset + n0 + 8 * ch) = val;
         }
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + eidx) : "memory");
     }
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TT > 128 ? 512 : 256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
   }
 }
 
@@ -418,7 +439,7 @@ bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t l
 
 size_t gemm_tc_workspace(const LayerView&, int64_t) { return 0; }
 
-template <int TT, int BITS>
+template <int TT, int BITS, bool FZ, bool DBG = false>
 static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   const LayerView& L = a.L;
   EncodeTiledFn enc = get_encode();
@@ -454,29 +475,33 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   p.gshift = -1;
   p.group32 = (L.group % 32 == 0) ? 1 : 0;
   if ((L.group & (L.group - 1)) == 0) { int sh = 0; while ((1 << sh) < L.group) ++sh; p.gshift = sh; }
+  p.inv_group = 1.0f / (float)L.group;
   p.err = g_err_flag;
   p.dbg = g_tc_dbg;
   const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN * BITS / 8;
   int off = 0;
   const int stage_bytes = TT * kBK * 2 + (kBK * BITS / 32) * kBN * 4;
-  const int fixed_bytes = L.G * (kBN * 2 + zq_row) + 64 + 256 + 1024;
-  int ns = tc_stages(TT);
-  while (ns > 2 && ns * stage_bytes + fixed_bytes > 220 * 1024) --ns;
-  if (ns * stage_bytes + fixed_bytes > 220 * 1024) return cudaErrorInvalidValue;
-  p.ns = ns;
-  p.off_x = off; off += ns * TT * kBK * 2;
-  p.off_w = off; off += ns * (kBK * BITS / 32) * kBN * 4;
+  const int fixed_bytes = L.G * (kBN * 2 + zq_row) + 64 + 1024 + 1024;
+  const int xb = TT * kBK * 2, wb = (kBK * BITS / 32) * kBN * 4, budget = 220 * 1024 - fixed_bytes;
+  int nsx = tc_stages(TT), nsw = kNSWMax;
+  while (nsw > 6 && nsx * xb + nsw * wb > budget) --nsw;
+  while (nsx > 2 && nsx * xb + nsw * wb > budget) --nsx;
+  if (nsx * xb + nsw * wb > budget) return cudaErrorInvalidValue;
+  (void)stage_bytes;
+  p.nsx = nsx; p.nsw = nsw;
+  p.off_x = off; off += nsx * xb;
+  p.off_w = off; off += nsw * wb;
   p.off_sc = off; off += L.G * kBN * 2;
   off = (off + 15) & ~15;
   p.off_zq = off; off += L.G * zq_row;
   off = (off + 15) & ~15;
-  p.off_bar = off; off += 256;
+  p.off_bar = off; off += 1024;
   const int smem_bytes = off + 1024;   // slack for 1024-byte alignment of the dynamic window
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_gptq_kernel<TT, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_gptq_kernel<TT, BITS, FZ, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
     attr_done[dev & 63] = true;
   }
@@ -485,18 +510,21 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   if ((a.ldy % 8) != 0 || (a.n_offset % 8) != 0) return cudaErrorInvalidValue;     // 16-byte epilogue stores
   dim3 grid((L.N + kBN - 1) / kBN, (a.M + TT - 1) / TT);
   count_launch();
-  gemm_tc_gptq_kernel<TT, BITS><<<grid, kTcThreads, smem_bytes, a.stream>>>(xmap, wmap, p);
+  gemm_tc_gptq_kernel<TT, BITS, FZ, DBG><<<grid, kTcThreads, smem_bytes, a.stream>>>(xmap, wmap, p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers) {
   // M is chunked so that a.M fits int and grid.y <= 65535
+  const bool fz = a.L.layout == B200Q_LAYOUT_HQQ;
+  // diagnostic timeline build: only the TT=128 4-bit integer-zero instantiation carries the stamps
+  if (g_tc_dbg && !fz && a.L.bits == 4 && pick_tt(a.M) == 128) return tc_launch<128, 4, false, true>(a, peers);
 #define B200Q_TC_DISPATCH(BITS)                                  \
   switch (pick_tt(a.M)) {                                       \
-    case 32: return tc_launch<32, BITS>(a, peers);              \
-    case 64: return tc_launch<64, BITS>(a, peers);              \
-    case 256: return tc_launch<256, BITS>(a, peers);            \
-    default: return tc_launch<128, BITS>(a, peers);             \
+    case 32: return (fz ? tc_launch<32, BITS, true>(a, peers) : tc_launch<32, BITS, false>(a, peers));              \
+    case 64: return (fz ? tc_launch<64, BITS, true>(a, peers) : tc_launch<64, BITS, false>(a, peers));              \
+    case 256: return (fz ? tc_launch<256, BITS, true>(a, peers) : tc_launch<256, BITS, false>(a, peers));            \
+    default: return (fz ? tc_launch<128, BITS, true>(a, peers) : tc_launch<128, BITS, false>(a, peers));             \
   }
   if (a.L.bits == 2) { B200Q_TC_DISPATCH(2) }
   if (a.L.bits == 8) { B200Q_TC_DISPATCH(8) }
