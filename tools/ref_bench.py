@@ -15,17 +15,27 @@ import qllm_b200  # noqa: E402
 from tools.microbench import rand_layer  # noqa: E402
 
 
-def timeit(fn, iters=50, warm=5):
-    for _ in range(warm):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / iters
+def timeit(fn, copies, reps=4):
+    """fn(i) enqueues one call on layer copy i.  All copies x reps calls are captured in one CUDA graph, so the number is
+    device time per call with no Python / launch-API overhead on either side and cold weights (copies exceed L2)."""
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for i in range(copies):
+            fn(i)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps):
+                for i in range(copies):
+                    fn(i)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * copies)
 
 
 def main():
@@ -39,25 +49,16 @@ def main():
             x = torch.randn(M, K, dtype=torch.float16, device=dev)
             la = [rand_layer("GEMM", 4, 128, K, N, dev, s) for s in range(copies)]
             lg = [rand_layer("GPTQ", 4, 128, K, N, dev, s) for s in range(copies)]
-            lm = None
-            it = [0]
-
-            def nxt(ls):
-                it[0] += 1
-                return ls[it[0] % copies]
-            r = {"K": K, "N": N, "M": M}
-            r["ref_awq_gemm_us"] = timeit(lambda: (lambda l: awq.gemm_forward_cuda(x, l.qweight, l.scales, l.qzeros, 8))(nxt(la)))
-            r["b200q_awq_us"] = timeit(lambda: nxt(la)(x))
+            r = {"K": K, "N": N, "M": M, "timing": "cuda graph, device time per call"}
+            r["ref_awq_gemm_us"] = timeit(lambda i: awq.gemm_forward_cuda(x, la[i].qweight, la[i].scales, la[i].qzeros, 8), copies)
+            r["b200q_awq_us"] = timeit(lambda i: la[i](x), copies)
             if M <= 8:
-                r["ref_ort_gemv_us"] = timeit(lambda: (lambda l: ort.gemv(x, l.qweight, l.scales, l.qzeros, None, 128, 4, K, 0))(nxt(lg)))
+                r["ref_ort_gemv_us"] = timeit(lambda i: ort.gemv(x, lg[i].qweight, lg[i].scales, lg[i].qzeros, None, 128, 4, K, 0), copies)
             else:
-                r["ref_ort_dequant_matmul_us"] = timeit(lambda: (lambda l: torch.matmul(x, ort.dequant(l.qweight, l.scales, l.qzeros, None, 128, 4, K, 0)))(nxt(lg)))
-            r["b200q_gptq_us"] = timeit(lambda: nxt(lg)(x))
-            if False and lm:            # the reference Marlin kernel raises cudaErrorIllegalInstruction on B200 (sm_100)
-                ws = torch.zeros(N // 128 * 16, dtype=torch.int32, device=dev)
-                C = torch.empty(M, N, dtype=torch.float16, device=dev)
-                r["ref_marlin_us"] = timeit(lambda: (lambda l: awq.mul(x, l.qweight, C, l.scales, ws, -1, -1, -1, 16))(nxt(lm)))
-                r["b200q_marlin_us"] = timeit(lambda: nxt(lm)(x))
+                r["ref_ort_dequant_matmul_us"] = timeit(
+                    lambda i: torch.matmul(x, ort.dequant(lg[i].qweight, lg[i].scales, lg[i].qzeros, None, 128, 4, K, 0)), copies)
+            r["b200q_gptq_us"] = timeit(lambda i: lg[i](x), copies)
+            # the reference Marlin kernel raises cudaErrorIllegalInstruction on B200 (sm_100) and poisons the context: not timed
             rows.append({k: (round(v, 2) if isinstance(v, float) else v) for k, v in r.items()})
             print(json.dumps(rows[-1]), flush=True)
 
