@@ -149,6 +149,15 @@ uint64_t b200q_launch_count(void);
  * appended launch after launch until `bytes` are used.  NULL (default) disables. */
 void b200q_debug_set_timeline(void* device_buf, size_t bytes);
 
+/* Diagnostic only: the decode kernel's launch plan for this layer at batch M (host-side, no CUDA call):
+ * out = {cluster size (CTAs that split K), column tiles, dynamic shared memory bytes per CTA, k-steps}. */
+int b200q_debug_decode_plan(const b200q_layer* layer, int64_t M, int32_t out[4]);
+
+/* Diagnostic / tuning only: override a dispatch or planner switch at run time (same switches as the B200Q_*
+ * environment variables): "force_cluster", "max_cluster", "planner", "fill_cap", "force_fma",
+ * "fma_max_m", "tt256_min_m".  Returns B200Q_ERR_UNSUPPORTED for an unknown name. */
+int b200q_debug_set_option(const char* name, double value);
+
 const char* b200q_strerror(int status);
 int b200q_last_cuda_error(void); /* cudaError_t of the most recent failing runtime call */
 int b200q_version(void);

@@ -20,7 +20,7 @@ class Layer(ctypes.Structure):
 
 EXPORTS = ["b200q_linear", "b200q_gemv", "b200q_gemm", "b200q_linear_sharded", "b200q_dequant", "b200q_unpack",
            "b200q_workspace_bytes", "b200q_gemv_max_m", "b200q_select_kernel", "b200q_launch_count",
-           "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4"]
+           "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4", "b200q_debug_decode_plan", "b200q_debug_set_option"]
 
 
 def _load():
@@ -53,6 +53,10 @@ def _load():
     lib.b200q_strerror.restype = ctypes.c_char_p
     lib.b200q_last_cuda_error.restype = ctypes.c_int
     lib.b200q_version.restype = ctypes.c_int
+    lib.b200q_debug_decode_plan.argtypes = [ctypes.POINTER(Layer), ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
+    lib.b200q_debug_decode_plan.restype = ctypes.c_int
+    lib.b200q_debug_set_option.argtypes = [ctypes.c_char_p, ctypes.c_double]
+    lib.b200q_debug_set_option.restype = ctypes.c_int
     lib.b200q_debug_set_timeline.argtypes = [P, SZ]
     lib.b200q_debug_set_timeline.restype = None
     return lib

@@ -1,7 +1,9 @@
 // extern "C" surface of libb200q.so: argument validation, kernel selection, status codes.
 // No torch, no allocation, no synchronisation (include/b200q.h states the contract).
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -74,6 +76,15 @@ static int gemv_variant() {
     if (t) gemm_tc_set_tt256_min_m(atoi(t));
     const char* c = getenv("B200Q_MAX_CLUSTER");
     if (c) gemv_rp_set_max_cluster(atoi(c));
+    const char* fc = getenv("B200Q_FORCE_CLUSTER");
+    if (fc) gemv_rp_set_force_cluster(atoi(fc));
+    const char* pm = getenv("B200Q_PLANNER");          // 0 = legacy power-of-two rule; "1,<cap>" = wave-aware with a slot-fill cap
+    if (pm) {
+      double cap = 0;
+      int mode = 1;
+      sscanf(pm, "%d,%lf", &mode, &cap);
+      gemv_rp_set_planner(mode, cap);
+    }
   }
   return v;
 }
@@ -239,6 +250,33 @@ const char* b200q_strerror(int status) {
 
 int b200q_last_cuda_error(void) { return g_last_cuda.load(); }
 /* diagnostic: per-CTA phase timestamps of the decode kernel (8 x u64 per CTA); NULL disables */
+int b200q_debug_set_option(const char* name, double value) {
+  if (!name) return B200Q_ERR_NULL;
+  gemv_variant();                                    // environment defaults first, then the override
+  const std::string n(name);
+  if (n == "force_cluster") gemv_rp_set_force_cluster((int)value);
+  else if (n == "max_cluster") gemv_rp_set_max_cluster((int)value);
+  else if (n == "planner") gemv_rp_set_planner((int)value, 0);
+  else if (n == "fill_cap") gemv_rp_set_planner(1, value);
+  else if (n == "force_fma") g_force_fma = value != 0;
+  else if (n == "fma_max_m") gemv_fma_set_max_m((int)value);
+  else if (n == "tt256_min_m") gemm_tc_set_tt256_min_m((int)value);
+  else return B200Q_ERR_UNSUPPORTED;
+  return B200Q_OK;
+}
+
+int b200q_debug_decode_plan(const b200q_layer* layer, int64_t M, int32_t out[4]) {
+  const int v = validate(layer);
+  if (v != B200Q_OK) return v;
+  if (!out || M < 1 || M > kGemvMaxM) return B200Q_ERR_SHAPE;
+  gemv_variant();
+  const LayerView V = make_view(layer);
+  int o[4];
+  if (!gemv_rp_describe(V, (int)M, o)) return B200Q_ERR_UNSUPPORTED;
+  for (int i = 0; i < 4; ++i) out[i] = o[i];
+  return B200Q_OK;
+}
+
 void b200q_debug_set_timeline(void* device_buf, size_t bytes) {
   gemv_variant();
   gemv_rp_set_debug((unsigned long long*)device_buf, bytes / 8);

@@ -131,7 +131,7 @@ template <int BITS>
 struct RpGptq {
   static constexpr int P = 32 / BITS;
   static constexpr int NT = 32, KSTEP = 4 * P, MAXSTEPS = 16, N_GRAN = 32;
-  static constexpr int ROWS_PER_STEP = 4, ROW_WORDS = 32, RS_WORDS = 40, SM_MIN_BLOCKS = 3;
+  static constexpr int ROWS_PER_STEP = 4, ROW_WORDS = 32, RS_WORDS = 32, SM_MIN_BLOCKS = 3;   // rows unpadded, chunks XOR-swizzled
   static constexpr int COLS_PER_CHUNK = 4, LANE_COLS = 4;       // columns per 16-byte chunk / per lane-g
   static constexpr int NTOT = 2;                               // output accumulators (sets)
   static constexpr int NACC = (BITS == 4) ? 4 : 2;             // 4-bit: {set} x {LO, HI}
@@ -144,8 +144,12 @@ struct RpGptq {
   __device__ static size_t src_word(const LayerView& L, int row, int n0) { return (size_t)row * L.N + n0; }
   __device__ static void load_smem(Step& w, const uint32_t* tile, int ls, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    w = r_lds128(tile + (size_t)(ls * 4 + t) * RS_WORDS + 4 * g);
+    w = r_lds128(tile + (size_t)(ls * 4 + t) * RS_WORDS + 4 * (g ^ (2 * t)));
   }
+  // shared-memory byte offset of 16-byte chunk cc of packed row `row`: the four rows a quarter-warp reads together
+  // start at the same bank, so chunk c of row r sits at c ^ 2(r & 3) (conflict-free LDS.128 without padding)
+  __device__ static int smem_chunk_byte(int row, int cc) { return row * (RS_WORDS * 4) + ((cc ^ (2 * (row & 3))) << 4); }
+  static constexpr int SWZ_ROWS = 4;
   // An MMA mixes the k-slots of all four t-lanes, so a step (4 packed rows) must lie inside one group.
   __device__ static int step_k(int s, int) { return s * KSTEP; }
   // (scale, zero) of 8 adjacent columns n..n+7 of group g, as fp32 (n % 8 == 0)
@@ -276,7 +280,7 @@ struct RpGptq {
 // ------------------------------------------------------------------------------------------------
 struct RpAwq {
   static constexpr int NT = 128, KSTEP = 16, MAXSTEPS = 4, N_GRAN = 32;
-  static constexpr int ROWS_PER_STEP = 16, ROW_WORDS = 16, RS_WORDS = 20, SM_MIN_BLOCKS = 2;
+  static constexpr int ROWS_PER_STEP = 16, ROW_WORDS = 16, RS_WORDS = 16, SM_MIN_BLOCKS = 2;   // unpadded, XOR-swizzled
   static constexpr int COLS_PER_CHUNK = 32, LANE_COLS = 16;
   static constexpr int NTOT = 8, NACC = 8;
   struct Step { uint2 r[4]; };
@@ -293,12 +297,19 @@ struct RpAwq {
   __device__ static size_t src_word(const LayerView& L, int row, int n0) { return (size_t)row * (L.N >> 3) + (n0 >> 3); }
   __device__ static void load_smem(Step& w, const uint32_t* tile, int ls, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    const uint32_t* base = tile + (size_t)(ls * 16 + 2 * t) * RS_WORDS + 2 * g;
-    w.r[0] = r_lds64(base);
-    w.r[1] = r_lds64(base + RS_WORDS);
-    w.r[2] = r_lds64(base + 8 * RS_WORDS);
-    w.r[3] = r_lds64(base + 9 * RS_WORDS);
+    // rows 2t, 2t+1 form one 128-byte unit (8 chunks of 16 B); chunk l of unit u sits at l ^ 2(u & 3)
+    const uint32_t* unit = tile + (size_t)(ls * 8 + t) * 32 + 2 * (g & 1);
+    const int c = g >> 1, x = 2 * t;
+    w.r[0] = r_lds64(unit + 4 * (c ^ x));
+    w.r[1] = r_lds64(unit + 4 * ((4 + c) ^ x));
+    w.r[2] = r_lds64(unit + 4 * 32 + 4 * (c ^ x));            // rows +8 / +9: unit + 4 (same u & 3)
+    w.r[3] = r_lds64(unit + 4 * 32 + 4 * ((4 + c) ^ x));
   }
+  __device__ static int smem_chunk_byte(int row, int cc) {
+    const int u = row >> 1, l = ((row & 1) << 2) + cc;
+    return u * 128 + ((l ^ (2 * (u & 3))) << 4);
+  }
+  static constexpr int SWZ_ROWS = 8;
   __device__ static int step_k(int s, int) { return s * KSTEP; }
   __device__ static void table_entries8(const LayerView& L, int g, int n, float2 (&e)[8]) {
     const uint4 sv = __ldg(reinterpret_cast<const uint4*>(L.s + (size_t)g * L.N + n));
@@ -381,6 +392,8 @@ struct RpMarlin {
   }
   __device__ static size_t src_word(const LayerView& L, int row, int n0) { return (size_t)row * (2 * (size_t)L.N) + 2 * n0; }
   __device__ static void load_smem(Step& w, const uint32_t* tile, int ls, int lane) { w = r_lds128(tile + (size_t)ls * RS_WORDS + 4 * lane); }
+  __device__ static int smem_chunk_byte(int row, int cc) { return row * (RS_WORDS * 4) + (cc << 4); }
+  static constexpr int SWZ_ROWS = 1;
   __device__ static int step_k(int s, int) { return s * KSTEP; }
   __device__ static float2 table_entry(const LayerView& L, int g, int n) {
     return make_float2(__half2float(__ldg(L.s + (size_t)g * L.N + marlin_scale_index(n, L.group == L.K))), 8.0f);
@@ -481,11 +494,12 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
     char* wt = smem + p.off_w;
     static_assert(kRpThreads % CPR == 0, "chunk column is fixed per thread");
     constexpr int RSTEP = kRpThreads / CPR;
+    static_assert(RSTEP % T::SWZ_ROWS == 0, "a thread's swizzle term is the same for every row it copies");
     const int cc = tid % CPR, r0 = tid / CPR;
     if (cc * T::COLS_PER_CHUNK < ncols) {
       const uint32_t* src = p.L.qw + T::src_word(p.L, row0 + r0, n0) + 4 * cc;
       const size_t sstep = (T::src_word(p.L, 1, 0) - T::src_word(p.L, 0, 0)) * RSTEP;
-      char* dst = wt + ((size_t)r0 * T::RS_WORDS + 4 * cc) * 4;
+      char* dst = wt + T::smem_chunk_byte(r0, cc);
       for (int r = r0; r < nrows; r += RSTEP) {
         cp_async16(dst, src);
         src += sstep;
@@ -622,7 +636,7 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
 
 // ------------------------------------------------------------------------------------------------
 struct RpPlan {
-  int kind, NT, KSTEP, MAXSTEPS, n_gran, RPS, RSW;
+  int kind, NT, KSTEP, MAXSTEPS, n_gran, RPS, RSW, min_blocks;
   bool sm;
   int n_tiles, cluster, steps_total, x_stride, group_shift;
   int off_x, off_tab, off_red, off_rbuf, off_w, smem_bytes;
@@ -630,6 +644,7 @@ struct RpPlan {
 
 template <class T>
 static void rp_fill(RpPlan& pl) {
+  pl.min_blocks = T::SM_MIN_BLOCKS;
   pl.NT = T::NT; pl.KSTEP = T::KSTEP; pl.MAXSTEPS = T::MAXSTEPS; pl.n_gran = T::N_GRAN; pl.RPS = T::ROWS_PER_STEP;
   pl.RSW = T::RS_WORDS;
 }
@@ -638,6 +653,9 @@ static int g_rp_max_cluster = 8;
 static bool g_rp_smem = true;
 static int g_rp_slice_kb = 40;
 static int g_rp_min_steps = 8;
+static int g_rp_planner = 1;
+static int g_rp_force_cluster = 0;      // tuning: B200Q_FORCE_CLUSTER
+static double g_rp_fill_cap = 0.0;       // 0 = per-kernel default
 static unsigned long long* g_rp_dbg = nullptr;
 static size_t g_rp_dbg_cap = 0, g_rp_dbg_pos = 0;   // in u64 entries; consecutive launches append
 
@@ -663,31 +681,65 @@ static bool rp_plan(const LayerView& L, int M, RpPlan& pl) {
   if ((L.group & (L.group - 1)) == 0) { int s = 0; while ((1 << s) < L.group) ++s; pl.group_shift = s; }
   pl.n_tiles = (L.N + pl.NT - 1) / pl.NT;
   pl.steps_total = L.K / pl.KSTEP;
+  // shared-memory footprint of a cluster size (a CTA's k-slice is at most ceil(steps / cs) steps)
+  auto layout = [&](int cs, RpPlan& q) {
+    const int slice_steps = (pl.steps_total + cs - 1) / cs;
+    const int kslice = slice_steps * pl.KSTEP;
+    q.x_stride = kslice * 2;
+    q.x_stride += (64 - (q.x_stride % 128) + 128) % 128;
+    const int gcap = kslice / L.group + 2;
+    int off = 0;
+    q.off_x = off; off += M * q.x_stride;
+    off = (off + 15) & ~15;
+    q.off_tab = off; off += gcap * pl.NT * 8;
+    off = (off + 15) & ~15;
+    q.off_red = off; off += kWarps * pl.NT * M * 4;
+    q.off_rbuf = off; off += (cs - 1) * pl.NT * M * 4;
+    off = (off + 127) & ~127;
+    q.off_w = off;
+    if (pl.sm) off += slice_steps * pl.RPS * pl.RSW * 4;
+    q.smem_bytes = off;
+  };
   int cs = 1;
-  if (pl.sm) {
-    const long long bytes = (long long)pl.steps_total * pl.RPS * pl.RSW * 4;
-    while (cs < g_rp_max_cluster && bytes / cs > (long long)g_rp_slice_kb * 1024) cs *= 2;
+  if (g_rp_planner == 0) {                 // legacy power-of-two rule (B200Q_PLANNER=0)
+    if (pl.sm) {
+      const long long bytes = (long long)pl.steps_total * pl.RPS * pl.RSW * 4;
+      while (cs < g_rp_max_cluster && bytes / cs > (long long)g_rp_slice_kb * 1024) cs *= 2;
+    } else {
+      while (cs < g_rp_max_cluster && (pl.steps_total + cs * kWarps - 1) / (cs * kWarps) > pl.MAXSTEPS) cs *= 2;
+    }
+    while (cs < g_rp_max_cluster && pl.n_tiles * cs < 148 && pl.steps_total / (2 * cs * kWarps) >= 2) cs *= 2;
+    while (cs > 1 && pl.steps_total / (cs * kWarps) < g_rp_min_steps && pl.n_tiles * (cs / 2) >= 96) cs /= 2;
   } else {
-    while (cs < g_rp_max_cluster && (pl.steps_total + cs * kWarps - 1) / (cs * kWarps) > pl.MAXSTEPS) cs *= 2;
+    // wave-aware (rule fitted to the B200 sweep in profiles/r1_decode_cluster_sweep.jsonl): keep the launch to the
+    // fewest waves of co-resident CTAs; inside one wave take the largest K split whose CTAs fill at most `cap` of the
+    // SM slots -- the free slots are where the next layer's CTAs prefetch their weights under programmatic dependent
+    // launch -- else the largest split that still fits one wave.
+    const int minb = pl.min_blocks;
+    const double cap = g_rp_fill_cap > 0 ? g_rp_fill_cap : (minb <= 2 ? 0.70 : 0.90);
+    int best_waves = 1 << 30, best_c = 1;
+    bool best_under = false;
+    for (int c = 1; c <= g_rp_max_cluster; ++c) {
+      if (c > 1 && pl.steps_total / c < kWarps / 2) break;              // at least half the warps get a step
+      RpPlan q;
+      layout(c, q);
+      if (q.smem_bytes > 200 * 1024) continue;
+      int per_sm = (226 * 1024) / (q.smem_bytes + 1024);
+      if (per_sm > minb) per_sm = minb;
+      if (per_sm < 1) per_sm = 1;
+      const int ctas = pl.n_tiles * c, slots = 148 * per_sm;
+      const int waves = (ctas + slots - 1) / slots;
+      const bool under = (double)ctas <= cap * waves * slots;
+      bool take = false;
+      if (waves < best_waves) take = true;
+      else if (waves == best_waves) take = under || !best_under;         // larger c wins unless it loses the free slots
+      if (take) { best_waves = waves; best_c = c; best_under = under; }
+    }
+    cs = best_c;
   }
-  while (cs < g_rp_max_cluster && pl.n_tiles * cs < 148 && pl.steps_total / (2 * cs * kWarps) >= 2) cs *= 2;
-  while (cs > 1 && pl.steps_total / (cs * kWarps) < g_rp_min_steps && pl.n_tiles * (cs / 2) >= 96) cs /= 2;
+  if (g_rp_force_cluster > 0 && g_rp_force_cluster <= 8 && pl.steps_total / g_rp_force_cluster >= 1) cs = g_rp_force_cluster;
   pl.cluster = cs;
-  const int kslice = ((pl.steps_total + cs - 1) / cs + kWarps) * pl.KSTEP;   // upper bound of a CTA's k-range
-  pl.x_stride = kslice * 2;
-  pl.x_stride += (64 - (pl.x_stride % 128) + 128) % 128;
-  const int gcap = kslice / L.group + 2;
-  int off = 0;
-  pl.off_x = off; off += M * pl.x_stride;
-  off = (off + 15) & ~15;
-  pl.off_tab = off; off += gcap * pl.NT * 8;
-  off = (off + 15) & ~15;
-  pl.off_red = off; off += kWarps * pl.NT * M * 4;
-  pl.off_rbuf = off; off += (cs - 1) * pl.NT * M * 4;
-  off = (off + 127) & ~127;
-  pl.off_w = off;
-  if (pl.sm) off += ((pl.steps_total + cs - 1) / cs + kWarps) * pl.RPS * pl.RSW * 4;
-  pl.smem_bytes = off;
+  layout(cs, pl);
   if (pl.smem_bytes > 200 * 1024) { pl.kind = 0; return false; }
   return true;
 }
@@ -700,6 +752,14 @@ bool gemv_rp_supported(const LayerView& L, int M, const __half* x, int64_t ldx) 
   return true;
 }
 
+// plan introspection (tests / tuning): {cluster, n_tiles, smem_bytes, steps_total}
+bool gemv_rp_describe(const LayerView& L, int M, int out[4]) {
+  RpPlan pl;
+  if (!rp_plan(L, M, pl)) return false;
+  out[0] = pl.cluster; out[1] = pl.n_tiles; out[2] = pl.smem_bytes; out[3] = pl.steps_total;
+  return true;
+}
+
 // shared-memory footprint of the plan (0 if unsupported): lets the dispatcher avoid >1-wave configurations
 int gemv_rp_smem_bytes(const LayerView& L, int M) {
   RpPlan pl;
@@ -709,6 +769,11 @@ int gemv_rp_smem_bytes(const LayerView& L, int M) {
 void gemv_rp_set_max_cluster(int c) { g_rp_max_cluster = c < 1 ? 1 : (c > 8 ? 8 : c); }
 void gemv_rp_set_smem(bool on, int slice_kb) { g_rp_smem = on; if (slice_kb > 0) g_rp_slice_kb = slice_kb; }
 void gemv_rp_set_min_steps(int n) { g_rp_min_steps = n; }
+void gemv_rp_set_force_cluster(int c) { g_rp_force_cluster = c; }
+void gemv_rp_set_planner(int mode, double fill_cap) {
+  g_rp_planner = mode;
+  if (fill_cap > 0) g_rp_fill_cap = fill_cap;
+}
 void gemv_rp_set_debug(unsigned long long* buf, size_t cap_entries) { g_rp_dbg = buf; g_rp_dbg_cap = cap_entries; g_rp_dbg_pos = 0; }
 
 template <class T, bool SM, int MC>

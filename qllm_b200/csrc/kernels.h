@@ -51,6 +51,9 @@ void gemv_rp_set_max_cluster(int c);
 int gemv_rp_smem_bytes(const LayerView& L, int M);
 void gemv_rp_set_smem(bool on, int slice_kb);
 void gemv_rp_set_min_steps(int n);
+void gemv_rp_set_force_cluster(int c);
+bool gemv_rp_describe(const LayerView& L, int M, int out[4]);
+void gemv_rp_set_planner(int mode, double fill_cap);
 void gemv_rp_set_debug(unsigned long long* buf, size_t cap_entries);
 
 // gemv_fma.cu : M <= 2 decode path (CUDA-core fp16x2 FMA, register prefetch, cluster split-K)
