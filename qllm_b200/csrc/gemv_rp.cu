@@ -47,7 +47,7 @@ struct RpParams {
   int64_t ldy, n_offset;
   int n_tiles, cluster, steps_total, group_shift;
   int x_stride;                   // bytes
-  int off_x, off_tab, off_red, off_rbuf, off_w;
+  int off_x, off_tab, off_red, off_rbuf, off_rbar, off_w;
   unsigned long long* dbg;        // optional per-CTA phase timestamps (diagnostic; nullptr in production)
 };
 
@@ -71,6 +71,16 @@ __device__ __forceinline__ void st_cluster_f32(const float* local_smem, uint32_t
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(rank));
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
+// remote store that also signals: value -> rank's shared memory, 4 bytes of complete_tx on rank's mbarrier
+__device__ __forceinline__ void st_async_f32(const float* local_smem, const uint64_t* local_bar, uint32_t rank, float v) {
+  uint32_t ra, rb;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_smem)), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(__float_as_uint(v)), "r"(rb)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -479,6 +489,17 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
 
   RP_STAMP(0);
   pdl_launch_dependents();
+  // cluster reduce rendezvous: rank 0 arms an mbarrier for the (cs-1) partial vectors it will receive through st.async;
+  // the cluster-wide arrive is issued now and only waited on right before the remote stores, far off the critical path.
+  uint64_t* rbar = reinterpret_cast<uint64_t*>(smem + p.off_rbar);
+  if (cs > 1) {
+    if (rank == 0 && tid == 0) {
+      mbar_init(rbar, 1);
+      mbar_expect_tx(rbar, (uint32_t)(cs - 1) * (uint32_t)(T::NT * p.M) * 4u);   // every rank sends NT*M floats
+      fence_mbar_init();
+    }
+    cluster_arrive_relaxed();
+  }
 
   // ---- 1. weights -> shared / registers, group table -> shared (independent of the upstream kernel) ----
   typename T::Step w[SM ? 1 : T::MAXSTEPS];
@@ -603,16 +624,18 @@ __global__ void __launch_bounds__(kRpThreads, SM ? T::SM_MIN_BLOCKS : 2) gemv_rp
     v[r] = sum;
   }
   if (cs > 1) {
+    cluster_wait();                          // completes the arrive issued at kernel start: rank 0's mbarrier is armed
     if (rank != 0) {
 #pragma unroll
       for (int r = 0; r < NV; ++r) {
         const int idx = tid + r * kRpThreads;
-        if (idx < total) st_cluster_f32(rbuf + (size_t)(rank - 1) * total + idx, 0u, v[r]);
+        if (idx < total) st_async_f32(rbuf + (size_t)(rank - 1) * total + idx, rbar, 0u, v[r]);
       }
+      RP_STAMP(5);
+      return;
     }
-    cluster_sync_all();
+    mbar_wait(rbar, 0);
     RP_STAMP(5);
-    if (rank != 0) return;
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
       const int idx = tid + r * kRpThreads;
@@ -639,7 +662,7 @@ struct RpPlan {
   int kind, NT, KSTEP, MAXSTEPS, n_gran, RPS, RSW, min_blocks;
   bool sm;
   int n_tiles, cluster, steps_total, x_stride, group_shift;
-  int off_x, off_tab, off_red, off_rbuf, off_w, smem_bytes;
+  int off_x, off_tab, off_red, off_rbuf, off_rbar, off_w, smem_bytes;
 };
 
 template <class T>
@@ -695,6 +718,8 @@ static bool rp_plan(const LayerView& L, int M, RpPlan& pl) {
     off = (off + 15) & ~15;
     q.off_red = off; off += kWarps * pl.NT * M * 4;
     q.off_rbuf = off; off += (cs - 1) * pl.NT * M * 4;
+    off = (off + 7) & ~7;
+    q.off_rbar = off; off += 8;
     off = (off + 127) & ~127;
     q.off_w = off;
     if (pl.sm) off += slice_steps * pl.RPS * pl.RSW * 4;
@@ -819,7 +844,7 @@ cudaError_t launch_gemv_rp(const LinearArgs& a, const PeerOut* peers) {
   p.ldy = a.ldy; p.n_offset = a.n_offset;
   p.n_tiles = pl.n_tiles; p.cluster = pl.cluster; p.steps_total = pl.steps_total; p.x_stride = pl.x_stride;
   p.group_shift = pl.group_shift;
-  p.off_x = pl.off_x; p.off_tab = pl.off_tab; p.off_red = pl.off_red; p.off_rbuf = pl.off_rbuf; p.off_w = pl.off_w;
+  p.off_x = pl.off_x; p.off_tab = pl.off_tab; p.off_red = pl.off_red; p.off_rbuf = pl.off_rbuf; p.off_rbar = pl.off_rbar; p.off_w = pl.off_w;
   p.dbg = nullptr;
   if (g_rp_dbg) {
     const size_t need = (size_t)pl.n_tiles * pl.cluster * 8;
