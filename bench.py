@@ -3,8 +3,10 @@
 
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on): one decode step
 (batch 1) of a random-init Llama-2-7B, int4 g128, AWQ pack_mode=GEMM -- the 224 QuantLinear calls of
-the 32 decoder blocks (q,k,v,o 4096->4096; gate,up 4096->11008; down 11008->4096), chained by real data
-dependencies, each call going through the C ABI (b200q_linear) exactly as QuantLinear.forward does.
+the 32 decoder blocks (q,k,v,o 4096->4096; gate,up 4096->11008; down 11008->4096), chained by the data
+dependencies of LlamaDecoderLayer (q,k,v read the block input; o reads v; gate,up read o; down reads gate), each
+going through the C ABI exactly as QuantLinear.forward does: siblings that share their input (q/k/v, gate/up) as one
+b200q_linear_group launch (the host shim's fuse_siblings), the others as b200q_linear -- 128 launches, 224 layers.
 A "step" = one token through all 224 layers.  3.4 GB of distinct packed weights: far larger than L2.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200q|reference]
@@ -172,6 +174,7 @@ class DecodeStep:
         import torch
         import qllm_b200
         self.lib, self.blocks, self.M, self.world, self.rank = qllm_b200.lib, blocks, M, world, rank
+        self.fuse = os.environ.get("B200Q_BENCH_NO_GROUP") is None
         f16 = dict(dtype=torch.float16, device=dev)
         self.h = torch.zeros(M, HIDDEN, **f16)
         self.bufs = {n: torch.zeros(M, N, **f16) for n, _, N in SHAPES}
@@ -206,15 +209,28 @@ class DecodeStep:
                 y[:, c0:c1].copy_(t[:, : c1 - c0])
         return y
 
+    def _group(self, layers, x, names, stream):
+        """Sibling layers sharing x (q/k/v, gate/up): one b200q_linear_group launch on one GPU; per-layer calls
+        (each followed by its all-gather) when column-sharded."""
+        if self.world > 1 or not self.fuse:
+            return [self._call(l, x, n, stream) for l, n in zip(layers, names)]
+        from qllm_b200 import check, Layer
+        n = len(layers)
+        descs = [l._descriptor() for l in layers]
+        ys = [self.bufs[nm] for nm in names]
+        arr = (ctypes.POINTER(Layer) * n)(*[ctypes.pointer(d) for d in descs])
+        yp = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
+        ld = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
+        check(self.lib.b200q_linear_group(arr, n, x.data_ptr(), self.M, x.stride(0), yp, ld, self.ws.data_ptr(),
+                                          self.ws.numel(), stream))
+        return ys
+
     def run(self, stream):
         h = self.h
         for b in self.blocks:
-            self._call(b["q"], h, "q", stream)
-            self._call(b["k"], h, "k", stream)
-            v = self._call(b["v"], h, "v", stream)
+            q, k, v = self._group([b["q"], b["k"], b["v"]], h, ["q", "k", "v"], stream)
             o = self._call(b["o"], v, "o", stream)
-            gt = self._call(b["gate"], o, "gate", stream)
-            self._call(b["up"], o, "up", stream)
+            gt, up = self._group([b["gate"], b["up"]], o, ["gate", "up"], stream)
             h = self._call(b["down"], gt, "down", stream)
         return h
 
@@ -287,8 +303,8 @@ def run_b200q(args, rank, world, local_rank):
     achieved = total_bytes * world / world / (ms_per_step * 1e-3) / 1e9      # whole-job algorithmic GB/s
     roofline = {"bound": "hbm", "achieved": achieved / world, "peak": P["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / world / P["hbm_gbs"], "traffic": None, "peak_source": P["source"],
-                "kernel": "gemv_rp_kernel<RpAwq> (decode)", "bytes_per_launch": total_bytes / n_layers,
-                "us_per_launch": ms_per_step * 1e3 / n_layers, "per_gpu": True}
+                "kernel": "gemv_stream_kernel<RpAwq> (decode)", "bytes_per_launch": total_bytes / launches_per_step,
+                "us_per_launch": ms_per_step * 1e3 / launches_per_step, "per_gpu": True}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         roofline["traffic"] = tr.get("decode_awq_dram_bytes_per_launch")
@@ -298,7 +314,9 @@ def run_b200q(args, rank, world, local_rank):
         "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": "Llama-2-7B int4 g128 AWQ pack_mode=GEMM, batch=1 decode: 224 chained QuantLinear calls per step",
+        "config": {"workload": "Llama-2-7B int4 g128 AWQ pack_mode=GEMM, batch=1 decode: the 224 QuantLinear layers of one token "
+                               "in LlamaDecoderLayer dependency order (q|k|v -> o -> gate|up -> down)",
+                   "launches_per_step": int(launches_per_step), "sibling_groups": bool(step.fuse and world == 1),
                    "M": M, "layers": n_layers, "parallelism": f"column-shard x{world} + all-gather" if world > 1 else "single GPU",
                    "l2_policy": "inputs (3.4 GB packed weights) larger than L2", "cuda_graph": True, "pdl": True,
                    "outputs_finite": finite},

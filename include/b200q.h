@@ -98,6 +98,19 @@ int b200q_gemm(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
                void* workspace, size_t workspace_bytes, b200q_stream_t stream);
 
 /*
+ * Sibling layers that share their input -- q_proj/k_proj/v_proj of LlamaAttention, gate_proj/up_proj of
+ * LlamaMLP -- as ONE launch: y[i][M, N_i] = x[M, K] @ dequant(layers[i]) (+ bias_i), i < n_layers <= 3.
+ * In the reference these are separate, back-to-back QuantLinear.forward calls on the same tensor
+ * (quant_linear_awq.py:142-148 et al., called from the HF attention / MLP modules); at decode sizes each
+ * call is launch- and latency-bound, so the host shim (qllm_b200.fuse_siblings) routes them here.  All
+ * layers must agree on (layout, bits, group_size, K, zero_bias); otherwise, or for M above
+ * b200q_gemv_max_m(), the call degrades to one b200q_linear per layer with identical results.
+ */
+int b200q_linear_group(const b200q_layer* const* layers, int32_t n_layers, const void* x, int64_t M, int64_t ldx,
+                       void* const* y, const int64_t* ldy, void* workspace, size_t workspace_bytes,
+                       b200q_stream_t stream);
+
+/*
  * Multi-GPU column-sharded forward with the all-gather fused into the epilogue: this rank computes
  * y[:, n_offset : n_offset + layer->N] and stores the tile into `n_peers` output buffers
  * (peer_y[r] = rank r's full [M, ldy] output, mapped through NVLink peer access / symmetric memory;
@@ -155,7 +168,8 @@ int b200q_debug_decode_plan(const b200q_layer* layer, int64_t M, int32_t out[4])
 
 /* Diagnostic / tuning only: override a dispatch or planner switch at run time (same switches as the B200Q_*
  * environment variables): "force_cluster", "max_cluster", "planner", "fill_cap", "force_fma",
- * "fma_max_m", "tt256_min_m".  Returns B200Q_ERR_UNSUPPORTED for an unknown name. */
+ * "fma_max_m", "tt256_min_m", "stream" (0 = pre-streaming decode kernels), "st_cluster", "st_depth", "st_tpc",
+ * "st_target", "st_ring_kb".  Returns B200Q_ERR_UNSUPPORTED for an unknown name. */
 int b200q_debug_set_option(const char* name, double value);
 
 const char* b200q_strerror(int status);

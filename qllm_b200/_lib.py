@@ -18,7 +18,7 @@ class Layer(ctypes.Structure):
                 ("g_idx", ctypes.c_void_p), ("bias", ctypes.c_void_p)]
 
 
-EXPORTS = ["b200q_linear", "b200q_gemv", "b200q_gemm", "b200q_linear_sharded", "b200q_dequant", "b200q_unpack",
+EXPORTS = ["b200q_linear", "b200q_linear_group", "b200q_gemv", "b200q_gemm", "b200q_linear_sharded", "b200q_dequant", "b200q_unpack",
            "b200q_workspace_bytes", "b200q_gemv_max_m", "b200q_select_kernel", "b200q_launch_count",
            "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4", "b200q_debug_decode_plan", "b200q_debug_set_option"]
 
@@ -37,6 +37,9 @@ def _load():
         getattr(lib, name).restype = ctypes.c_int
     lib.b200q_linear_sharded.argtypes = [LP, P, I64, I64, ctypes.POINTER(P), ctypes.c_int32, I64, I64, P, SZ, P]
     lib.b200q_linear_sharded.restype = ctypes.c_int
+    lib.b200q_linear_group.argtypes = [ctypes.POINTER(LP), ctypes.c_int32, P, I64, I64, ctypes.POINTER(P),
+                                       ctypes.POINTER(I64), P, SZ, P]
+    lib.b200q_linear_group.restype = ctypes.c_int
     lib.b200q_dequant.argtypes = [LP, P, P]
     lib.b200q_dequant.restype = ctypes.c_int
     lib.b200q_unpack.argtypes = [LP, P, P, P]

@@ -12,6 +12,11 @@ namespace b200q {
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_last_cuda{0};
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool decode_carveout_max() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200Q_CARVEOUT"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 
 static int cuda_status(cudaError_t e) {
   if (e == cudaSuccess) return B200Q_OK;
@@ -59,11 +64,18 @@ enum { KERNEL_GEMV_MMA = 1, KERNEL_GEMM_TC = 2, KERNEL_GENERIC = 3 };
 // Tuning/diagnostic switches, read once: B200Q_GEMV=v1 selects the bulk-copy/mbarrier decode kernel
 // (gemv_mma.cu), =v2 the register-prefetch variant of gemv_rp.cu; default is its cp.async/smem variant.
 static bool g_force_fma = false;
+static bool g_use_stream = true;       // B200Q_GEMV=rp (or v1 / v2) selects the pre-streaming decode kernels
 static int gemv_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200Q_GEMV");
     v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+    if (e && (e[0] == 'v' || e[0] == 'r')) g_use_stream = false;
+    const char* so[6] = {"B200Q_ST_CLUSTER", "B200Q_ST_DEPTH", "B200Q_ST_TPC", "B200Q_ST_TARGET", "B200Q_ST_RING_KB", "B200Q_ST_LEAN"};
+    for (int i = 0; i < 6; ++i) {
+      const char* sv = getenv(so[i]);
+      if (sv) gemv_stream_set_option(i, atoi(sv));
+    }
     if (e && e[0] == 'v') gemv_fma_set_max_m(0);        // any explicit B200Q_GEMV=v* disables the FMA kernel
     const char* fm = getenv("B200Q_FMA_MAX_M");
     if (fm) gemv_fma_set_max_m(atoi(fm));
@@ -88,7 +100,14 @@ static int gemv_variant() {
   }
   return v;
 }
+static LinearArgs probe_args(const LayerView& V, int M, const __half* x, int64_t ldx) {
+  LinearArgs a = {};
+  a.L = V; a.x = x; a.ldx = ldx; a.M = M;
+  return a;
+}
 static bool decode_supported(const LayerView& V, int M, const __half* x, int64_t ldx) {
+  gemv_variant();
+  if (g_use_stream) { const LinearArgs a = probe_args(V, M, x, ldx); if (gemv_stream_supported(&a, 1)) return true; }
   if (gemv_variant() == 2 && (gemv_fma_supported(V, M, x, ldx) || gemv_rp_supported(V, M, x, ldx))) return true;
   return gemv_mma_supported(V, M, x, ldx);
 }
@@ -132,6 +151,7 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   a.L = V; a.x = (const __half*)x; a.ldx = ldx; a.M = (int)M; a.y = (__half*)y; a.ldy = ldy; a.n_offset = n_offset;
   a.workspace = ws; a.workspace_bytes = ws_bytes; a.stream = (cudaStream_t)stream;
   if (kern == KERNEL_GEMV_MMA) {
+    if (g_use_stream && gemv_stream_supported(&a, 1)) return cuda_status(launch_gemv_stream(&a, 1, peers));
     if (gemv_variant() == 2) {
       // Measured on B200 (profiles/README.md): the MMA kernel with the packed slice staged in shared memory wins
       // while its slice leaves >= 2 CTAs per SM; for long-K layers (slice > 112 KB) the register-prefetch FMA
@@ -191,6 +211,31 @@ int b200q_linear_sharded(const b200q_layer* layer, const void* x, int64_t M, int
     po.y[i] = (__half*)peer_y[i];
   }
   return run(layer, x, M, ldx, &po, nullptr, ldy, n_offset, workspace, workspace_bytes, stream, 0);
+}
+
+int b200q_linear_group(const b200q_layer* const* layers, int32_t n_layers, const void* x, int64_t M, int64_t ldx,
+                       void* const* y, const int64_t* ldy, void* workspace, size_t workspace_bytes, b200q_stream_t stream) {
+  if (!layers || !y || !ldy) return B200Q_ERR_NULL;
+  if (n_layers < 1 || n_layers > kMaxGroupLayers) return B200Q_ERR_SHAPE;
+  gemv_variant();
+  LinearArgs a[kMaxGroupLayers];
+  bool fused = g_use_stream && M >= 1 && M <= kGemvMaxM;
+  for (int i = 0; i < n_layers; ++i) {
+    const int v = validate(layers[i]);
+    if (v != B200Q_OK) return v;
+    if (!x || !y[i]) return B200Q_ERR_NULL;
+    if (M < 1 || ldx < layers[i]->K || ldy[i] < layers[i]->N) return B200Q_ERR_SHAPE;
+    a[i] = {};
+    a[i].L = make_view(layers[i]); a[i].x = (const __half*)x; a[i].ldx = ldx; a[i].M = (int)(fused ? M : 1);
+    a[i].y = (__half*)y[i]; a[i].ldy = ldy[i]; a[i].n_offset = 0;
+    a[i].workspace = workspace; a[i].workspace_bytes = workspace_bytes; a[i].stream = (cudaStream_t)stream;
+  }
+  if (fused && gemv_stream_supported(a, n_layers)) return cuda_status(launch_gemv_stream(a, n_layers, nullptr));
+  for (int i = 0; i < n_layers; ++i) {      // not fusable (shape / layout mix / M): same result, one launch per layer
+    const int st = run(layers[i], x, M, ldx, nullptr, y[i], ldy[i], 0, workspace, workspace_bytes, stream, 0);
+    if (st != B200Q_OK) return st;
+  }
+  return B200Q_OK;
 }
 
 int b200q_dequant(const b200q_layer* layer, void* w_out, b200q_stream_t stream) {
@@ -261,6 +306,13 @@ int b200q_debug_set_option(const char* name, double value) {
   else if (n == "force_fma") g_force_fma = value != 0;
   else if (n == "fma_max_m") gemv_fma_set_max_m((int)value);
   else if (n == "tt256_min_m") gemm_tc_set_tt256_min_m((int)value);
+  else if (n == "stream") g_use_stream = value != 0;
+  else if (n == "st_cluster") gemv_stream_set_option(0, (int)value);
+  else if (n == "st_depth") gemv_stream_set_option(1, (int)value);
+  else if (n == "st_tpc") gemv_stream_set_option(2, (int)value);
+  else if (n == "st_target") gemv_stream_set_option(3, (int)value);
+  else if (n == "st_ring_kb") gemv_stream_set_option(4, (int)value);
+  else if (n == "st_lean") gemv_stream_set_option(5, (int)value);
   else return B200Q_ERR_UNSUPPORTED;
   return B200Q_OK;
 }
@@ -271,7 +323,12 @@ int b200q_debug_decode_plan(const b200q_layer* layer, int64_t M, int32_t out[4])
   if (!out || M < 1 || M > kGemvMaxM) return B200Q_ERR_SHAPE;
   gemv_variant();
   const LayerView V = make_view(layer);
-  int o[4];
+  int o[6];
+  const LinearArgs pa = probe_args(V, (int)M, nullptr, V.K);
+  if (g_use_stream && gemv_stream_describe(&pa, 1, o)) {
+    for (int i = 0; i < 4; ++i) out[i] = o[i];
+    return B200Q_OK;
+  }
   if (!gemv_rp_describe(V, (int)M, o)) return B200Q_ERR_UNSUPPORTED;
   for (int i = 0; i < 4; ++i) out[i] = o[i];
   return B200Q_OK;
@@ -280,6 +337,7 @@ int b200q_debug_decode_plan(const b200q_layer* layer, int64_t M, int32_t out[4])
 void b200q_debug_set_timeline(void* device_buf, size_t bytes) {
   gemv_variant();
   gemv_rp_set_debug((unsigned long long*)device_buf, bytes / 8);
+  gemv_stream_set_debug((unsigned long long*)device_buf, bytes / 8);
   gemm_tc_set_debug(bytes >= 64 * 1024 ? (unsigned long long*)device_buf : nullptr);   // GEMM: CTA(0,0), 8 stamps per k-block
 }
 int b200q_version(void) { return B200Q_VERSION; }

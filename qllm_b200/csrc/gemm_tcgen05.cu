@@ -10,9 +10,12 @@
 //     [M, K] activation matrix (rows beyond M are zero-filled by TMA);
 //   * accumulators (fp32) stay in TMEM; the epilogue reads them with tcgen05.ld, adds bias, converts
 //     to fp16 and stores y[tok, n] (coalesced along n across the warp).
-// Warp roles (256 threads): w0 TMA producer | w1 MMA issuer (one thread) | w2 TMEM allocator |
-// w4-7 dequant + epilogue.  mbarrier rings: input stages (TMA -> dequant/MMA), A stages in TMEM
-// (dequant -> MMA), accumulator-ready.
+// Warp roles (896 threads): w0-23 dequant + epilogue (three teams of eight) | w24 X TMA producer | w25 packed-W TMA
+// producer | w26 TMEM allocator | w27 MMA issuer (one thread).  The control warps carry the HIGHEST warp ids: the
+// SM's issue arbiter favours high warp ids, and the single MMA-issuing thread is the serial resource of the CTA
+// (measured: as warp 1 it was starved to ~560 cycles per k-block against a 256-cycle MMA floor).
+// mbarrier rings: X stages (TMA -> MMA), packed-W stages (TMA -> dequant), A stages in TMEM (dequant -> MMA; their
+// release, one tcgen05.commit per k-block, also frees the X stage), accumulator-ready.
 //
 // Replaces: ort_ops.dequant + cuBLAS (quant_linear_gptq.py:81-85), gemm_forward_cuda
 // (gemm_cuda_gen.cu:1102-1161), marlin mul (marlin_cuda.cpp:29-74) at M > 8.
@@ -26,6 +29,7 @@ namespace b200q {
 static constexpr int kDqWarps = 8;      // dequant warps that cooperate on one k-block (two per TMEM lane quadrant)
 static constexpr int kDqPar = 3;        // k-blocks dequantised concurrently: team p takes k-blocks p, p+kDqPar, ...
 static constexpr int kTcThreads = (4 + kDqWarps * kDqPar) * 32;   // 896
+static constexpr int kWXProd = kDqWarps * kDqPar, kWWProd = kWXProd + 1, kWAlloc = kWXProd + 2, kWMma = kWXProd + 3;
 static constexpr int kNSXMax = 8;     // X-tile stages (TMA -> MMA):      8 for TT <= 128, 5 for TT = 256
 static constexpr int kNSWMax = 16;    // packed-W stages (TMA -> dequant): sized to what shared memory leaves
 __host__ __device__ constexpr int tc_stages(int tt) { return tt <= 128 ? 8 : 5; }
@@ -50,10 +54,11 @@ struct TcParams {
 
 __device__ __forceinline__ unsigned long long tc_gtime() {
   unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));      // SM clock: every stamp comes from CTA (0,0), i.e. one SM
   return t;
 }
-// stamps: [kb][0..3] dequant warp 4 (inputs landed, ALU done, A stage free, TMEM store issued), [kb][4..5] MMA thread
+// stamps (SM cycles): [kb][0..3] lead warp of the dequant team that owns kb (packed words landed, ALU done, A stage
+// free, TMEM store retired + signalled), [kb][4..7] MMA thread (X landed, A landed, MMAs issued, commits issued)
 #define TC_STAMP(kb, i) do { if (DBG && dbg_on) p.dbg[(size_t)(kb) * 8 + (i)] = tc_gtime(); } while (0)
 
 // ---- small PTX wrappers -----------------------------------------------------------------------
@@ -173,59 +178,69 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (tid == 0) {
-    for (int s = 0; s < kNSXMax; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }
+    for (int s = 0; s < kNSXMax; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }   // empty_x: unused
     for (int s = 0; s < kNSWMax; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], kDqWarps); }
     for (int s = 0; s < kNA; ++s) { mbar_init(&a_full[s], kDqWarps); mbar_init(&a_empty[s], 1); }
-    mbar_init(acc_full, 1);
+    mbar_init(acc_full, TT <= 128 ? 2 : 1);
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == kWAlloc) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // group tables for this CTA's 128 columns (all groups)
-  for (int idx = tid; idx < p.L.G * kBN; idx += kTcThreads) {
-    const int g = idx / kBN, n = idx % kBN;
-    sc[idx] = (n0 + n < p.L.N) ? __ldg(p.L.s + (size_t)g * p.L.N + n0 + n) : __float2half(0.f);
-  }
-  if (FZ) {
-    for (int idx = tid; idx < p.L.G * kBN; idx += kTcThreads) {
-      const int g = idx / kBN, n = idx % kBN;
-      reinterpret_cast<__half*>(zq)[idx] =
-          (n0 + n < p.L.N) ? __ldg(reinterpret_cast<const __half*>(p.L.qz) + (size_t)g * p.L.N + n0 + n) : __float2half(0.f);
-    }
-  } else {
-    constexpr int ZW = kBN * BITS / 32;                                 // packed zero words of this tile per group
-    const size_t zrow = ((size_t)p.L.N * BITS) >> 5;
-    for (int idx = tid; idx < p.L.G * ZW; idx += kTcThreads) {
-      const int g = idx / ZW, wv = idx % ZW;
-      reinterpret_cast<uint32_t*>(zq)[idx] =
-          ((n0 * BITS) / 32 + wv < (int)zrow) ? __ldg(reinterpret_cast<const uint32_t*>(p.L.qz) + (size_t)g * zrow + (n0 * BITS) / 32 + wv) : 0u;
-    }
-  }
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                         // barriers initialised, TMEM allocated: the TMA producers start right away
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (warp < kDqWarps * kDqPar) {
+    // group tables for this CTA's 128 columns (all groups): only the dequant warps need them, so their load
+    // latency overlaps the first TMA round trips instead of preceding them
+    constexpr int kDqThreads = kDqWarps * kDqPar * 32;
+    for (int idx = tid; idx < p.L.G * kBN; idx += kDqThreads) {
+      const int g = idx / kBN, n = idx % kBN;
+      sc[idx] = (n0 + n < p.L.N) ? __ldg(p.L.s + (size_t)g * p.L.N + n0 + n) : __float2half(0.f);
+    }
+    if (FZ) {
+      for (int idx = tid; idx < p.L.G * kBN; idx += kDqThreads) {
+        const int g = idx / kBN, n = idx % kBN;
+        reinterpret_cast<__half*>(zq)[idx] =
+            (n0 + n < p.L.N) ? __ldg(reinterpret_cast<const __half*>(p.L.qz) + (size_t)g * p.L.N + n0 + n) : __float2half(0.f);
+      }
+    } else {
+      constexpr int ZW = kBN * BITS / 32;                                 // packed zero words of this tile per group
+      const size_t zrow = ((size_t)p.L.N * BITS) >> 5;
+      for (int idx = tid; idx < p.L.G * ZW; idx += kDqThreads) {
+        const int g = idx / ZW, wv = idx % ZW;
+        reinterpret_cast<uint32_t*>(zq)[idx] =
+            ((n0 * BITS) / 32 + wv < (int)zrow) ? __ldg(reinterpret_cast<const uint32_t*>(p.L.qz) + (size_t)g * zrow + (n0 * BITS) / 32 + wv) : 0u;
+      }
+    }
+    asm volatile("bar.sync 8, %0;" ::"n"(kDqWarps * kDqPar * 32) : "memory");
+  }
 
   constexpr int P = 32 / BITS;                     // k values per packed word
   constexpr int RS = kBK / P;                      // packed rows per stage
   constexpr int WH = RS / 2;                       // words per column per half-stage (32 k)
   constexpr uint32_t X_BYTES = TT * kBK * 2, W_BYTES = RS * kBN * 4;
-  constexpr int kACol = TT;                        // A stages sit right after the TT accumulator columns
+  constexpr int NI = (TT <= 128) ? 2 : 1;           // MMA-issuing threads (k-blocks i, i + NI, ...), one accumulator each
+  constexpr int kACol = NI * TT;                   // A stages sit right after the accumulator columns
 
-  if (warp == 0) {                         // X producer: the ring only spans TMA latency + MMA lag
+  if (warp == kWXProd) {                   // X producer: the ring only spans TMA latency + MMA lag
     if (lane == 0) {
       int s = 0;
-      uint32_t ph = 0;
       for (int kb = 0; kb < p.kblocks; ++kb) {
-        if (!mbar_wait_bounded(&empty_x[s], ph ^ 1u, p.err, 1)) break;
+        // X stage s was last read by the MMAs of k-block kb - nsx, whose completion is signalled on that k-block's
+        // A-stage barrier (one commit per k-block releases both)
+        if (kb >= p.nsx) {
+          const int kp = kb - p.nsx;
+          if (!mbar_wait_bounded(&a_empty[kp % kNA], (uint32_t)((kp / kNA) & 1), p.err, 1)) break;
+        }
         mbar_expect_tx(&full_x[s], X_BYTES);
         tma_load_2d(xst + (size_t)s * X_BYTES, &xmap, &full_x[s], kb * kBK, tok0);
-        if (++s == p.nsx) { s = 0; ph ^= 1u; }
+        if (++s == p.nsx) s = 0;
       }
     }
-  } else if (warp == 3) {                  // packed-W producer: runs far ahead (HBM latency + dequant + A ring)
+  } else if (warp == kWWProd) {                  // packed-W producer: runs far ahead (HBM latency + dequant + A ring)
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
@@ -236,34 +251,47 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         if (++s == p.nsw) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWMma || (NI == 2 && warp == kWAlloc)) {
+    // MMA issuer(s).  The tensor pipe accepts roughly one tcgen05.mma at a time, so a single issuing thread leaves it
+    // idle for the ~300 cycles it spends on the two mbarrier waits and the commit of each k-block (measured: 504 cycles
+    // per k-block against the 256-cycle MMA time at TT = 128).  Two threads in two warps alternate k-blocks, each into
+    // its own accumulator (summed in the epilogue), so one thread's waits hide under the other's MMAs.
     if (lane == 0) {
+      const int me = (NI == 2 && warp == kWAlloc) ? 1 : 0;
       // instruction descriptor: D=f32, A=B=f16, both K-major, N=TT, M=128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(kBN >> 4) << 24);
+      const uint64_t bdesc0 = umma_desc_k_sw128(smem_u32(xst));
+      const uint32_t d_tmem = tmem + me * TT;
       bool ok = true;
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < p.kblocks && ok; ++kb) {
-        const int sa = kb % kNA;
-        ok = mbar_wait_bounded(&full_x[s], ph, p.err, 2) && mbar_wait_bounded(&a_full[sa], (kb / kNA) & 1, p.err, 3);
+      // ring cursors advance NI stages per iteration (no runtime division on the issuing thread)
+      int s = me % p.nsx, sa = me;
+      uint32_t ph = (uint32_t)((me / p.nsx) & 1), pha = 0;
+      for (int kb = me; kb < p.kblocks && ok; kb += NI) {
+        ok = mbar_wait_bounded(&full_x[s], ph, p.err, 2);
         TC_STAMP(kb, 4);
+        ok = ok && mbar_wait_bounded(&a_full[sa], pha, p.err, 3);
+        TC_STAMP(kb, 5);
         tc_fence_after();
-        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(xst + (size_t)s * X_BYTES));
+        const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)s * (X_BYTES >> 4));
+        const uint32_t a_src = tmem + kACol + sa * 32;
 #pragma unroll
         for (int j = 0; j < kBK / 16; ++j)
-          tc_mma_ts(tmem, tmem + kACol + sa * 32 + j * 8, bdesc + (uint64_t)(2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
-        tc_commit(&empty_x[s]);
-        tc_commit(&a_empty[sa]);
-        TC_STAMP(kb, 5);
-        if (++s == p.nsx) { s = 0; ph ^= 1u; }
+          tc_mma_ts(d_tmem, a_src + j * 8, bdesc + (uint64_t)(2 * j), idesc, (kb >= NI || j != 0) ? 1u : 0u);
+        TC_STAMP(kb, 6);
+        tc_commit(&a_empty[sa]);                 // frees A stage sa and X stage s
+        TC_STAMP(kb, 7);
+        s += NI;
+        if (s >= p.nsx) { s -= p.nsx; ph ^= 1u; }
+        sa += NI;
+        if (sa >= kNA) { sa -= kNA; pha ^= 1u; }
       }
       tc_commit(acc_full);
     }
-  } else if (warp >= 4) {
+  } else if (warp < kDqWarps * kDqPar) {
     const int q = warp & 3;                     // TMEM lane quadrant this warp may access (warp id % 4)
-    const int half = ((warp - 4) >> 2) & 1;     // which half (32 k) of a stage
-    const int par = (warp - 4) >> 3;            // team: k-blocks par, par + kDqPar, ...
-    const int eidx = (warp - 4) >> 2;           // epilogue slot 0 .. 2*kDqPar-1 (token chunks eidx, eidx + 2*kDqPar, ...)
+    const int half = (warp >> 2) & 1;           // which half (32 k) of a stage
+    const int par = warp >> 3;                  // team: k-blocks par, par + kDqPar, ...
+    const int eidx = warp >> 2;                 // epilogue slot 0 .. 2*kDqPar-1 (token chunks eidx, eidx + 2*kDqPar, ...)
     const int n = q * 32 + lane;                // column within the CTA tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     int gcur = -1;
@@ -322,7 +350,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     for (int kb = par; kb < p.kblocks; kb += kDqPar) {
       const int sa = kb % kNA;
       mbar_wait_bounded(&full_w[s], ph, p.err, 4);
-      if (warp == 4 && lane == 0) TC_STAMP(kb, 0);
+      if ((warp & 7) == 0 && lane == 0) TC_STAMP(kb, 0);
       uint32_t w[WH];
       const uint32_t* ws = ws_lane + (size_t)s * (W_BYTES / 4);
 #pragma unroll
@@ -344,16 +372,16 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
           dq_word(w[r], a + r * (P / 2));
         }
       }
-      if (warp == 4 && lane == 0) TC_STAMP(kb, 1);
+      if ((warp & 7) == 0 && lane == 0) TC_STAMP(kb, 1);
       mbar_wait_bounded(&a_empty[sa], ((kb / kNA) + 1) & 1, p.err, 5);
-      if (warp == 4 && lane == 0) TC_STAMP(kb, 2);
+      if ((warp & 7) == 0 && lane == 0) TC_STAMP(kb, 2);
       tc_fence_after();
       tc_st16(a_dst + sa * 32, a);
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
       mbar_arrive_lane0(&a_full[sa], lane);
-      if (warp == 4 && lane == 0) TC_STAMP(kb, 3);
+      if ((warp & 7) == 0 && lane == 0) TC_STAMP(kb, 3);
       s += kDqPar;
       while (s >= kNS) { s -= kNS; ph ^= 1u; }
     }
@@ -367,7 +395,15 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     for (int c0 = eidx * 32; c0 < TT && ok; c0 += 64 * kDqPar) {
       uint32_t v[32];
       tc_ld32(tmem + lane_addr + c0, v);
-      tc_wait_ld();
+      if (NI == 2 && p.kblocks > 1) {             // the second issuer's accumulator exists only if it had a k-block
+        uint32_t v2[32];
+        tc_ld32(tmem + lane_addr + TT + c0, v2);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+      } else {
+        tc_wait_ld();
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) stg[(size_t)i * (kBN + 8) + n] = __float2half_rn(__uint_as_float(v[i]) + bias);
       asm volatile("bar.sync %0, 128;" ::"r"(1 + eidx) : "memory");
@@ -387,7 +423,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 2) {
+  if (warp == kWAlloc) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
   }

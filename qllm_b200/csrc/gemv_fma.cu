@@ -407,6 +407,8 @@ static cudaError_t fma_launch_k(const FmaParams& p, const FmaPlan& pl, cudaStrea
   if (!attr_done[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(gemv_fma_kernel<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return e;
+    // all of the SM's unified L1/shared array as shared memory, so that consecutive layers' CTAs can be co-resident
+    if (decode_carveout_max()) cudaFuncSetAttribute(gemv_fma_kernel<T, MB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_done[dev & 63] = true;
   }
   cudaLaunchConfig_t cfg = {};

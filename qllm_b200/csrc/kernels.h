@@ -9,6 +9,7 @@
 namespace b200q {
 
 void count_launch(uint64_t n = 1);
+bool decode_carveout_max();     // B200Q_CARVEOUT=0 leaves the driver's default L1/shared split
 
 struct LinearArgs {
   LayerView L;
@@ -55,6 +56,14 @@ void gemv_rp_set_force_cluster(int c);
 bool gemv_rp_describe(const LayerView& L, int M, int out[4]);
 void gemv_rp_set_planner(int mode, double fill_cap);
 void gemv_rp_set_debug(unsigned long long* buf, size_t cap_entries);
+
+// gemv_stream.cu : streaming decode path (per-warp cp.async rings, sibling layers fused in one launch), M <= 8
+static constexpr int kMaxGroupLayers = 3;
+bool gemv_stream_supported(const LinearArgs* a, int n);
+cudaError_t launch_gemv_stream(const LinearArgs* a, int n, const PeerOut* peers);
+bool gemv_stream_describe(const LinearArgs* a, int n, int out[6]);
+void gemv_stream_set_option(int which, int value);
+void gemv_stream_set_debug(unsigned long long* buf, size_t cap_entries);
 
 // gemv_fma.cu : M <= 2 decode path (CUDA-core fp16x2 FMA, register prefetch, cluster split-K)
 bool gemv_fma_supported(const LayerView& L, int M, const __half* x, int64_t ldx);

@@ -122,6 +122,12 @@ class _B200QuantLinearBase(nn.Module):
         return self._shadow_desc
 
     # -- forward ------------------------------------------------------------------------------
+    def __call__(self, x):
+        grp = getattr(self, "_sibling_group", None)
+        if grp is not None:
+            return grp.forward_of(self, x)
+        return super().__call__(x)
+
     def forward(self, x):
         desc = self._descriptor()
         out_shape = x.shape[:-1] + (self.outfeatures,)
@@ -358,6 +364,84 @@ class QuantLinearMarlin(_B200QuantLinearBase):
         gi = self._default_g_idx().long().to(q.device)
         w = ((q.float() - 8.0) * s.float()[gi]).to(torch.float16)
         return w.t().contiguous().cpu(), s.cpu(), torch.full_like(s, 8, dtype=torch.int32).cpu()
+
+
+def linear_group(layers, x):
+    """[layer(x) for layer in layers] for sibling QuantLinears that share their input (q/k/v, gate/up), as one
+    launch of b200q_linear_group at decode sizes (identical results; falls back per layer inside the library)."""
+    descs = [l._descriptor() for l in layers]
+    K = layers[0].infeatures
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.dtype != torch.float16:
+        x2 = x2.to(torch.float16)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    if M == 0 or M > lib.b200q_gemv_max_m() or any(l.infeatures != K for l in layers):
+        return [l(x) for l in layers]
+    n = len(layers)
+    ys = [torch.empty((M, l.outfeatures), dtype=torch.float16, device=x.device) for l in layers]
+    LP = ctypes.POINTER(Layer)
+    arr = (LP * n)(*[ctypes.pointer(d) for d in descs])
+    yp = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
+    ld = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
+    need = max(lib.b200q_workspace_bytes(ctypes.byref(d), M) for d in descs)
+    ws = _workspace(x.device, need)
+    check(lib.b200q_linear_group(arr, n, x2.data_ptr(), M, x2.stride(0), yp, ld, ws.data_ptr(), ws.numel(),
+                                 torch.cuda.current_stream(x.device).cuda_stream), "b200q_linear_group")
+    outs = []
+    for l, y in zip(layers, ys):
+        if y.dtype != x.dtype:
+            y = y.to(x.dtype)
+        outs.append(y.reshape(x.shape[:-1] + (l.outfeatures,)))
+    return outs
+
+
+class _SiblingGroup:
+    """Lazy fusion of sibling QuantLinears behind unmodified callers (HF LlamaAttention calls q_proj(x), k_proj(x),
+    v_proj(x) one after the other on the same tensor): the first sibling's forward computes all of them in one
+    b200q_linear_group launch and parks the others' results, which are handed out when their forward is called
+    with the same tensor (checked by identity and version counter); any other call takes the plain path."""
+
+    def __init__(self, layers):
+        self.layers = list(layers)
+        self.key, self.parked = None, {}
+
+    def forward_of(self, layer, x):
+        key = (id(x), x._version, x.data_ptr(), tuple(x.shape))
+        if self.key == key and id(layer) in self.parked:
+            return self.parked.pop(id(layer))
+        if layer is not self.layers[0] or x.reshape(-1, x.shape[-1]).shape[0] > lib.b200q_gemv_max_m() or not x.is_cuda:
+            return _B200QuantLinearBase.forward(layer, x)
+        outs = linear_group(self.layers, x)
+        self.key = key
+        self._x = x                      # keeps id(x) from being recycled while results are parked
+        self.parked = {id(l): y for l, y in zip(self.layers[1:], outs[1:])}
+        return outs[0]
+
+
+SIBLING_SETS = (("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj"), ("w1", "w3"))
+
+
+def fuse_siblings(model, sibling_sets=SIBLING_SETS):
+    """Install lazy sibling fusion on every parent module that holds a full sibling set of b200q QuantLinears with
+    the same (class, bits, groupsize, infeatures).  Returns the number of groups installed.  The model's own
+    forward code is untouched (drop-in); call once after the checkpoint is loaded."""
+    n = 0
+    for parent in model.modules():
+        for names in sibling_sets:
+            subs = [getattr(parent, nm, None) for nm in names]
+            if not all(isinstance(m, _B200QuantLinearBase) for m in subs):
+                continue
+            a = subs[0]
+            if any(type(m) is not type(a) or m.bits != a.bits or m.groupsize != a.groupsize or m.infeatures != a.infeatures
+                   or getattr(m, "act_order", None) for m in subs):
+                continue
+            grp = _SiblingGroup(subs)
+            for m in subs:
+                m._sibling_group = grp
+            n += 1
+    return n
 
 
 def select_quant_linear(pack_mode: str, wbits: int, quant_method: str):

@@ -274,3 +274,133 @@ def test_tcgen05_gemm_2bit_8bit(layout, bits, gs, K, N, M):
     x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
     y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
     assert rel_err(y, oracle_forward(L, x)) < TOL
+
+
+# ---- streaming decode kernel: sibling groups, plan variations, legacy path ------------------------
+GROUP_CASES = [("GEMM", 4, 128, 1024, (512, 256, 256)), ("GEMM", 4, 64, 512, (1024, 1024)), ("GPTQ", 4, 128, 1024, (256, 96, 160)),
+               ("GPTQ", 2, 64, 512, (128, 64)), ("GPTQ", 8, 128, 512, (128, 128, 64)), ("HQQ", 4, 64, 1024, (256, 128)),
+               ("MARLIN", 4, 128, 1024, (512, 256, 256)), ("GEMM", 4, 128, 4096, (4096, 4096, 4096))]
+
+
+@pytest.mark.parametrize("layout,bits,gs,K,Ns", GROUP_CASES)
+@pytest.mark.parametrize("M", [1, 2, 8])
+def test_decode_sibling_group_vs_oracle(layout, bits, gs, K, Ns, M):
+    """b200q_linear_group (q/k/v-, gate/up-style siblings in one launch) == the per-layer oracle results."""
+    import qllm_b200
+    if K * max(Ns) > 2 ** 22 and M != 1:
+        pytest.skip("full-size group: M=1 only (oracle time)")
+    Ls = [O.make_layer(layout, bits, gs, K, N, seed=K + 13 * N + i, bias=(i == 1), float_zeros=(layout == "HQQ"))
+          for i, N in enumerate(Ns)]
+    layers = [layer_from_dict(L) for L in Ls]
+    x = np.random.default_rng(M + K).standard_normal((M, K)).astype(np.float16)
+    n0 = qllm_b200.lib.b200q_launch_count()
+    ys = qllm_b200.linear_group(layers, torch.from_numpy(x).cuda())
+    assert qllm_b200.lib.b200q_launch_count() - n0 == 1          # fused: one launch for the whole group
+    for L, y in zip(Ls, ys):
+        assert rel_err(y.float().cpu().numpy(), oracle_forward(L, x)) < TOL
+    # and the same as the one-layer-at-a-time path up to the summation order of the K split
+    for layer, y in zip(layers, ys):
+        y1 = layer(torch.from_numpy(x).cuda()).float()
+        assert (y1 - y.float()).abs().max() <= 1e-3 * y1.abs().max()
+
+
+def test_decode_group_mixed_falls_back_per_layer():
+    import qllm_b200
+    La = O.make_layer("GEMM", 4, 128, 512, 256, seed=1)
+    Lb = O.make_layer("GEMM", 4, 64, 512, 256, seed=2)               # different group size: not fusable
+    layers = [layer_from_dict(La), layer_from_dict(Lb)]
+    x = np.random.default_rng(0).standard_normal((1, 512)).astype(np.float16)
+    n0 = qllm_b200.lib.b200q_launch_count()
+    ys = qllm_b200.linear_group(layers, torch.from_numpy(x).cuda())
+    assert qllm_b200.lib.b200q_launch_count() - n0 == 2
+    for L, y in zip((La, Lb), ys):
+        assert rel_err(y.float().cpu().numpy(), oracle_forward(L, x)) < TOL
+
+
+@pytest.mark.parametrize("opt,val", [("st_cluster", 1), ("st_cluster", 3), ("st_cluster", 8), ("st_depth", 2), ("st_depth", 16),
+                                     ("st_tpc", 2), ("st_tpc", 4), ("st_target", 400)])
+@pytest.mark.parametrize("layout,K,N", [("GEMM", 2048, 640), ("GPTQ", 2048, 416), ("MARLIN", 2048, 320)])
+def test_stream_kernel_plan_variations(opt, val, layout, K, N):
+    """Every (cluster, ring depth, tiles-per-CTA) the planner can pick gives the same answer."""
+    import qllm_b200
+    lib = qllm_b200.lib
+    if layout == "MARLIN":
+        N = 512                                                      # the Marlin ctor wants N % 256 == 0
+    L = O.make_layer(layout, 4, 128, K, N, seed=K + N)
+    layer = layer_from_dict(L)
+    x = np.random.default_rng(3).standard_normal((3, K)).astype(np.float16)
+    xt = torch.from_numpy(x).cuda()
+    base = layer(xt)
+    assert lib.b200q_debug_set_option(opt.encode(), float(val)) == 0
+    try:
+        y = layer(xt)
+        y1 = layer(xt[:1])
+    finally:
+        lib.b200q_debug_set_option(opt.encode(), 0.0 if opt != "st_target" else 120.0)
+    ref = oracle_forward(L, x)
+    assert rel_err(y.float().cpu().numpy(), ref) < TOL
+    assert rel_err(y1.float().cpu().numpy(), ref[:1]) < TOL
+    assert rel_err(base.float().cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("layout,bits,gs,K,N", [("GEMM", 4, 128, 1024, 1024), ("GPTQ", 4, 128, 1024, 512), ("GPTQ", 2, 64, 1024, 128),
+                                                ("MARLIN", 4, 128, 1024, 512), ("GEMM", 4, 128, 11008, 4096)])
+def test_pre_streaming_decode_kernels_still_agree(layout, bits, gs, K, N):
+    """B200Q_GEMV=rp path (whole-slice prefetch kernels) kept as an alternative: same oracle, same bar."""
+    import qllm_b200
+    lib = qllm_b200.lib
+    L = O.make_layer(layout, bits, gs, K, N, seed=K + N + 1) if K * N < 2 ** 22 else None
+    if L is None:
+        rng = np.random.default_rng(1)
+        L = dict(layout=layout, bits=4, group_size=gs, K=K, N=N, bias=None, g_idx=O.default_g_idx(K, gs))
+        L["qweight"] = rng.integers(-2**31, 2**31, size=(K, N // 8), dtype=np.int64).astype(np.int32)
+        L["qzeros"] = rng.integers(-2**31, 2**31, size=(K // gs, N // 8), dtype=np.int64).astype(np.int32)
+        L["scales"] = rng.uniform(0.002, 0.012, size=(K // gs, N)).astype(np.float16)
+    layer = layer_from_dict(L)
+    x = torch.randn(2, K, dtype=torch.float16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    y_stream = layer(x)
+    assert lib.b200q_debug_set_option(b"stream", 0.0) == 0
+    try:
+        y_old = layer(x)
+    finally:
+        lib.b200q_debug_set_option(b"stream", 1.0)
+    W = layer.dequantize()
+    ref = x.double() @ W.double()
+    for y in (y_stream, y_old):
+        assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < TOL
+
+
+def test_fuse_siblings_is_transparent_to_the_caller():
+    """HF-style attention / MLP modules calling q_proj(x), k_proj(x), v_proj(x) one after the other get the fused
+    launch without any change to their forward code, and any other calling pattern still gives the right answer."""
+    import qllm_b200
+
+    class Attn(torch.nn.Module):
+        def __init__(self, mods):
+            super().__init__()
+            self.q_proj, self.k_proj, self.v_proj, self.o_proj = mods
+
+        def forward(self, h):
+            q, k, v = self.q_proj(h), self.k_proj(h), self.v_proj(h)
+            return self.o_proj(q + k + v)
+
+    K = 512
+    Ls = [O.make_layer("GEMM", 4, 128, K, K, seed=40 + i) for i in range(4)]
+    attn = Attn([layer_from_dict(L) for L in Ls])
+    h = torch.randn(1, 1, K, dtype=torch.float16, device="cuda")
+    plain = attn(h)
+    n0 = qllm_b200.lib.b200q_launch_count()
+    assert qllm_b200.fuse_siblings(attn) == 1
+    fused = attn(h)
+    assert qllm_b200.lib.b200q_launch_count() - n0 == 2              # qkv in one launch + o_proj
+    assert (plain.float() - fused.float()).abs().max() <= 2e-3 * plain.float().abs().max()
+    # out-of-order / different-input calls bypass the parked results
+    h2 = torch.randn(1, 1, K, dtype=torch.float16, device="cuda")
+    k_only = attn.k_proj(h2)
+    assert torch.equal(k_only, qllm_b200.q_layers._B200QuantLinearBase.forward(attn.k_proj, h2))
+    q1 = attn.q_proj(h)
+    v2 = attn.v_proj(h2)                                             # parked v belongs to h, not h2
+    assert torch.equal(v2, qllm_b200.q_layers._B200QuantLinearBase.forward(attn.v_proj, h2))
+    h.add_(1.0)                                                      # in-place update bumps the version counter
+    k3 = attn.k_proj(h)
+    assert torch.equal(k3, qllm_b200.q_layers._B200QuantLinearBase.forward(attn.k_proj, h))

@@ -1,4 +1,4 @@
-"""Per-k-block phase stamps of CTA (0,0) of the tcgen05 GEMM (b200q_debug_set_timeline)."""
+"""Per-k-block phase stamps (SM cycles, %clock64) of CTA (0,0) of the tcgen05 GEMM (b200q_debug_set_timeline)."""
 import ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,11 +13,17 @@ buf = torch.zeros(1 << 16, dtype=torch.int64, device=dev)
 qllm_b200.lib.b200q_debug_set_timeline(buf.data_ptr(), buf.numel() * 8)
 l(x); torch.cuda.synchronize()
 qllm_b200.lib.b200q_debug_set_timeline(None, 0)
-t = buf.cpu().numpy().reshape(-1, 8)[: K // 64].astype(np.float64)
+nkb = K // 64
+t = buf.cpu().numpy().reshape(-1, 8)[:nkb].astype(np.float64)
 t0 = t[t > 0].min()
-names = ["dq:in_landed", "dq:alu_done", "dq:a_free", "dq:st_issued", "mma:ready", "mma:issued"]
-print("kb  " + "  ".join(f"{n:>13s}" for n in names) + "   (us since first stamp)")
-for kb in list(range(0, 12)) + list(range(K // 64 - 4, K // 64)):
-    print(f"{kb:3d} " + "  ".join(f"{(t[kb, j] - t0) / 1e3:13.2f}" for j in range(6)))
-d = np.diff(t[:, 5])
-print("median us per k-block (mma issue to issue):", np.median(d) / 1e3)
+names = ["dq:w_landed", "dq:alu_done", "dq:a_free", "dq:signalled", "mma:x_landed", "mma:a_landed", "mma:issued", "mma:committed"]
+print("kb  " + "  ".join(f"{n:>13s}" for n in names) + "   (SM cycles since first stamp)")
+for kb in list(range(0, 16)) + list(range(nkb // 2, nkb // 2 + 8)) + list(range(nkb - 6, nkb)):
+    print(f"{kb:3d} " + "  ".join(f"{(t[kb, j] - t0):13.0f}" for j in range(8)))
+mid = slice(8, nkb - 4)
+print("median cycles per k-block (mma issue to issue):", np.median(np.diff(t[:, 6])[mid]))
+print("median cycles: wait X", np.median((t[:, 4] - np.roll(t[:, 7], 1))[mid]), "| wait A", np.median((t[:, 5] - t[:, 4])[mid]),
+      "| issue 4 MMAs", np.median((t[:, 6] - t[:, 5])[mid]), "| 2 commits", np.median((t[:, 7] - t[:, 6])[mid]))
+print("median cycles dequant team: LDS+ALU", np.median((t[:, 1] - t[:, 0])[mid]), "| wait A stage free", np.median((t[:, 2] - t[:, 1])[mid]),
+      "| st+wait::st+arrive", np.median((t[:, 3] - t[:, 2])[mid]), "| A signalled -> MMA saw it", np.median((t[:, 5] - t[:, 3])[mid]))
+print("total cycles first stamp -> last commit:", t[:, 7].max() - t0)

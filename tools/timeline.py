@@ -1,5 +1,6 @@
-"""Phase timeline of the decode kernel across back-to-back launches (PDL chain), from the per-CTA
-%globaltimer stamps of b200q_debug_set_timeline.  python tools/timeline.py [--layout GEMM] [--shape 4096x4096]"""
+"""Phase timeline of the decode kernel across a chain of launches replayed from ONE CUDA graph (PDL edges, no host
+launch gaps), from the per-CTA %globaltimer stamps of b200q_debug_set_timeline.
+python tools/timeline.py [--layout GEMM] [--shape 4096x4096] [--launches 12]"""
 import argparse
 import ctypes
 import os
@@ -25,23 +26,35 @@ x = torch.randn(1, K, dtype=torch.float16, device=dev)
 y = torch.empty(1, N, dtype=torch.float16, device=dev)
 descs = [l._descriptor() for l in layers]
 ws = torch.zeros(1 << 22, dtype=torch.uint8, device=dev)
-st = torch.cuda.current_stream().cuda_stream
 lib = qllm_b200.lib
-for i in range(copies):
-    qllm_b200.check(lib.b200q_linear(ctypes.byref(descs[i]), x.data_ptr(), 1, K, y.data_ptr(), N, ws.data_ptr(), ws.numel(), st))
-torch.cuda.synchronize()
 buf = torch.zeros(1 << 20, dtype=torch.int64, device=dev)
-lib.b200q_debug_set_timeline(buf.data_ptr(), buf.numel() * 8)
-for i in range(a.launches):
-    qllm_b200.check(lib.b200q_linear(ctypes.byref(descs[i % copies]), x.data_ptr(), 1, K, y.data_ptr(), N, ws.data_ptr(), ws.numel(), st))
+
+
+def chain(st, n):
+    for i in range(n):
+        qllm_b200.check(lib.b200q_linear(ctypes.byref(descs[i % copies]), x.data_ptr(), 1, K, y.data_ptr(), N, ws.data_ptr(), ws.numel(), st))
+
+
+chain(torch.cuda.current_stream().cuda_stream, copies)
 torch.cuda.synchronize()
-lib.b200q_debug_set_timeline(None, 0)
+s = torch.cuda.Stream()
+with torch.cuda.stream(s):
+    g = torch.cuda.CUDAGraph()
+    lib.b200q_debug_set_timeline(buf.data_ptr(), buf.numel() * 8)     # stamp offsets are fixed at capture time
+    with torch.cuda.graph(g, stream=s):
+        chain(torch.cuda.current_stream().cuda_stream, a.launches)
+    lib.b200q_debug_set_timeline(None, 0)
+    g.replay()
+    torch.cuda.synchronize()
+    buf.zero_()
+    g.replay()
+torch.cuda.synchronize()
 t = buf.cpu().numpy().reshape(-1, 8)
 used = np.nonzero(t[:, 0])[0]
 nct = len(used) // a.launches
-print(f"{a.layout} {K}x{N}: {nct} CTAs per launch")
+print(f"{a.layout} {K}x{N}: {nct} CTAs per launch (CUDA graph replay)")
 t0 = t[used][:, 0].min()
-names = ["start", "prefetch_issued", "upstream_done", "operands_ready", "math_done", "cluster_reduced", "stored"]
+names = ["start", "ring+table", "upstream_done", "-", "math_done", "cluster_reduced", "stored"]
 for li in range(a.launches):
     blk = t[used[li * nct:(li + 1) * nct]].astype(np.float64)
     row = []
@@ -49,5 +62,5 @@ for li in range(a.launches):
         col = blk[:, j]
         col = col[col > 0]
         if len(col):
-            row.append(f"{nm}[{(col.min()-t0)/1e3:7.2f},{(np.median(col)-t0)/1e3:7.2f},{(col.max()-t0)/1e3:7.2f}]")
+            row.append(f"{nm}[{(col.min()-t0)/1e3:6.2f},{(np.median(col)-t0)/1e3:6.2f},{(col.max()-t0)/1e3:6.2f}]")
     print(f"launch {li:2d}: " + " ".join(row))
