@@ -43,7 +43,7 @@ struct StParams {
   const __half* x;
   int64_t ldx;
   int M;
-  int cluster, tpc, depth, steps_total, group_shift, gcap;
+  int cluster, tpc, depth, steps_total, group_shift, gcap, split_q, split_r;
   int x_stride;                                  // bytes of one staged activation row
   int red_stride;                                // floats between two warps' partial-sum vectors
   int off_x, off_tab, off_red, off_rbuf, off_rbar, off_ring, off_zpad;
@@ -111,8 +111,8 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
 #pragma unroll
   for (int r = 0; r < NV; ++r) {
     const int idx = tid + r * kRpThreads;
-    if (idx < totalv && idx / p.M < ncols_cta) {
-      const int n = idx / p.M, m = idx - n * p.M;
+    const int n = (MC == 1) ? idx : idx / p.M, m = (MC == 1) ? 0 : idx - n * p.M;
+    if (idx < totalv && n < ncols_cta) {
       float o = v[r];
       if (SL.bias) o += __half2float(__ldg(SL.bias + n0 + n));
       const __half h = __float2half_rn(o);
@@ -164,10 +164,11 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_stream_kernel(const __grid
   const int n0 = t0 * NT;
   const int ncols_cta = min(nt * NT, L.N - n0);
 
-  const int U = cs * kWarps, S = p.steps_total;
+  // K split: unit u (= cluster rank * 8 + warp) owns steps [u q + min(u, r), (u + 1) q + min(u + 1, r)), q = S / U, r = S % U
   const int unit = rank * kWarps + warp;
-  const int s_begin = (int)(((long long)unit * S) / U), s_end = (int)(((long long)(unit + 1) * S) / U);
-  const int cta_s0 = (int)(((long long)rank * kWarps * S) / U), cta_s1 = (int)(((long long)(rank + 1) * kWarps * S) / U);
+  const int s_begin = unit * p.split_q + min(unit, p.split_r), s_end = (unit + 1) * p.split_q + min(unit + 1, p.split_r);
+  const int cta_s0 = rank * kWarps * p.split_q + min(rank * kWarps, p.split_r);
+  const int cta_s1 = (rank + 1) * kWarps * p.split_q + min((rank + 1) * kWarps, p.split_r);
   const int k_cta0 = cta_s0 * T::KSTEP, k_cta1 = cta_s1 * T::KSTEP;
   RpCtx cx;
   cx.M = p.M; cx.k_cta0 = k_cta0; cx.x_stride = p.x_stride; cx.group = p.group; cx.gshift = p.group_shift;
@@ -202,18 +203,23 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_stream_kernel(const __grid
   for (int d = 0; d < D; ++d) issue_next(d);
 
   // per-(group, column) (scale, zero) pairs of the CTA's k-slice, fp32: [tile][group][NT]
-  for (int item = tid; item < nt * g_count * (NT / 8); item += kRpThreads) {
-    const int c8 = (item % (NT / 8)) * 8, gl = (item / (NT / 8)) % g_count, t = item / ((NT / 8) * g_count);
-    const int n = n0 + t * NT + c8;
-    float2 e[8];
-    if (n < L.N) T::table_entries8(L, cx.g_first + gl, n, e);
-    else {
+  {
+    constexpr int TX = NT / 8, TY = kRpThreads / TX;        // a thread owns one 8-column block; rows (tile, group) strided by TY
+    const int c8 = (tid % TX) * 8;
+    for (int t = 0; t < nt; ++t) {
+      const int n = n0 + t * NT + c8;
+      for (int gl = tid / TX; gl < g_count; gl += TY) {
+        float2 e[8];
+        if (n < L.N) T::table_entries8(L, cx.g_first + gl, n, e);
+        else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
+          for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
+        }
+        float4* dst = reinterpret_cast<float4*>(tab + ((size_t)t * p.gcap + gl) * NT + c8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(e[2 * i].x, e[2 * i].y, e[2 * i + 1].x, e[2 * i + 1].y);
+      }
     }
-    float4* dst = reinterpret_cast<float4*>(tab + ((size_t)t * p.gcap + gl) * NT + c8);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = make_float4(e[2 * i].x, e[2 * i].y, e[2 * i + 1].x, e[2 * i + 1].y);
   }
   __syncthreads();                                          // table visible; still ahead of the dependency
   ST_STAMP(1);
@@ -223,10 +229,9 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_stream_kernel(const __grid
   ST_STAMP(2);
   {
     const int kw0 = s_begin * T::KSTEP, nv = (nsw * T::KSTEP) >> 3;
-    for (int idx = lane; idx < p.M * nv; idx += 32) {
-      const int m = idx / nv, v = idx - m * nv;
-      cp_async16(xs + (size_t)m * p.x_stride + (size_t)(kw0 - k_cta0) * 2 + 16 * v, p.x + (size_t)m * p.ldx + kw0 + 8 * v);
-    }
+    for (int m = 0; m < (MC == 1 ? 1 : p.M); ++m)
+      for (int v = lane; v < nv; v += 32)
+        cp_async16(xs + (size_t)m * p.x_stride + (size_t)(kw0 - k_cta0) * 2 + 16 * v, p.x + (size_t)m * p.ldx + kw0 + 8 * v);
     cp_async_commit();
   }
 
@@ -327,10 +332,11 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_awq_lean_kernel(const __gr
   const int n0 = t0 * NT;
   const int ncols_cta = min(nt * NT, L.N - n0);
 
-  const int U = cs * kWarps, S = p.steps_total;
+  // K split: unit u (= cluster rank * 8 + warp) owns steps [u q + min(u, r), (u + 1) q + min(u + 1, r)), q = S / U, r = S % U
   const int unit = rank * kWarps + warp;
-  const int s_begin = (int)(((long long)unit * S) / U), s_end = (int)(((long long)(unit + 1) * S) / U);
-  const int cta_s0 = (int)(((long long)rank * kWarps * S) / U), cta_s1 = (int)(((long long)(rank + 1) * kWarps * S) / U);
+  const int s_begin = unit * p.split_q + min(unit, p.split_r), s_end = (unit + 1) * p.split_q + min(unit + 1, p.split_r);
+  const int cta_s0 = rank * kWarps * p.split_q + min(rank * kWarps, p.split_r);
+  const int cta_s1 = (rank + 1) * kWarps * p.split_q + min((rank + 1) * kWarps, p.split_r);
   const int k_cta0 = cta_s0 * KSTEP, k_cta1 = cta_s1 * KSTEP;
   const int gsh = p.group_shift;
   const int g_first = k_cta0 >> gsh;
@@ -362,11 +368,11 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_awq_lean_kernel(const __gr
   const uint32_t* src = L.qw + (size_t)(s_begin * KSTEP + r0) * pitch + (size_t)(n0 >> 3) + 4 * cc;
   bool pc = cc * 32 < min(NT, L.N - n0);
   int irem = nsw, itiles = nt;                                           // issue cursor: steps left in its tile, tiles left
-  auto issue = [&](int slot) {
+  auto issue = [&](uint32_t dst) {
     if (itiles > 0) {
       if (pc) {
-        cp_async16_s(wr + slot * STEP_BYTES, src);
-        cp_async16_s(wr + slot * STEP_BYTES + 512, src + src_hi);
+        cp_async16_s(dst, src);
+        cp_async16_s(dst + 512, src + src_hi);
       }
       src += src_step;
       if (--irem == 0) {                                                 // next 128-column tile, back to this warp's first k
@@ -379,25 +385,29 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_awq_lean_kernel(const __gr
     cp_async_commit();
   };
   if (nsw == 0) itiles = 0;
-#pragma unroll
-  for (int d = 0; d < D; ++d) issue(d);
+#pragma unroll 1
+  for (int d = 0; d < D; ++d) issue(wr + d * STEP_BYTES);
 
   // (scale, zero) table of the CTA's k-slice: [tile][group][NT] float2; zero pad for lanes without an activation row
-  for (int item = tid; item < nt * g_count * (NT / 8); item += kRpThreads) {
-    const int c8 = (item % (NT / 8)) * 8, gl = (item / (NT / 8)) % g_count, tt = item / ((NT / 8) * g_count);
-    const int n = n0 + tt * NT + c8;
-    float2 e[8];
-    if (n < L.N) T::table_entries8(L, g_first + gl, n, e);
-    else {
+  {
+    const int c8 = (tid & 15) * 8;                         // a thread owns one 8-column block; groups strided by 16
+    for (int tt = 0; tt < nt; ++tt) {
+      const int n = n0 + tt * NT + c8;
+      for (int gl = tid >> 4; gl < g_count; gl += 16) {
+        float2 e[8];
+        if (n < L.N) T::table_entries8(L, g_first + gl, n, e);
+        else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
+          for (int i = 0; i < 8; ++i) e[i] = make_float2(0.f, 0.f);
+        }
+        float4* dst = reinterpret_cast<float4*>(tab + ((size_t)tt * p.gcap + gl) * NT + c8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(e[2 * i].x, e[2 * i].y, e[2 * i + 1].x, e[2 * i + 1].y);
+      }
     }
-    float4* dst = reinterpret_cast<float4*>(tab + ((size_t)tt * p.gcap + gl) * NT + c8);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = make_float4(e[2 * i].x, e[2 * i].y, e[2 * i + 1].x, e[2 * i + 1].y);
   }
   uint32_t* zpad = reinterpret_cast<uint32_t*>(smem + p.off_zpad);
-  if (tid < (D * 32 + 64) / 4) zpad[tid] = 0u;
+  if (tid < 16) zpad[tid] = 0u;
   __syncthreads();
   ST_STAMP(1);
 
@@ -406,15 +416,14 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_awq_lean_kernel(const __gr
   ST_STAMP(2);
   {
     const int kw0 = s_begin * KSTEP, nv = (nsw * KSTEP) >> 3;
-    for (int idx = lane; idx < p.M * nv; idx += 32) {
-      const int m = idx / nv, v = idx - m * nv;
-      cp_async16(xs + (size_t)m * p.x_stride + (size_t)(kw0 - k_cta0) * 2 + 16 * v, p.x + (size_t)m * p.ldx + kw0 + 8 * v);
-    }
+    for (int m = 0; m < (MC == 1 ? 1 : p.M); ++m)
+      for (int v = lane; v < nv; v += 32)
+        cp_async16(xs + (size_t)m * p.x_stride + (size_t)(kw0 - k_cta0) * 2 + 16 * v, p.x + (size_t)m * p.ldx + kw0 + 8 * v);
     cp_async_commit();
   }
   // B fragment source: row g of the staged activations (k-slots 2t, 2t+1 | +8), or the zero pad
   uint32_t xp = (g < p.M) ? smem_u32(xs) + (uint32_t)(g * p.x_stride + (s_begin * KSTEP - k_cta0 + 2 * t) * 2) : smem_u32(zpad);
-  const uint32_t xadv = (g < p.M) ? D * 32u : 0u, xrewind = (g < p.M) ? (uint32_t)(nsw * 32) : 0u;
+  const uint32_t xstep = (g < p.M) ? 32u : 0u, xrewind = (g < p.M) ? (uint32_t)(nsw * 32) : 0u;
 
   float tot[8][4], acc[8][4], accS[4] = {0.f, 0.f, 0.f, 0.f};
   zero4(tot);
@@ -422,7 +431,7 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_awq_lean_kernel(const __gr
   const int spg = p.group >> 4;                                          // steps per group
   const int gl0 = ((s_begin * KSTEP) >> gsh) - g_first;
   const int gleft0 = spg - (s_begin & (spg - 1));
-  int gleft = gleft0, crem = nsw, tcur = 0, dirty = 0;
+  int gleft = gleft0, crem = nsw, tcur = 0;
   const float2* tabrow = tab + (size_t)gl0 * NT + 16 * g;
   float* redw = red + (size_t)warp * p.red_stride;
   const int ms = p.M;
@@ -435,54 +444,51 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_awq_lean_kernel(const __gr
     }
     zero4(acc);
     accS[0] = accS[1] = accS[2] = accS[3] = 0.f;
-    dirty = 0;
   };
 
   cp_async_wait<0>();
   __syncwarp();
-  for (int base = 0; base < total; base += D) {
+  // One rolled loop (the body must stay resident in the instruction cache: an unrolled-by-D version measured most of
+  // its stall cycles on instruction fetch); the slot's shared-memory addresses are base + slot * 1 KB.
+#pragma unroll 1
+  for (int i = 0; i < total; ++i) {
+    const uint32_t so = (uint32_t)(i & (D - 1)) * STEP_BYTES;
+    cp_async_wait<D - 1>();
+    __syncwarp();
+    const uint2 wr0 = lds64_s(rdA + so), wr1 = lds64_s(rdB + so);
+    const uint2 wr2 = lds64_s(rdA + so + 512), wr3 = lds64_s(rdB + so + 512);
+    const uint32_t b0 = lds32_s(xp), b1 = lds32_s(xp + 16);
+    xp += xstep;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      if (base + d < total) {                                            // warp-uniform
-        cp_async_wait<D - 1>();
-        __syncwarp();
-        const uint2 wr0 = lds64_s(rdA + d * STEP_BYTES), wr1 = lds64_s(rdB + d * STEP_BYTES);
-        const uint2 wr2 = lds64_s(rdA + d * STEP_BYTES + 512), wr3 = lds64_s(rdB + d * STEP_BYTES + 512);
-        const uint32_t b0 = lds32_s(xp + d * 32), b1 = lds32_s(xp + d * 32 + 16);
-#pragma unroll
-        for (int wc = 0; wc < 2; ++wc) {
-          const uint32_t wa = wc ? wr0.y : wr0.x, wb = wc ? wr1.y : wr1.x;
-          const uint32_t wcw = wc ? wr2.y : wr2.x, wd = wc ? wr3.y : wr3.x;
-          const uint32_t u01 = prmt(wa, wb, 0x5410), v01 = prmt(wa, wb, 0x7632);
-          const uint32_t u23 = prmt(wcw, wd, 0x5410), v23 = prmt(wcw, wd, 0x7632);
-          const uint32_t u01h = u01 >> 8, v01h = v01 >> 8, u23h = u23 >> 8, v23h = v23 >> 8;
-          mma_16816(acc[wc * 4 + 0], u01 & LO4, v01 & LO4, u23 & LO4, v23 & LO4, b0, b1);
-          mma_16816(acc[wc * 4 + 1], u01 & HI4, v01 & HI4, u23 & HI4, v23 & HI4, b0, b1);
-          mma_16816(acc[wc * 4 + 2], u01h & LO4, v01h & LO4, u23h & LO4, v23h & LO4, b0, b1);
-          mma_16816(acc[wc * 4 + 3], u01h & HI4, v01h & HI4, u23h & HI4, v23h & HI4, b0, b1);
-        }
-        mma_16816(accS, ONES, ONES, ONES, ONES, b0, b1);
-        dirty = 1;
-        __syncwarp();                                                    // every lane has read slot d
-        issue(d);
-        if (--gleft == 0) {                                              // group boundary
-          group_close();
-          tabrow += NT;
-          gleft = spg;
-        }
-        if (--crem == 0) {                                               // tile boundary: park the partial sums
-          if (dirty) group_close();
-          T::store_tot(redw + (size_t)tcur * NT * ms, ms, tot, lane, p.M);
-          zero4(tot);
-          ++tcur;
-          crem = nsw;
-          gleft = gleft0;
-          tabrow = tab + ((size_t)tcur * p.gcap + gl0) * NT + 16 * g;
-          xp -= xrewind;                                                 // back to this warp's first k
-        }
+    for (int wc = 0; wc < 2; ++wc) {
+      const uint32_t wa = wc ? wr0.y : wr0.x, wb = wc ? wr1.y : wr1.x;
+      const uint32_t wcw = wc ? wr2.y : wr2.x, wd = wc ? wr3.y : wr3.x;
+      const uint32_t u01 = prmt(wa, wb, 0x5410), v01 = prmt(wa, wb, 0x7632);
+      const uint32_t u23 = prmt(wcw, wd, 0x5410), v23 = prmt(wcw, wd, 0x7632);
+      const uint32_t u01h = u01 >> 8, v01h = v01 >> 8, u23h = u23 >> 8, v23h = v23 >> 8;
+      mma_16816(acc[wc * 4 + 0], u01 & LO4, v01 & LO4, u23 & LO4, v23 & LO4, b0, b1);
+      mma_16816(acc[wc * 4 + 1], u01 & HI4, v01 & HI4, u23 & HI4, v23 & HI4, b0, b1);
+      mma_16816(acc[wc * 4 + 2], u01h & LO4, v01h & LO4, u23h & LO4, v23h & LO4, b0, b1);
+      mma_16816(acc[wc * 4 + 3], u01h & HI4, v01h & HI4, u23h & HI4, v23h & HI4, b0, b1);
+    }
+    mma_16816(accS, ONES, ONES, ONES, ONES, b0, b1);
+    __syncwarp();                                                        // every lane has read the slot
+    issue(wr + so);
+    --crem;
+    if (--gleft == 0 || crem == 0) {                                     // group and / or tile boundary (warp-uniform)
+      group_close();
+      tabrow += NT;
+      gleft = spg;
+      if (crem == 0) {                                                   // park the tile's partial sums, restart at this warp's first k
+        T::store_tot(redw + (size_t)tcur * NT * ms, ms, tot, lane, p.M);
+        zero4(tot);
+        ++tcur;
+        crem = nsw;
+        gleft = gleft0;
+        tabrow = tab + ((size_t)tcur * p.gcap + gl0) * NT + 16 * g;
+        xp -= xrewind;
       }
     }
-    xp += xadv;
   }
   if (total == 0) {
     cp_async_wait<0>();
@@ -583,7 +589,9 @@ static bool st_plan(const LinearArgs* a, int n, StPlan& pl) {
   if (pl.lean) depth = depth < 4 ? 4 : (depth > 8 ? 8 : depth);            // instantiated ring depths
   pl.depth = depth;
 
-  const int slice_steps = (pl.steps_total + cs - 1) / cs + 1;
+  // unit u of the K split owns q (+1 for the first r units) steps, so cluster rank 0 holds the longest slice
+  const int split_q = pl.steps_total / (cs * kWarps), split_r = pl.steps_total % (cs * kWarps);
+  const int slice_steps = kWarps * split_q + (split_r < kWarps ? split_r : kWarps);
   const int kslice = slice_steps * pl.KSTEP;
   pl.x_stride = kslice * 2;
   pl.x_stride += (64 - (pl.x_stride % 128) + 128) % 128;
@@ -703,6 +711,7 @@ cudaError_t launch_gemv_stream(const LinearArgs* a, int n, const PeerOut* peers)
   p.layout = L.layout; p.bits = L.bits; p.group = L.group; p.K = L.K; p.G = L.G; p.zero_bias = L.zero_bias;
   p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M;
   p.cluster = pl.cluster; p.tpc = pl.tpc; p.depth = pl.depth; p.steps_total = pl.steps_total; p.group_shift = pl.group_shift;
+  p.split_q = pl.steps_total / (pl.cluster * kWarps); p.split_r = pl.steps_total % (pl.cluster * kWarps);
   p.gcap = pl.gcap; p.x_stride = pl.x_stride; p.red_stride = pl.tpc * pl.NT * a[0].M;
   p.off_x = pl.off_x; p.off_tab = pl.off_tab; p.off_red = pl.off_red; p.off_rbuf = pl.off_rbuf; p.off_rbar = pl.off_rbar;
   p.off_ring = pl.off_ring; p.off_zpad = pl.off_zpad;
