@@ -180,13 +180,13 @@ class DecodeStep:
         self.bufs = {n: torch.zeros(M, N, **f16) for n, _, N in SHAPES}
         self.part = {n: torch.zeros(M, max(shard_cols(N, world, r)[1] - shard_cols(N, world, r)[0] for r in range(world)), **f16)
                      for n, _, N in SHAPES} if world > 1 else None
-        need = max(self.lib.b200q_workspace_bytes(ctypes.byref(l._descriptor()), M) for l in blocks[0].values())
+        need = max(self.lib.b200q_workspace_bytes(ctypes.byref(l._decode_descriptor(M)), M) for l in blocks[0].values())
         self.ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=dev)
         self.torch = torch
 
     def _call(self, layer, x, name, stream):
         from qllm_b200 import check
-        desc = layer._descriptor()
+        desc = layer._decode_descriptor(self.M)
         if self.world == 1:
             y = self.bufs[name]
             check(self.lib.b200q_linear(ctypes.byref(desc), x.data_ptr(), self.M, x.stride(0), y.data_ptr(), y.stride(0),
@@ -216,7 +216,7 @@ class DecodeStep:
             return [self._call(l, x, n, stream) for l, n in zip(layers, names)]
         from qllm_b200 import check, Layer
         n = len(layers)
-        descs = [l._descriptor() for l in layers]
+        descs = [l._decode_descriptor(self.M) for l in layers]
         ys = [self.bufs[nm] for nm in names]
         arr = (ctypes.POINTER(Layer) * n)(*[ctypes.pointer(d) for d in descs])
         yp = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
@@ -303,7 +303,7 @@ def run_b200q(args, rank, world, local_rank):
     achieved = total_bytes * world / world / (ms_per_step * 1e-3) / 1e9      # whole-job algorithmic GB/s
     roofline = {"bound": "hbm", "achieved": achieved / world, "peak": P["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / world / P["hbm_gbs"], "traffic": None, "peak_source": P["source"],
-                "kernel": "gemv_stream_kernel<RpAwq> (decode)", "bytes_per_launch": total_bytes / launches_per_step,
+                "kernel": "gemv_imma_kernel (decode, IMMA.16832 on the K-packed re-layout)", "bytes_per_launch": total_bytes / launches_per_step,
                 "us_per_launch": ms_per_step * 1e3 / launches_per_step, "per_gpu": True}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))

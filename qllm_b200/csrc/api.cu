@@ -76,6 +76,11 @@ static int gemv_variant() {
       const char* sv = getenv(so[i]);
       if (sv) gemv_stream_set_option(i, atoi(sv));
     }
+    const char* io[5] = {"B200Q_IMMA", "B200Q_IM_CLUSTER", "B200Q_IM_DEPTH", "B200Q_IM_TPC", "B200Q_IM_TARGET"};
+    for (int i = 0; i < 5; ++i) {
+      const char* sv = getenv(io[i]);
+      if (sv) gemv_imma_set_option(i, atoi(sv));
+    }
     if (e && e[0] == 'v') gemv_fma_set_max_m(0);        // any explicit B200Q_GEMV=v* disables the FMA kernel
     const char* fm = getenv("B200Q_FMA_MAX_M");
     if (fm) gemv_fma_set_max_m(atoi(fm));
@@ -107,7 +112,10 @@ static LinearArgs probe_args(const LayerView& V, int M, const __half* x, int64_t
 }
 static bool decode_supported(const LayerView& V, int M, const __half* x, int64_t ldx) {
   gemv_variant();
-  if (g_use_stream) { const LinearArgs a = probe_args(V, M, x, ldx); if (gemv_stream_supported(&a, 1)) return true; }
+  if (g_use_stream) {
+    const LinearArgs a = probe_args(V, M, x, ldx);
+    if (gemv_imma_supported(&a, 1) || gemv_stream_supported(&a, 1)) return true;
+  }
   if (gemv_variant() == 2 && (gemv_fma_supported(V, M, x, ldx) || gemv_rp_supported(V, M, x, ldx))) return true;
   return gemv_mma_supported(V, M, x, ldx);
 }
@@ -151,6 +159,7 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   a.L = V; a.x = (const __half*)x; a.ldx = ldx; a.M = (int)M; a.y = (__half*)y; a.ldy = ldy; a.n_offset = n_offset;
   a.workspace = ws; a.workspace_bytes = ws_bytes; a.stream = (cudaStream_t)stream;
   if (kern == KERNEL_GEMV_MMA) {
+    if (g_use_stream && gemv_imma_supported(&a, 1)) return cuda_status(launch_gemv_imma(&a, 1, peers));
     if (g_use_stream && gemv_stream_supported(&a, 1)) return cuda_status(launch_gemv_stream(&a, 1, peers));
     if (gemv_variant() == 2) {
       // Measured on B200 (profiles/README.md): the MMA kernel with the packed slice staged in shared memory wins
@@ -230,6 +239,7 @@ int b200q_linear_group(const b200q_layer* const* layers, int32_t n_layers, const
     a[i].y = (__half*)y[i]; a[i].ldy = ldy[i]; a[i].n_offset = 0;
     a[i].workspace = workspace; a[i].workspace_bytes = workspace_bytes; a[i].stream = (cudaStream_t)stream;
   }
+  if (fused && gemv_imma_supported(a, n_layers)) return cuda_status(launch_gemv_imma(a, n_layers, nullptr));
   if (fused && gemv_stream_supported(a, n_layers)) return cuda_status(launch_gemv_stream(a, n_layers, nullptr));
   for (int i = 0; i < n_layers; ++i) {      // not fusable (shape / layout mix / M): same result, one launch per layer
     const int st = run(layers[i], x, M, ldx, nullptr, y[i], ldy[i], 0, workspace, workspace_bytes, stream, 0);
@@ -313,6 +323,11 @@ int b200q_debug_set_option(const char* name, double value) {
   else if (n == "st_target") gemv_stream_set_option(3, (int)value);
   else if (n == "st_ring_kb") gemv_stream_set_option(4, (int)value);
   else if (n == "st_lean") gemv_stream_set_option(5, (int)value);
+  else if (n == "imma") gemv_imma_set_option(0, (int)value);
+  else if (n == "im_cluster") gemv_imma_set_option(1, (int)value);
+  else if (n == "im_depth") gemv_imma_set_option(2, (int)value);
+  else if (n == "im_tpc") gemv_imma_set_option(3, (int)value);
+  else if (n == "im_target") gemv_imma_set_option(4, (int)value);
   else return B200Q_ERR_UNSUPPORTED;
   return B200Q_OK;
 }
@@ -325,7 +340,7 @@ int b200q_debug_decode_plan(const b200q_layer* layer, int64_t M, int32_t out[4])
   const LayerView V = make_view(layer);
   int o[6];
   const LinearArgs pa = probe_args(V, (int)M, nullptr, V.K);
-  if (g_use_stream && gemv_stream_describe(&pa, 1, o)) {
+  if (g_use_stream && (gemv_imma_describe(&pa, 1, o) || gemv_stream_describe(&pa, 1, o))) {
     for (int i = 0; i < 4; ++i) out[i] = o[i];
     return B200Q_OK;
   }
@@ -338,6 +353,7 @@ void b200q_debug_set_timeline(void* device_buf, size_t bytes) {
   gemv_variant();
   gemv_rp_set_debug((unsigned long long*)device_buf, bytes / 8);
   gemv_stream_set_debug((unsigned long long*)device_buf, bytes / 8);
+  gemv_imma_set_debug((unsigned long long*)device_buf, bytes / 8);
   gemm_tc_set_debug(bytes >= 64 * 1024 ? (unsigned long long*)device_buf : nullptr);   // GEMM: CTA(0,0), 8 stamps per k-block
 }
 int b200q_version(void) { return B200Q_VERSION; }

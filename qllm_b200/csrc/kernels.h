@@ -65,6 +65,13 @@ bool gemv_stream_describe(const LinearArgs* a, int n, int out[6]);
 void gemv_stream_set_option(int which, int value);
 void gemv_stream_set_debug(unsigned long long* buf, size_t cap_entries);
 
+// gemv_imma.cu : integer-tensor-path decode kernel for K-packed 4-bit layers, M <= 2
+bool gemv_imma_supported(const LinearArgs* a, int n);
+cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers);
+bool gemv_imma_describe(const LinearArgs* a, int n, int out[6]);
+void gemv_imma_set_option(int which, int value);
+void gemv_imma_set_debug(unsigned long long* buf, size_t cap_entries);
+
 // gemv_fma.cu : M <= 2 decode path (CUDA-core fp16x2 FMA, register prefetch, cluster split-K)
 bool gemv_fma_supported(const LayerView& L, int M, const __half* x, int64_t ldx);
 cudaError_t launch_gemv_fma(const LinearArgs& a, const PeerOut* peers);

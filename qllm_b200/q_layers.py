@@ -16,6 +16,7 @@ forward on CPU tensors raises, exactly like the reference's AWQ/Marlin layers (S
 """
 import ctypes
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -24,6 +25,10 @@ from . import codec
 from ._lib import (LAYOUT_AWQ_GEMM, LAYOUT_GPTQ, LAYOUT_HQQ, LAYOUT_MARLIN, Layer, check, lib)
 
 _workspaces = {}
+
+# Decode (M <= 2) on AWQ-GEMM / Marlin layers runs on the layer's exact K-packed re-layout (the integer-tensor-path
+# kernel, csrc/gemv_imma.cu); B200Q_DECODE_RELAYOUT=0 keeps decode on the checkpoint bytes (fp16-path kernels).
+DECODE_RELAYOUT = os.environ.get("B200Q_DECODE_RELAYOUT", "1") != "0"
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
@@ -121,6 +126,13 @@ class _B200QuantLinearBase(nn.Module):
             self._shadow, self._shadow_desc, self._shadow_key = (qw, qz, sc), d, key
         return self._shadow_desc
 
+    def _decode_descriptor(self, M):
+        """Descriptor the decode kernels should read at batch M: the checkpoint buffers, or -- AWQ-GEMM / Marlin at
+        M <= 2 -- the one-time exact K-packed re-layout that the integer-tensor-path kernel consumes."""
+        if DECODE_RELAYOUT and M <= 2 and self._layout in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN):
+            return self._gemm_descriptor()
+        return self._descriptor()
+
     # -- forward ------------------------------------------------------------------------------
     def __call__(self, x):
         grp = getattr(self, "_sibling_group", None)
@@ -141,6 +153,8 @@ class _B200QuantLinearBase(nn.Module):
         if M > 0:
             if M > lib.b200q_gemv_max_m() and lib.b200q_select_kernel(ctypes.byref(desc), M) != 2:
                 desc = self._gemm_descriptor()
+            elif M <= 2:
+                desc = self._decode_descriptor(M)
             need = lib.b200q_workspace_bytes(ctypes.byref(desc), M)
             ws = _workspace(x.device, need)
             st = lib.b200q_linear(ctypes.byref(desc), x2.data_ptr(), M, x2.stride(0), y.data_ptr(), y.stride(0),
@@ -369,9 +383,9 @@ class QuantLinearMarlin(_B200QuantLinearBase):
 def linear_group(layers, x):
     """[layer(x) for layer in layers] for sibling QuantLinears that share their input (q/k/v, gate/up), as one
     launch of b200q_linear_group at decode sizes (identical results; falls back per layer inside the library)."""
-    descs = [l._descriptor() for l in layers]
     K = layers[0].infeatures
     x2 = x.reshape(-1, x.shape[-1])
+    descs = [l._decode_descriptor(x2.shape[0]) for l in layers]
     if x2.dtype != torch.float16:
         x2 = x2.to(torch.float16)
     if x2.stride(-1) != 1:

@@ -293,6 +293,8 @@ def test_decode_sibling_group_vs_oracle(layout, bits, gs, K, Ns, M):
           for i, N in enumerate(Ns)]
     layers = [layer_from_dict(L) for L in Ls]
     x = np.random.default_rng(M + K).standard_normal((M, K)).astype(np.float16)
+    for l in layers:
+        l._decode_descriptor(M)                                  # one-time re-layout (AWQ / Marlin) is not part of the call
     n0 = qllm_b200.lib.b200q_launch_count()
     ys = qllm_b200.linear_group(layers, torch.from_numpy(x).cuda())
     assert qllm_b200.lib.b200q_launch_count() - n0 == 1          # fused: one launch for the whole group
@@ -310,6 +312,8 @@ def test_decode_group_mixed_falls_back_per_layer():
     Lb = O.make_layer("GEMM", 4, 64, 512, 256, seed=2)               # different group size: not fusable
     layers = [layer_from_dict(La), layer_from_dict(Lb)]
     x = np.random.default_rng(0).standard_normal((1, 512)).astype(np.float16)
+    for l in layers:
+        l._decode_descriptor(1)
     n0 = qllm_b200.lib.b200q_launch_count()
     ys = qllm_b200.linear_group(layers, torch.from_numpy(x).cuda())
     assert qllm_b200.lib.b200q_launch_count() - n0 == 2
@@ -404,3 +408,50 @@ def test_fuse_siblings_is_transparent_to_the_caller():
     h.add_(1.0)                                                      # in-place update bumps the version counter
     k3 = attn.k_proj(h)
     assert torch.equal(k3, qllm_b200.q_layers._B200QuantLinearBase.forward(attn.k_proj, h))
+
+
+# ---- integer-tensor-path decode kernel (gemv_imma.cu): plan variations, M = 2, partial tiles, fallbacks ----
+@pytest.mark.parametrize("opt,val", [("im_cluster", 1), ("im_cluster", 3), ("im_cluster", 8), ("im_depth", 2), ("im_depth", 4), ("im_tpc", 2),
+                                     ("im_target", 40), ("im_target", 290)])
+@pytest.mark.parametrize("layout,gs,K,N", [("GPTQ", 128, 2048, 416), ("GPTQ", 32, 1024, 160), ("HQQ", 64, 2048, 256), ("GEMM", 128, 2048, 640),
+                                           ("MARLIN", 128, 2048, 512), ("GPTQ", -1, 1024, 96)])
+def test_imma_kernel_plan_variations(opt, val, layout, gs, K, N):
+    import qllm_b200
+    lib = qllm_b200.lib
+    L = O.make_layer(layout, 4, gs, K, N, seed=K + N + 7, bias=True, float_zeros=(layout == "HQQ"))
+    layer = layer_from_dict(L)
+    x = np.random.default_rng(5).standard_normal((2, K)).astype(np.float16)
+    x[0, 5] = 37.0                                                   # an outlier: the digit split is scaled per 128-k part
+    x[1, K // 2] = -0.001
+    xt = torch.from_numpy(x).cuda()
+    assert lib.b200q_debug_set_option(opt.encode(), float(val)) == 0
+    try:
+        y2 = layer(xt)
+        y1 = layer(xt[:1])
+    finally:
+        lib.b200q_debug_set_option(opt.encode(), 148.0 if opt == "im_target" else 0.0)
+    ref = oracle_forward(L, x)
+    assert rel_err(y2.float().cpu().numpy(), ref) < TOL
+    assert rel_err(y1.float().cpu().numpy(), ref[:1]) < TOL
+
+
+def test_imma_kernel_matches_fp16_path_and_handles_extremes():
+    """Same layer through the integer path and (imma = 0) the fp16-sub-normal path; activations spanning fp16's range."""
+    import qllm_b200
+    lib = qllm_b200.lib
+    K, N = 4096, 1024
+    L = O.make_layer("GPTQ", 4, 128, K, N, seed=99)
+    layer = layer_from_dict(L)
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((1, K)) * np.exp(rng.uniform(-9, 5, size=(1, K)))).astype(np.float16)   # 6 decades of magnitude
+    x[0, :128] = 0.0                                                 # an all-zero part
+    xt = torch.from_numpy(x).cuda()
+    y_int = layer(xt).float().cpu().numpy()
+    lib.b200q_debug_set_option(b"imma", 0.0)
+    try:
+        y_f16 = layer(xt).float().cpu().numpy()
+    finally:
+        lib.b200q_debug_set_option(b"imma", 1.0)
+    ref = oracle_forward(L, x)
+    assert rel_err(y_int, ref) < TOL and rel_err(y_f16, ref) < TOL
+    assert rel_err(y_int, ref) <= rel_err(y_f16, ref) + 2e-4        # the fixed-point split loses nothing against fp16 MMA inputs

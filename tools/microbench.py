@@ -57,7 +57,7 @@ def time_shape(layout, bits, gs, K, N, M, iters=200, use_graph=False, force=None
     layers = [rand_layer(layout, bits, gs, K, N, dev, s) for s in range(copies)]
     x = torch.randn(M, K, dtype=torch.float16, device=dev)
     y = torch.empty(M, N, dtype=torch.float16, device=dev)
-    descs = [l._descriptor() for l in layers]
+    descs = [l._decode_descriptor(M) for l in layers]
     need = qllm_b200.lib.b200q_workspace_bytes(ctypes.byref(descs[0]), M)
     ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=dev)
     fn = {None: qllm_b200.lib.b200q_linear, "gemv": qllm_b200.lib.b200q_gemv, "gemm": qllm_b200.lib.b200q_gemm}[force]

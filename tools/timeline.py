@@ -24,7 +24,7 @@ copies = 24
 layers = [rand_layer(a.layout, 4, 128, K, N, dev, s) for s in range(copies)]
 x = torch.randn(1, K, dtype=torch.float16, device=dev)
 y = torch.empty(1, N, dtype=torch.float16, device=dev)
-descs = [l._descriptor() for l in layers]
+descs = [l._decode_descriptor(1) for l in layers]
 ws = torch.zeros(1 << 22, dtype=torch.uint8, device=dev)
 lib = qllm_b200.lib
 buf = torch.zeros(1 << 20, dtype=torch.int64, device=dev)
