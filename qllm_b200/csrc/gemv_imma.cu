@@ -21,9 +21,10 @@
 
 namespace b200q {
 
-static constexpr int kINT = 128;            // columns per tile
-static constexpr int kIStep = 32;           // k per step (one m16n8k32)
-static constexpr int kIStepBytes = 2048;    // 4 packed rows x 128 words
+static constexpr int kINT = 64;             // columns per tile
+static constexpr int kIStep = 64;           // k per step (two m16n8k32 deep)
+static constexpr int kIRow = 288;           // shared-memory pitch of a packed row: 256 B + 32 B pad (conflict-free LDS.128)
+static constexpr int kIStepBytes = 8 * kIRow;   // one ring slot: 8 packed rows (64 k) x 64 columns
 static constexpr uint32_t NIB = 0x0f0f0f0fu;
 
 __device__ __forceinline__ void imma_16832(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -32,20 +33,22 @@ __device__ __forceinline__ void imma_16832(int (&d)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// Shared-memory placement of one step: packed row r (0..3) is 512 B; its 16-byte chunk c sits at c ^ 2r, so the
-// quarter-warps of an LDS.128 (rows t = 0..3, chunks 8i + g) fall into distinct banks.
-// Column map of a tile: MMA j = 2i + h (i = 0..3, h = 0..1), row g -> column 32i + 4g + 2h, row g + 8 -> that + 1
-// (a lane's LDS.128 #i = its four words 32i + 4g .. + 3 of packed row t).
-//
-// Activation digits in shared memory: [step][column c < 4 MTOK][t = 0..3][8 B] -- the B fragment (b0, b1) of lane
-// (g = c, t): bytes 0..3 = digit at k = 8t + {0,2,4,6}, bytes 4..7 = k = 8t + {1,3,5,7} (the order the unpack yields).
+// Tile = 64 columns, step = 64 k (8 packed rows of 256 B).  The tile is kept narrow so that a thread needs ~70
+// registers (16 int32 accumulators, 8 fp32 partial sums) and three CTAs -- 24 warps -- share an SM: at decode sizes every
+// warp runs a mostly serial instruction stream, and the time of a layer is that stream's length.
+// Shared-memory placement of one step: packed rows 288 B apart, so the quarter-warps of an LDS.128 (rows t = 0..3 of a
+// k-half, 16-byte chunks 8i + g) fall into distinct banks without any swizzle; every address is base + immediate.
+// Column map of a tile: MMA j = 2i + h (i, h = 0..1), row g -> column 32i + 4g + 2h, row g + 8 -> that + 1
+// (a lane's LDS.128 #i = its four words 32i + 4g .. + 3 of packed row 4 kh + t).
+// Activation digits in shared memory, per 32-k sub-step: [column c < 4 MTOK][t = 0..3][8 B] -- the B fragment (b0, b1) of
+// lane (g = c, t): bytes 0..3 = digit at k = 8t + {0,2,4,6}, bytes 4..7 = k = 8t + {1,3,5,7} (the order the unpack yields).
 // Column 4m + d holds digit d (most significant first) of token m; column 4m + 3 is absent (lanes read a zero pad).
 template <int MTOK, int D>
-__global__ void __launch_bounds__(kRpThreads, 2) gemv_imma_kernel(const __grid_constant__ StParams p) {
+__global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_constant__ StParams p) {
   extern __shared__ __align__(128) char smem[];
   using T = RpGptq<4>;                                                   // table_entries8: (scale, zero) decode of the K-packed layout
   constexpr int NT = kINT, MC = (MTOK == 1) ? 1 : 2;
-  constexpr int XQ_STEP = 32 * 4 * MTOK;                                 // digit bytes per step
+  constexpr int XQ_SUB = 32 * 4 * MTOK;                                  // digit bytes per 32-k sub-step
   float2* tab = reinterpret_cast<float2*>(smem + p.off_tab);
   float* red = reinterpret_cast<float*>(smem + p.off_red);
   float* rbuf = reinterpret_cast<float*>(smem + p.off_rbuf);
@@ -89,39 +92,45 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_imma_kernel(const __grid_c
     cluster_arrive_relaxed();
   }
 
-  // ---- per-lane constants ----
+  // ---- per-warp ring of D slots filled with cp.async: lane -> packed rows lane / 16 + {0, 2, 4, 6}, chunk lane % 16 ----
   const uint32_t ring = smem_u32(smem + p.off_ring) + (uint32_t)warp * (D * kIStepBytes);
-  const uint32_t rd = ring + (uint32_t)(t * 512 + ((g ^ (2 * t)) << 4));                     // + 128 i, + slot
-  // copies: packed row i (0..3) of the step, chunk `lane` (4 columns); 32 chunks = 128 columns per row
-  const size_t pitch = (size_t)L.N;                                                          // words per packed row
-  const uint32_t* src = L.qw + (size_t)(s_begin * 4) * pitch + n0 + 4 * lane;
-  bool pc = 4 * lane < min(NT, L.N - n0);
+  const uint32_t rd = ring + (uint32_t)(t * kIRow + g * 16);                                 // + 128 i, + 4 kIRow kh, + slot
+  const uint32_t wr = ring + (uint32_t)((lane >> 4) * kIRow + (lane & 15) * 16);             // + 2 kIRow r, + slot
+  int pitch = L.N;                                                                           // words per packed row
+  uint32_t wr_ = wr, rd_ = rd;
+  asm volatile("" : "+r"(wr_), "+r"(rd_), "+r"(pitch));                                      // keep in registers: ptxas otherwise re-derives them per step
+  const uint32_t* src = L.qw + ((size_t)(s_begin * 8) + (lane >> 4)) * (size_t)pitch + n0 + 4 * (lane & 15);
+  bool pc = 4 * (lane & 15) < min(NT, L.N - n0);
   int irem = nsw, itiles = (nsw > 0) ? nt : 0;
-  auto issue = [&](uint32_t slot) {
+  auto issue = [&](uint32_t slot_wr) {
     if (itiles > 0) {
       if (pc) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) cp_async16_s(slot + r * 512 + ((lane ^ (2 * r)) << 4), src + r * pitch);
+        const uint32_t* s1 = src + 2 * pitch;
+        const uint32_t* s2 = s1 + 2 * pitch;
+        cp_async16_s(slot_wr, src);
+        cp_async16_s(slot_wr + 2 * kIRow, s1);
+        cp_async16_s(slot_wr + 4 * kIRow, s2);
+        cp_async16_s(slot_wr + 6 * kIRow, s2 + 2 * pitch);
       }
-      src += 4 * pitch;
+      src += 8 * pitch;
       if (--irem == 0) {                                                                     // next tile, back to this warp's first k
         irem = nsw;
         --itiles;
-        src += NT - (ptrdiff_t)((size_t)nsw * 4 * pitch);
-        pc = 4 * lane < L.N - (n0 + (nt - itiles) * NT);
+        src += NT - (ptrdiff_t)((size_t)nsw * 8 * (size_t)pitch);
+        pc = 4 * (lane & 15) < L.N - (n0 + (nt - itiles) * NT);
       }
     }
     cp_async_commit();
   };
 #pragma unroll 1
-  for (int d = 0; d < D; ++d) issue(ring + d * kIStepBytes);
+  for (int d = 0; d < D; ++d) issue(wr_ + d * kIStepBytes);
 
   // (scale, zero) table of the CTA's k-slice: [tile][group][NT] float2
   {
-    const int c8 = (tid & 15) * 8;
+    const int c8 = (tid & 7) * 8;
     for (int tt = 0; tt < nt; ++tt) {
       const int n = n0 + tt * NT + c8;
-      for (int gl = tid >> 4; gl < g_count; gl += 16) {
+      for (int gl = tid >> 3; gl < g_count; gl += 32) {
         float2 e[8];
         if (n < L.N) T::table_entries8(L, g_first + gl, n, e);
         else {
@@ -140,23 +149,23 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_imma_kernel(const __grid_c
   ST_STAMP(1);
 
   // ---- activations: wait for the upstream kernel, then split this warp's k-range into digits ----
-  // parts: <= 128 k, never across a group boundary; part table (per warp): {2^-E, sum(x)} per token
+  // parts: <= 128 k (4 sub-steps of 32 k), never across a group boundary; part table (per warp): {2^-E, sum(x)} per token
   pdl_wait();
   ST_STAMP(2);
-  char* xq = smem + p.off_x + (size_t)(s_begin - cta_s0) * XQ_STEP;     // this warp's digit steps
+  char* xq = smem + p.off_x + (size_t)(s_begin - cta_s0) * (2 * XQ_SUB);   // this warp's digit sub-steps
   float2* part = reinterpret_cast<float2*>(smem + p.off_part) + (size_t)warp * (p.part_cap * MTOK);
-  const int part_steps = min(4, p.group >> 5);                           // steps per full part
+  const int part_sub = min(4, p.group >> 5);                             // sub-steps per full part (2 or 4: group >= 64)
   {
-    int ks = s_begin, pi = 0;
-    while (ks < s_end) {
-      // steps until the next part boundary (absolute k multiple of part_steps * 32: group boundaries are such multiples)
-      const int lim = min(s_end, (ks / part_steps + 1) * part_steps);
-      const int len = (lim - ks) * kIStep;                               // k in this part (<= 128)
+    int ks = 2 * s_begin, pi = 0;                                        // in 32-k sub-steps
+    const int ke = 2 * s_end;
+    while (ks < ke) {
+      const int lim = min(ke, (ks / part_sub + 1) * part_sub);
+      const int len = (lim - ks) * 32;                                   // k in this part (<= 128)
 #pragma unroll
       for (int m = 0; m < MTOK; ++m) {
         float xv[4] = {0.f, 0.f, 0.f, 0.f};
         if (4 * lane < len) {
-          const uint2 raw = *reinterpret_cast<const uint2*>(p.x + (size_t)m * p.ldx + (size_t)ks * kIStep + 4 * lane);
+          const uint2 raw = *reinterpret_cast<const uint2*>(p.x + (size_t)m * p.ldx + (size_t)ks * 32 + 4 * lane);
           const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
           xv[0] = __low2float(h01); xv[1] = __high2float(h01); xv[2] = __low2float(h23); xv[3] = __high2float(h23);
         }
@@ -185,12 +194,12 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_imma_kernel(const __grid_c
         for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
         if (lane == 0) part[pi * MTOK + m] = make_float2(isc, (float)tsum * isc);
         if (4 * lane < len) {
-          // element e of this lane: k' = 4 (lane % 8) + e inside its step -> word t' = (lane % 8) / 2, kk = 4 (lane & 1) + e:
+          // element e of this lane: k' = 4 (lane % 8) + e inside its sub-step -> word t' = (lane % 8) / 2, kk = 4 (lane & 1) + e:
           // even kk -> byte kk / 2 of the first half, odd kk -> byte kk / 2 of the second half
-          const int st = (ks - s_begin) + (lane >> 3), tq = (lane & 7) >> 1, bo = 2 * (lane & 1);
+          const int st = (ks - 2 * s_begin) + (lane >> 3), tq = (lane & 7) >> 1, bo = 2 * (lane & 1);
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
-            char* dst = xq + (size_t)st * XQ_STEP + (size_t)(4 * m + d) * 32 + tq * 8 + bo;
+            char* dst = xq + (size_t)st * XQ_SUB + (size_t)(4 * m + d) * 32 + tq * 8 + bo;
             const uint32_t v = dig[d];
             *reinterpret_cast<uint16_t*>(dst) = (uint16_t)((v & 0xffu) | ((v >> 8) & 0xff00u));              // e = 0, 2
             *reinterpret_cast<uint16_t*>(dst + 4) = (uint16_t)(((v >> 8) & 0xffu) | ((v >> 16) & 0xff00u));  // e = 1, 3
@@ -204,31 +213,32 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_imma_kernel(const __grid_c
   // B fragment source: column g of the digit block (digit columns 4m + {0,1,2}), else the zero pad
   const bool xreal = (g & 3) < 3 && (g >> 2) < MTOK;
   uint32_t xp = xreal ? smem_u32(xq) + (uint32_t)(g * 32 + t * 8) : smem_u32(zpad);
-  const uint32_t xstep = xreal ? (uint32_t)XQ_STEP : 0u, xrewind = xreal ? (uint32_t)(nsw * XQ_STEP) : 0u;
+  const uint32_t xsub = xreal ? (uint32_t)XQ_SUB : 0u, xrewind = xreal ? (uint32_t)(nsw * 2 * XQ_SUB) : 0u;
   // fix-up role of this lane: token t >> 1; even t holds digits 0, 1 (v = d0 2^7 + d1, worth 2^7), odd t digit 2 (v = d2 2^7, worth 2^-7)
   const int mytok = t >> 1;
   const bool fx_on = mytok < MTOK;
-  const float dscale = (t & 1) ? (1.0f / 128.0f) : 128.0f, zflag = (t & 1) ? 0.f : 1.f;   // odd t: v = d2 << 7
+  const float dscale = (t & 1) ? (1.0f / 128.0f) : 128.0f, zflag = (t & 1) ? 0.f : 1.f;
 
-  int acc[8][4];
-  float tot[8][2];
+  int acc[4][4];
+  float tot[4][2];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0; tot[q][0] = tot[q][1] = 0.f; }
-  // part / group / tile cursors
-  const int pleft0 = part_steps - (s_begin % part_steps);
+  for (int q = 0; q < 4; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0; tot[q][0] = tot[q][1] = 0.f; }
+  // part / tile cursors (in steps; a part is part_sub / 2 = 1 or 2 steps)
+  const int psteps = part_sub >> 1;
+  const int pleft0 = psteps - (s_begin & (psteps - 1));
   int pleft = min(pleft0, nsw), crem = nsw, tcur = 0, pi = 0, kcur = s_begin;
   float* redw = red + (size_t)warp * p.red_stride;
   const int ms = p.M;
 
   auto part_close = [&]() {
-    // y += s * (2^-E * dscale * (d_even 2^7 + d_odd) - zflag * z * sum(x)) for this lane's 16 (column, token) outputs
+    // y += s * (2^-E * dscale * (d_a 2^7 + d_b) - zflag * z * sum(x)) for this lane's 8 (column, token) outputs
     if (fx_on) {
       const float2 pt = part[pi * MTOK + mytok];
       const float xs = pt.x * dscale, sxz = pt.y * zflag;
-      const int gl = ((kcur - 1) * kIStep >> gsh) - g_first;             // group of the part just finished
+      const int gl = (((kcur - 1) * kIStep) >> gsh) - g_first;           // group of the part just finished
       const float2* row = tab + ((size_t)tcur * p.gcap + gl) * NT + 4 * g;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         const float4 e01 = *reinterpret_cast<const float4*>(row + 32 * i), e23 = *reinterpret_cast<const float4*>(row + 32 * i + 2);
         // MMA 2i: rows g / g+8 = columns +0 / +1; MMA 2i+1: columns +2 / +3
         const float v00 = (float)((acc[2 * i][0] << 7) + acc[2 * i][1]), v01 = (float)((acc[2 * i][2] << 7) + acc[2 * i][3]);
@@ -240,38 +250,37 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_imma_kernel(const __grid_c
       }
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0;
+    for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0;
     ++pi;
   };
 
   cp_async_wait<0>();
-  __syncwarp();
+  __syncwarp();                                                          // ring, digits and part table visible to the warp
 #pragma unroll 1
   for (int i = 0; i < total; ++i) {
     const uint32_t so = (uint32_t)(i & (D - 1)) * kIStepBytes;
     cp_async_wait<D - 1>();
     __syncwarp();
-    uint4 w[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) w[q] = lds128_s(rd + so + q * 128);
-    const uint2 xb = lds64_s(xp);
-    xp += xstep;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t w0 = w[q].x, w1 = w[q].y, w2 = w[q].z, w3 = w[q].w;
-      imma_16832(acc[2 * q], w0 & NIB, w1 & NIB, (w0 >> 4) & NIB, (w1 >> 4) & NIB, xb.x, xb.y);
-      imma_16832(acc[2 * q + 1], w2 & NIB, w3 & NIB, (w2 >> 4) & NIB, (w3 >> 4) & NIB, xb.x, xb.y);
+    for (int kh = 0; kh < 2; ++kh) {
+      const uint4 wa = lds128_s(rd_ + so + kh * 4 * kIRow), wb = lds128_s(rd_ + so + kh * 4 * kIRow + 128);
+      const uint2 xb = lds64_s(xp);
+      xp += xsub;
+      imma_16832(acc[0], wa.x & NIB, wa.y & NIB, (wa.x >> 4) & NIB, (wa.y >> 4) & NIB, xb.x, xb.y);
+      imma_16832(acc[1], wa.z & NIB, wa.w & NIB, (wa.z >> 4) & NIB, (wa.w >> 4) & NIB, xb.x, xb.y);
+      imma_16832(acc[2], wb.x & NIB, wb.y & NIB, (wb.x >> 4) & NIB, (wb.y >> 4) & NIB, xb.x, xb.y);
+      imma_16832(acc[3], wb.z & NIB, wb.w & NIB, (wb.z >> 4) & NIB, (wb.w >> 4) & NIB, xb.x, xb.y);
     }
     __syncwarp();                                                        // every lane has read the slot
-    issue(ring + so);
+    issue(wr_ + so);
     ++kcur;
     --crem;
     if (--pleft == 0 || crem == 0) {                                     // part and / or tile boundary (warp-uniform)
       part_close();
-      pleft = min(part_steps, crem);
+      pleft = min(psteps, crem);
       if (crem == 0) {                                                   // tile done: combine the digit lanes, park the sums
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           const float a0 = tot[q][0] + __shfl_xor_sync(0xffffffffu, tot[q][0], 1);
           const float a1 = tot[q][1] + __shfl_xor_sync(0xffffffffu, tot[q][1], 1);
           if (fx_on && !(t & 1)) {
@@ -303,10 +312,10 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_imma_kernel(const __grid_c
 struct ImPlan {
   int ctas, cluster, tpc, depth, steps_total, group_shift, gcap, part_cap, split_q, split_r;
   int cta0[kMaxGroupLayers];
-  int off_x, off_tab, off_red, off_rbuf, off_rbar, off_ring, off_zpad, off_part, smem_bytes;
+  int off_x, off_tab, off_red, off_rbuf, off_rbar, off_ring, off_zpad, off_part, off_mbar, smem_bytes;
 };
 
-static int g_im_on = 1, g_im_cluster = 0, g_im_depth = 0, g_im_tpc = 0, g_im_target = 148;
+static int g_im_on = 1, g_im_cluster = 0, g_im_depth = 0, g_im_tpc = 0, g_im_target = 296;
 static unsigned long long* g_im_dbg = nullptr;
 static size_t g_im_dbg_cap = 0, g_im_dbg_pos = 0;
 void gemv_imma_set_option(int which, int value) {
@@ -330,7 +339,7 @@ static bool im_plan(const LinearArgs* a, int n, ImPlan& pl) {
         B.g_idx != nullptr || a[i].M != M || a[i].x != a[0].x || a[i].ldx != a[0].ldx)
       return false;
   }
-  // a step (32 k) lies inside one group; groups are powers of two (count-down bookkeeping by shifts)
+  // a step (64 k) lies inside one group; groups are powers of two (count-down bookkeeping by shifts)
   if (L.group < kIStep || (L.group & (L.group - 1)) != 0 || L.K % L.group != 0 || L.K % kIStep != 0) return false;
   int tiles = 0;
   for (int i = 0; i < n; ++i) {
@@ -340,8 +349,11 @@ static bool im_plan(const LinearArgs* a, int n, ImPlan& pl) {
   pl.group_shift = 0;
   while ((1 << pl.group_shift) < L.group) ++pl.group_shift;
   pl.steps_total = L.K / kIStep;
-  int tpc = (tiles >= 2 * g_im_target) ? 2 : 1;
-  if (g_im_tpc == 1 || g_im_tpc == 2) tpc = g_im_tpc;
+  // tiles per CTA: widest walk (<= 256 columns) that still leaves >= target CTA groups
+  int tpc = 1;
+  for (int c = 2; c <= 4; c *= 2)
+    if ((tiles + c - 1) / c >= g_im_target) tpc = c;
+  if (g_im_tpc == 1 || g_im_tpc == 2 || g_im_tpc == 4) tpc = g_im_tpc;
   int groups = 0;
   for (int i = 0; i < n; ++i) {
     pl.cta0[i] = groups;
@@ -351,34 +363,41 @@ static bool im_plan(const LinearArgs* a, int n, ImPlan& pl) {
   while (cs < 8 && groups * cs < g_im_target && pl.steps_total / ((cs + 1) * kWarps) >= 2) ++cs;
   if (g_im_cluster > 0 && g_im_cluster <= 8 && pl.steps_total / (g_im_cluster * kWarps) >= 1) cs = g_im_cluster;
   pl.tpc = tpc; pl.cluster = cs; pl.ctas = groups * cs;
-  if (pl.ctas > 148 * 2) return false;
+  if (pl.ctas > 148 * 3) return false;                                   // three CTAs per SM (80 registers per thread)
   pl.split_q = pl.steps_total / (cs * kWarps);
   pl.split_r = pl.steps_total % (cs * kWarps);
   const int seq = (pl.split_q + (pl.split_r ? 1 : 0)) * tpc;             // longest per-warp step sequence
   const int per_sm = (pl.ctas + 147) / 148;
-  int depth = (per_sm >= 2 || seq <= 2) ? 2 : 4;                         // 32 / 64 KB of ring per CTA
-  if (g_im_depth == 2 || g_im_depth == 4) depth = g_im_depth;
-  pl.depth = depth;
   const int slice_steps = kWarps * pl.split_q + (pl.split_r < kWarps ? pl.split_r : kWarps);
   const int kslice = slice_steps * kIStep;
   pl.gcap = kslice / L.group + 2;
-  const int part_steps = (L.group >> 5) < 4 ? (L.group >> 5) : 4;
-  pl.part_cap = (pl.split_q + 1 + part_steps - 1) / part_steps + 2;      // parts per warp
-  int off = 0;
-  pl.off_x = off; off += slice_steps * 32 * 4 * M;                       // digit steps of the CTA's slice
-  off = (off + 15) & ~15;
-  pl.off_tab = off; off += tpc * pl.gcap * kINT * 8;
-  off = (off + 15) & ~15;
-  pl.off_red = off; off += kWarps * tpc * kINT * M * 4;
-  pl.off_rbuf = off; off += (cs - 1) * tpc * kINT * M * 4;
-  off = (off + 7) & ~7;
-  pl.off_rbar = off; off += 8;
-  pl.off_part = off; off += kWarps * pl.part_cap * M * 8;
-  off = (off + 127) & ~127;
-  pl.off_zpad = off; off += 128;
-  pl.off_ring = off; off += kWarps * depth * kIStepBytes;
-  pl.smem_bytes = off;
-  return pl.smem_bytes <= 100 * 1024;
+  const int psteps = (L.group >> 6) < 2 ? 1 : 2;                         // steps per part (<= 128 k)
+  pl.part_cap = (pl.split_q + 1 + psteps - 1) / psteps + 2;              // parts per warp
+  auto layout = [&](int depth) {
+    int off = 0;
+    pl.off_x = off; off += slice_steps * 2 * 32 * 4 * M;                 // digit sub-steps of the CTA's slice
+    off = (off + 15) & ~15;
+    pl.off_tab = off; off += tpc * pl.gcap * kINT * 8;
+    off = (off + 15) & ~15;
+    pl.off_red = off; off += kWarps * tpc * kINT * M * 4;
+    pl.off_rbuf = off; off += (cs - 1) * tpc * kINT * M * 4;
+    off = (off + 7) & ~7;
+    pl.off_rbar = off; off += 8;
+    pl.off_part = off; off += kWarps * pl.part_cap * M * 8;
+    pl.off_mbar = off; off += kWarps * depth * 8;
+    off = (off + 127) & ~127;
+    pl.off_zpad = off; off += 128;
+    pl.off_ring = off; off += kWarps * depth * kIStepBytes;
+    pl.smem_bytes = off;
+    pl.depth = depth;
+  };
+  // ring depth: four slots per warp (74 KB per CTA) only when the launch leaves one CTA per SM, else two (37 KB)
+  int depth = (per_sm >= 2 || seq <= 2) ? 2 : 4;
+  if (g_im_depth == 2 || g_im_depth == 4) depth = g_im_depth;
+  layout(depth);
+  if (pl.smem_bytes > 72 * 1024 && depth == 4) layout(2);
+  (void)seq;
+  return pl.smem_bytes <= 72 * 1024;
 }
 
 bool gemv_imma_supported(const LinearArgs* a, int n) {
@@ -403,7 +422,7 @@ static cudaError_t im_launch_k(const StParams& p, const ImPlan& pl, cudaStream_t
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemv_imma_kernel<MTOK, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemv_imma_kernel<MTOK, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
     if (e != cudaSuccess) return e;
     if (decode_carveout_max()) cudaFuncSetAttribute(gemv_imma_kernel<MTOK, D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_done[dev & 63] = true;
@@ -446,7 +465,7 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers) {
   p.gcap = pl.gcap; p.split_q = pl.split_q; p.split_r = pl.split_r; p.part_cap = pl.part_cap;
   p.x_stride = 0; p.red_stride = pl.tpc * kINT * a[0].M;
   p.off_x = pl.off_x; p.off_tab = pl.off_tab; p.off_red = pl.off_red; p.off_rbuf = pl.off_rbuf; p.off_rbar = pl.off_rbar;
-  p.off_ring = pl.off_ring; p.off_zpad = pl.off_zpad; p.off_part = pl.off_part;
+  p.off_ring = pl.off_ring; p.off_zpad = pl.off_zpad; p.off_part = pl.off_part; p.off_mbar = pl.off_mbar;
   p.dbg = nullptr;
   if (g_im_dbg) {
     const size_t need = (size_t)pl.ctas * 8;

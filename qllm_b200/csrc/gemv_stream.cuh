@@ -27,7 +27,7 @@ struct StParams {
   int cluster, tpc, depth, steps_total, group_shift, gcap, split_q, split_r, part_cap;
   int x_stride;                                  // bytes of one staged activation row
   int red_stride;                                // floats between two warps' partial-sum vectors
-  int off_x, off_tab, off_red, off_rbuf, off_rbar, off_ring, off_zpad, off_part;
+  int off_x, off_tab, off_red, off_rbuf, off_rbar, off_ring, off_zpad, off_part, off_mbar;
   unsigned long long* dbg;                       // optional per-CTA phase stamps (diagnostic)
 };
 
