@@ -175,6 +175,7 @@ class DecodeStep:
         import qllm_b200
         self.lib, self.blocks, self.M, self.world, self.rank = qllm_b200.lib, blocks, M, world, rank
         self.fuse = os.environ.get("B200Q_BENCH_NO_GROUP") is None
+        self.chain = os.environ.get("B200Q_BENCH_NO_CHAIN") is None
         f16 = dict(dtype=torch.float16, device=dev)
         self.h = torch.zeros(M, HIDDEN, **f16)
         self.bufs = {n: torch.zeros(M, N, **f16) for n, _, N in SHAPES}
@@ -225,14 +226,103 @@ class DecodeStep:
                                           self.ws.numel(), stream))
         return ys
 
+    def _hint(self, layers):
+        """b200q_prefetch_hint: the layers that follow the next call (what qllm_b200.link_decode_chain installs)."""
+        if not self.chain or self.world > 1:
+            return
+        from qllm_b200 import check, Layer
+        descs = [l._decode_descriptor(self.M) for l in layers]
+        arr = (ctypes.POINTER(Layer) * len(descs))(*[ctypes.pointer(d) for d in descs])
+        check(self.lib.b200q_prefetch_hint(arr, len(descs)))
+
     def run(self, stream):
         h = self.h
-        for b in self.blocks:
+        nb = len(self.blocks)
+        for i, b in enumerate(self.blocks):
+            self._hint([b["o"]])
             q, k, v = self._group([b["q"], b["k"], b["v"]], h, ["q", "k", "v"], stream)
+            self._hint([b["gate"], b["up"]])
             o = self._call(b["o"], v, "o", stream)
+            self._hint([b["down"]])
             gt, up = self._group([b["gate"], b["up"]], o, ["gate", "up"], stream)
+            if i + 1 < nb:
+                n = self.blocks[i + 1]
+                self._hint([n["q"], n["k"], n["v"]])
             h = self._call(b["down"], gt, "down", stream)
         return h
+
+
+class FusedShardedStep:
+    """N > 1: every call is one b200q_linear_group_sharded launch -- this rank's column shards, stored into every
+    rank's replica over NVLink, with the cross-GPU hand-off inside the kernels: tagged activations (flag-in-data:
+    a consumer lane spins on exactly the words it needs; no fence, atomic or barrier), or -- B200Q_BENCH_COUNTERS=1 --
+    the counter protocol (post / wait).  No collective and no host work between layers; the whole token (epoch advance
+    + 128 launches + the final untag / wait) is one CUDA graph."""
+    CALLS = (("q", "k", "v"), ("o",), ("gate", "up"), ("down",))
+    X_OF = (None, "v", "o", "gate")          # input of call j (None: the block input = previous block's down / h)
+
+    def __init__(self, blocks, dev, M, rank, world):
+        import torch
+        import torch.distributed as dist
+        import qllm_b200
+        from qllm_b200.sharding import PeerArena, sharded_group_posts
+        self.lib, self.blocks, self.M, self.world, self.rank, self.torch = qllm_b200.lib, blocks, M, world, rank, torch
+        self.tagged = os.environ.get("B200Q_BENCH_COUNTERS") is None
+        esz = 4 if self.tagged else 2
+        full = {n: N for n, _, N in SHAPES}
+        self.arena = PeerArena(sum(((M * N * esz + 255) & ~255) for N in full.values()), n_slots=8 + 4 * len(blocks))
+        self.off = {n: self.arena.carve(M * N * esz) for n, N in full.items()}
+        self.bufs = {n: self.arena.local_view(self.off[n], (M, N), torch.int32 if self.tagged else torch.float16) for n, N in full.items()}
+        self.full = full
+        self.h = torch.zeros(M, HIDDEN, dtype=torch.float16, device=dev)
+        self.out = torch.zeros(M, HIDDEN, dtype=torch.float16, device=dev)
+        mine = [sharded_group_posts([blocks[0][n] for n in names], M) for names in self.CALLS]
+        every = [None] * world
+        dist.all_gather_object(every, mine)
+        self.wait_counts = [sum(every[r][j] for r in range(world) if r != rank) for j in range(len(self.CALLS))]
+        need = max(self.lib.b200q_workspace_bytes(ctypes.byref(l._decode_descriptor(M)), M) for l in blocks[0].values())
+        self.ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+        self.fuse, self.chain = True, False
+        # load the kernels locally (lazy module loading can take seconds) before any rank waits on a peer (2 s bound)
+        for l in blocks[0].values():
+            l(torch.zeros(M, l.infeatures, dtype=torch.float16, device=dev))
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def run(self, stream):
+        from qllm_b200.sharding import sharded_group_forward
+        from qllm_b200._lib import PEER_X_TAGGED, PEER_Y_TAGGED
+        A, M = self.arena, self.M
+        A.advance(stream)
+        x_name, wait_slot, wait_count = None, -1, 0
+        stride = 4 * len(self.blocks) + 1
+        for i, b in enumerate(self.blocks):
+            for j, names in enumerate(self.CALLS):
+                slot = 1 + 4 * i + j
+                if self.X_OF[j] is not None:
+                    x_name = self.X_OF[j]
+                layers = [b[n] for n in names]
+                offs, fulls, col0s = [self.off[n] for n in names], [self.full[n] for n in names], [l.col0 for l in layers]
+                if self.tagged:
+                    flags = PEER_Y_TAGGED | (PEER_X_TAGGED if x_name is not None else 0)
+                    sync = A.sync_desc(flags=flags, tag_stride=stride, y_seq=slot, x_seq=slot - 1)
+                else:
+                    sync = A.sync_desc(wait_slot, wait_count, slot)
+                if x_name is None:
+                    sharded_group_forward(A, layers, self.h, offs, fulls, col0s, sync, self.ws, stream)
+                else:
+                    xb = self.bufs[x_name]
+                    sharded_group_forward(A, layers, None, offs, fulls, col0s, sync, self.ws, stream,
+                                          x_ptr=xb.data_ptr(), M=M, ldx=xb.stride(0))
+                wait_slot, wait_count = slot, self.wait_counts[j]
+            x_name = "down"
+        # the host (or lm_head) reads the complete hidden state as plain fp16
+        if self.tagged:
+            A.untag(self.off["down"], M, HIDDEN, self.out, stride, 4 * len(self.blocks), stream)
+        else:
+            A.wait(wait_slot, wait_count, stream)
+            self.out.copy_(self.bufs["down"])
+        return self.out
 
 
 def run_b200q(args, rank, world, local_rank):
@@ -245,7 +335,20 @@ def run_b200q(args, rank, world, local_rank):
     steps, warm = max(1, args.steps), max(3, args.warmup)
     blocks = build_model(dev, rank, world, "GEMM")
     M = 1
-    step = DecodeStep(blocks, dev, M, rank, world)
+    fused_err = None
+    step = None
+    if world > 1 and os.environ.get("B200Q_BENCH_NCCL") is None:
+        try:
+            step = FusedShardedStep(blocks, dev, M, rank, world)
+        except Exception as e:                            # symmetric memory unavailable: NCCL all-gather per layer
+            fused_err = f"{type(e).__name__}: {e}"[:200]
+        ok = torch.tensor([0 if step is None else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            step = None
+    fused_sharded = step is not None
+    if step is None:
+        step = DecodeStep(blocks, dev, M, rank, world)
     h0 = (torch.randn(M, HIDDEN, generator=torch.Generator().manual_seed(7)) * 1.0).to(torch.float16)
     h0_pinned = h0.pin_memory()
     y_pinned = torch.empty(M, HIDDEN, dtype=torch.float16).pin_memory()
@@ -295,6 +398,13 @@ def run_b200q(args, rank, world, local_rank):
     ms_per_step = ms / steps
     tok_s = 1e3 / ms_per_step
     finite = bool(torch.isfinite(out.float()).all().item())
+    replicas_equal, timeouts = None, None
+    if world > 1:
+        allout = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(allout, out.contiguous())
+        replicas_equal = all(bool(torch.equal(allout[0], t)) for t in allout[1:])
+        if fused_sharded:
+            timeouts = bool(step.arena.poisoned())
 
     if rank != 0:
         return
@@ -317,7 +427,11 @@ def run_b200q(args, rank, world, local_rank):
         "config": {"workload": "Llama-2-7B int4 g128 AWQ pack_mode=GEMM, batch=1 decode: the 224 QuantLinear layers of one token "
                                "in LlamaDecoderLayer dependency order (q|k|v -> o -> gate|up -> down)",
                    "launches_per_step": int(launches_per_step), "sibling_groups": bool(step.fuse and world == 1),
-                   "M": M, "layers": n_layers, "parallelism": f"column-shard x{world} + all-gather" if world > 1 else "single GPU",
+                   "next_layer_l2_prefetch": bool(step.chain and world == 1),
+                   "M": M, "layers": n_layers, "parallelism": (f"column-shard x{world}, all-gather + hand-off fused into the decode kernels (NVLink peer stores, "
+                                    + ("tagged activations" if getattr(step, "tagged", False) else "counter post/wait") + ")" if fused_sharded
+                                   else f"column-shard x{world} + NCCL all-gather per layer") if world > 1 else "single GPU",
+                   "fused_sharded_error": fused_err, "replicas_equal": replicas_equal, "peer_wait_timeouts": timeouts,
                    "l2_policy": "inputs (3.4 GB packed weights) larger than L2", "cuda_graph": True, "pdl": True,
                    "outputs_finite": finite},
         "clocks": clk.summary(),

@@ -111,6 +111,19 @@ int b200q_linear_group(const b200q_layer* const* layers, int32_t n_layers, const
                        b200q_stream_t stream);
 
 /*
+ * One-shot hint for decode chains: `next_layers` (n_layers <= 3, one sibling group) are the layers that will run
+ * right AFTER the calling thread's next b200q_linear / _linear_group / _linear_sharded call on the same stream.
+ * The decode kernel launched by that next call asks for their packed bytes to be brought from HBM into L2
+ * (cp.async.bulk.prefetch.L2) as soon as its own last weight load has been issued, so HBM keeps streaming across
+ * the kernel boundary (reduction, store, hand-off, the next launch's prologue).  Purely a performance hint:
+ * results are unaffected; kernels without the mechanism ignore it; n_layers = 0 clears a pending hint.
+ * No reference equivalent: the reference issues each QuantLinear.forward in isolation
+ * (quant_linear_gptq.py:136-143, quant_linear_awq.py:142-148).  The host shim derives the order from the
+ * model's module tree (qllm_b200.link_decode_chain).
+ */
+int b200q_prefetch_hint(const b200q_layer* const* next_layers, int32_t n_layers);
+
+/*
  * Multi-GPU column-sharded forward with the all-gather fused into the epilogue: this rank computes
  * y[:, n_offset : n_offset + layer->N] and stores the tile into `n_peers` output buffers
  * (peer_y[r] = rank r's full [M, ldy] output, mapped through NVLink peer access / symmetric memory;
@@ -119,6 +132,68 @@ int b200q_linear_group(const b200q_layer* const* layers, int32_t n_layers, const
 int b200q_linear_sharded(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx,
                          void* const* peer_y, int32_t n_peers, int64_t ldy, int64_t n_offset,
                          void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+
+/*
+ * Column-sharded decode with the all-gather AND the cross-GPU hand-off fused into the kernel (M <= b200q_gemv_max_m()):
+ * sibling layers that share x (n_layers <= 3) run as one launch; this rank computes columns
+ * [n_offset[i], n_offset[i] + layers[i]->N) of output i and stores them into all n_peers replicas
+ * peer_y[i * n_peers + r] (rank r's full [M, ldy[i]] buffer, mapped into this process through NVLink peer access /
+ * symmetric memory); no collective kernel and no host involvement between layers.
+ *   - before reading x the kernel waits until the LOCAL counter word counters[self][wait_slot] has reached
+ *     (*epoch) * wait_count, i.e. every peer's storing CTAs of the layer(s) that produced x have posted
+ *     (wait_slot < 0: x is local, no wait);
+ *   - after the stores of all its CTAs are performed the launch adds b200q_sharded_posts() (currently 1: the storing
+ *     CTAs arrive on a local counter in `workspace`, the last one posts) to counters[r][post_slot] on every peer
+ *     r != self (release, system scope; post_slot < 0: nobody consumes this output remotely), so wait_count of the
+ *     consumer = sum over the (n_peers - 1) peers of their producer's posts.
+ * Counters (u64, symmetric memory, zero at start, slot 0 reserved: set to ~0 when a wait timed out after 2 s) only
+ * ever grow and *epoch is the step number (>= 1, local memory, b200q_peer_epoch_advance once per token), so the whole
+ * token, advance included, is CUDA-graph capturable.  The caller keeps ranks in lock-step by construction: a rank
+ * cannot run ahead of a peer by more than the layers between two waits.
+ * Returns B200Q_ERR_UNSUPPORTED where no streaming decode kernel covers the layers (use b200q_linear_sharded plus
+ * a collective there).  No reference equivalent (the reference is single-GPU).
+ */
+typedef struct b200q_peer_sync {
+  int32_t n_peers;            /* ranks, 1..8 (1: plain local group call) */
+  int32_t self;               /* this rank */
+  uint64_t* const* counters;  /* [n_peers] device pointers: rank r's counter array as mapped in this process */
+  const uint64_t* epoch;      /* local device word: current step number */
+  int32_t wait_slot;          /* counter index awaited before x is read, or -1 */
+  uint32_t wait_count;        /* posts per step that complete wait_slot */
+  int32_t post_slot;          /* counter index posted on every peer after the stores, or -1 */
+  uint32_t flags;             /* B200Q_PEER_Y_TAGGED | B200Q_PEER_X_TAGGED, see below */
+  uint32_t tag_stride;        /* tagged mode: calls per step (any value > every seq) */
+  uint32_t y_seq;             /* tagged mode: index of THIS call inside the step (tags its outputs) */
+  uint32_t x_seq;             /* tagged mode: index of the call that produced x (b200q_peer_untag: that produced `tagged`) */
+} b200q_peer_sync;
+/*
+ * Tagged activations (flag-in-data, the low-latency form of the hand-off; measured on 2 x B200 the counter form costs
+ * ~4-10 us per launch in system-scope fences after the NVLink stores plus ~3-6 us of polling, the tagged form one
+ * NVLink write latency): an element is a 32-bit word  fp16 | tag << 16,  tag = ((*epoch) * tag_stride + seq) & 0xffff
+ * with seq = the index of the writing call inside the step, so a buffer that is rewritten several times per step (once
+ * per decoder block) never shows a stale word with the awaited tag.  Naturally aligned 4-byte stores are single-copy
+ * atomic, so value and tag arrive together and neither side needs a fence, an atomic or a counter.
+ *   B200Q_PEER_Y_TAGGED: peer_y[] are uint32 [M, ldy] buffers; the epilogue writes tagged words (post_slot is ignored).
+ *   B200Q_PEER_X_TAGGED: x is a uint32 [M, ldx] tagged buffer (16-byte aligned); every lane spins on exactly the words
+ *     it needs until they carry this step's tag (wait_slot is ignored).  Integer-path decode kernel only
+ *     (4-bit K-packed layers, M <= 2); elsewhere B200Q_ERR_UNSUPPORTED.
+ * A buffer must not already hold the awaited tag (zero-initialise, epoch starts at 1, tag_stride > 0; consecutive writes
+ * of one buffer differ in seq).  b200q_peer_untag() converts a tagged buffer to plain fp16 for consumers outside the engine.
+ */
+#define B200Q_PEER_Y_TAGGED 1u
+#define B200Q_PEER_X_TAGGED 2u
+int b200q_peer_untag(const void* tagged, int64_t ld_tagged, void* y, int64_t ldy, int64_t M, int64_t N,
+                     const b200q_peer_sync* sync, b200q_stream_t stream);
+int b200q_linear_group_sharded(const b200q_layer* const* layers, int32_t n_layers, const void* x, int64_t M, int64_t ldx,
+                               void* const* peer_y, const int64_t* ldy, const int64_t* n_offset, const b200q_peer_sync* sync,
+                               void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+/* Posts per peer of one b200q_linear_group_sharded call on these layers at batch M; < 0: status. */
+int b200q_sharded_posts(const b200q_layer* const* layers, int32_t n_layers, int64_t M);
+/* The wait half alone, for consumers outside the engine (attention, lm_head, a device-to-host copy): enqueues a
+ * one-thread kernel that returns once counters[self][wait_slot] >= (*epoch) * wait_count (same 2 s bound). */
+int b200q_peer_wait(const b200q_peer_sync* sync, b200q_stream_t stream);
+/* *epoch += 1 on `stream` (one tiny kernel; capture it at the head of the token's CUDA graph). */
+int b200q_peer_epoch_advance(uint64_t* epoch, b200q_stream_t stream);
 
 /*
  * W_out[K, N] (fp16, row-major, ld = N) = dequant(layer), rounded once: fp16((q - z) * s).

@@ -8,6 +8,7 @@ from ._build import LIB
 B200Q_OK = 0
 LAYOUT_GPTQ, LAYOUT_AWQ_GEMM, LAYOUT_MARLIN, LAYOUT_HQQ = 0, 1, 2, 3
 KERNEL_GEMV, KERNEL_GEMM, KERNEL_GENERIC = 1, 2, 3
+PEER_Y_TAGGED, PEER_X_TAGGED = 1, 2
 
 
 class Layer(ctypes.Structure):
@@ -18,9 +19,18 @@ class Layer(ctypes.Structure):
                 ("g_idx", ctypes.c_void_p), ("bias", ctypes.c_void_p)]
 
 
+class PeerSync(ctypes.Structure):
+    """struct b200q_peer_sync"""
+    _fields_ = [("n_peers", ctypes.c_int32), ("self_rank", ctypes.c_int32), ("counters", ctypes.POINTER(ctypes.c_void_p)),
+                ("epoch", ctypes.c_void_p), ("wait_slot", ctypes.c_int32), ("wait_count", ctypes.c_uint32),
+                ("post_slot", ctypes.c_int32), ("flags", ctypes.c_uint32),
+                ("tag_stride", ctypes.c_uint32), ("y_seq", ctypes.c_uint32), ("x_seq", ctypes.c_uint32)]
+
+
 EXPORTS = ["b200q_linear", "b200q_linear_group", "b200q_gemv", "b200q_gemm", "b200q_linear_sharded", "b200q_dequant", "b200q_unpack",
            "b200q_workspace_bytes", "b200q_gemv_max_m", "b200q_select_kernel", "b200q_launch_count",
-           "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4", "b200q_debug_decode_plan", "b200q_debug_set_option"]
+           "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4", "b200q_debug_decode_plan", "b200q_debug_set_option", "b200q_prefetch_hint", "b200q_linear_group_sharded", "b200q_sharded_posts",
+           "b200q_peer_epoch_advance", "b200q_peer_wait", "b200q_peer_untag"]
 
 
 def _load():
@@ -40,6 +50,19 @@ def _load():
     lib.b200q_linear_group.argtypes = [ctypes.POINTER(LP), ctypes.c_int32, P, I64, I64, ctypes.POINTER(P),
                                        ctypes.POINTER(I64), P, SZ, P]
     lib.b200q_linear_group.restype = ctypes.c_int
+    lib.b200q_prefetch_hint.argtypes = [ctypes.POINTER(LP), ctypes.c_int32]
+    lib.b200q_prefetch_hint.restype = ctypes.c_int
+    lib.b200q_linear_group_sharded.argtypes = [ctypes.POINTER(LP), ctypes.c_int32, P, I64, I64, ctypes.POINTER(P),
+                                               ctypes.POINTER(I64), ctypes.POINTER(I64), ctypes.POINTER(PeerSync), P, SZ, P]
+    lib.b200q_linear_group_sharded.restype = ctypes.c_int
+    lib.b200q_sharded_posts.argtypes = [ctypes.POINTER(LP), ctypes.c_int32, I64]
+    lib.b200q_sharded_posts.restype = ctypes.c_int
+    lib.b200q_peer_untag.argtypes = [P, I64, P, I64, I64, I64, ctypes.POINTER(PeerSync), P]
+    lib.b200q_peer_untag.restype = ctypes.c_int
+    lib.b200q_peer_wait.argtypes = [ctypes.POINTER(PeerSync), P]
+    lib.b200q_peer_wait.restype = ctypes.c_int
+    lib.b200q_peer_epoch_advance.argtypes = [P, P]
+    lib.b200q_peer_epoch_advance.restype = ctypes.c_int
     lib.b200q_dequant.argtypes = [LP, P, P]
     lib.b200q_dequant.restype = ctypes.c_int
     lib.b200q_unpack.argtypes = [LP, P, P, P]

@@ -18,6 +18,18 @@ bool decode_carveout_max() {
   return v != 0;
 }
 
+static int g_sync_flags = -1;
+int decode_sync_flags() {
+  if (g_sync_flags < 0) { const char* e = getenv("B200Q_SYNC_FLAGS"); g_sync_flags = e ? atoi(e) : 0; }
+  return g_sync_flags;
+}
+static thread_local PrefetchHint g_hint = {};
+PrefetchHint take_prefetch_hint() {
+  const PrefetchHint h = g_hint;
+  g_hint.n = 0;
+  return h;
+}
+
 static int cuda_status(cudaError_t e) {
   if (e == cudaSuccess) return B200Q_OK;
   g_last_cuda.store((int)e);
@@ -76,8 +88,8 @@ static int gemv_variant() {
       const char* sv = getenv(so[i]);
       if (sv) gemv_stream_set_option(i, atoi(sv));
     }
-    const char* io[5] = {"B200Q_IMMA", "B200Q_IM_CLUSTER", "B200Q_IM_DEPTH", "B200Q_IM_TPC", "B200Q_IM_TARGET"};
-    for (int i = 0; i < 5; ++i) {
+    const char* io[6] = {"B200Q_IMMA", "B200Q_IM_CLUSTER", "B200Q_IM_DEPTH", "B200Q_IM_TPC", "B200Q_IM_TARGET", "B200Q_IM_PREFETCH"};
+    for (int i = 0; i < 6; ++i) {
       const char* sv = getenv(io[i]);
       if (sv) gemv_imma_set_option(i, atoi(sv));
     }
@@ -248,6 +260,169 @@ int b200q_linear_group(const b200q_layer* const* layers, int32_t n_layers, const
   return B200Q_OK;
 }
 
+__global__ void peer_epoch_advance_kernel(unsigned long long* epoch) { *epoch += 1ull; }
+
+int b200q_peer_epoch_advance(uint64_t* epoch, b200q_stream_t stream) {
+  if (!epoch) return B200Q_ERR_NULL;
+  if ((uintptr_t)epoch & 7) return B200Q_ERR_ALIGNMENT;
+  count_launch();
+  peer_epoch_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)epoch);
+  return cuda_status(cudaGetLastError());
+}
+
+// x of a non-b200q consumer (attention, lm_head, the host): one thread waits as the decode kernels do
+__global__ void peer_wait_kernel(const unsigned long long* counter, const unsigned long long* epoch, unsigned int count,
+                                 unsigned long long* poison) {
+  const unsigned long long target = *reinterpret_cast<const volatile unsigned long long*>(epoch) * count;
+  unsigned long long v, t0 = 0;
+  unsigned spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+    if (v >= target) break;
+    if ((++spins & 1023u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) { *poison = ~0ull; break; }
+    }
+  }
+}
+
+int b200q_peer_wait(const b200q_peer_sync* sync, b200q_stream_t stream) {
+  if (!sync) return B200Q_ERR_NULL;
+  if (sync->n_peers < 1 || sync->n_peers > kMaxPeers || sync->self < 0 || sync->self >= sync->n_peers) return B200Q_ERR_SHAPE;
+  if (sync->n_peers == 1 || sync->wait_slot < 0) return B200Q_OK;
+  if (!sync->counters || !sync->counters[sync->self] || !sync->epoch) return B200Q_ERR_NULL;
+  unsigned long long* c = (unsigned long long*)sync->counters[sync->self];
+  count_launch();
+  peer_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(c + sync->wait_slot, (const unsigned long long*)sync->epoch, sync->wait_count, c);
+  return cuda_status(cudaGetLastError());
+}
+
+// tagged words -> plain fp16, waiting for this step's tag on every word (consumers outside the engine)
+__global__ void peer_untag_kernel(const uint32_t* src, int64_t lds, __half* dst, int64_t ldd, int M, int N,
+                                  const unsigned long long* epoch, unsigned int stride, unsigned int seq, unsigned long long* poison) {
+  const uint32_t tag = ((uint32_t)(*reinterpret_cast<const volatile unsigned long long*>(epoch)) * stride + seq) & 0xffffu;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)M * N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i - (int64_t)m * N);
+    const volatile uint32_t* w = src + (size_t)m * lds + n;
+    uint32_t v, spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+      v = *w;
+      if ((v >> 16) == tag) break;
+      if ((++spins & 1023u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000ull) { *poison = ~0ull; break; }
+      }
+    }
+    dst[(size_t)m * ldd + n] = __ushort_as_half((unsigned short)(v & 0xffffu));
+  }
+}
+
+int b200q_peer_untag(const void* tagged, int64_t ld_tagged, void* y, int64_t ldy, int64_t M, int64_t N,
+                     const b200q_peer_sync* sync, b200q_stream_t stream) {
+  if (!tagged || !y || !sync || !sync->epoch || !sync->counters) return B200Q_ERR_NULL;
+  if (sync->self < 0 || sync->self >= sync->n_peers || sync->n_peers > kMaxPeers || !sync->counters[sync->self]) return B200Q_ERR_SHAPE;
+  if (M < 1 || N < 1 || ld_tagged < N || ldy < N) return B200Q_ERR_SHAPE;
+  const int64_t total = M * N;
+  const int blocks = (int)((total + 255) / 256 < 148 ? (total + 255) / 256 : 148);
+  count_launch();
+  peer_untag_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)tagged, ld_tagged, (__half*)y, ldy, (int)M, (int)N,
+                                                             (const unsigned long long*)sync->epoch, sync->tag_stride, sync->x_seq,
+                                                             (unsigned long long*)sync->counters[sync->self]);
+  return cuda_status(cudaGetLastError());
+}
+
+static int group_args(const b200q_layer* const* layers, int32_t n_layers, const void* x, int64_t M, int64_t ldx, LinearArgs* a) {
+  if (!layers) return B200Q_ERR_NULL;
+  if (n_layers < 1 || n_layers > kMaxGroupLayers) return B200Q_ERR_SHAPE;
+  if (M < 1 || M > kGemvMaxM) return B200Q_ERR_SHAPE;
+  gemv_variant();
+  for (int i = 0; i < n_layers; ++i) {
+    const int v = validate(layers[i]);
+    if (v != B200Q_OK) return v;
+    if (ldx < layers[i]->K) return B200Q_ERR_SHAPE;
+    a[i] = {};
+    a[i].L = make_view(layers[i]); a[i].x = (const __half*)x; a[i].ldx = ldx; a[i].M = (int)M;
+  }
+  return B200Q_OK;
+}
+
+int b200q_sharded_posts(const b200q_layer* const* layers, int32_t n_layers, int64_t M) {
+  LinearArgs a[kMaxGroupLayers];
+  const int v = group_args(layers, n_layers, (const void*)16, M, 1 << 30, a);
+  if (v != B200Q_OK) return v;
+  int n = gemv_imma_posts(a, n_layers);
+  if (n < 0) n = gemv_stream_posts(a, n_layers);
+  return n < 0 ? B200Q_ERR_UNSUPPORTED : n;
+}
+
+int b200q_linear_group_sharded(const b200q_layer* const* layers, int32_t n_layers, const void* x, int64_t M, int64_t ldx,
+                               void* const* peer_y, const int64_t* ldy, const int64_t* n_offset, const b200q_peer_sync* sync,
+                               void* workspace, size_t workspace_bytes, b200q_stream_t stream) {
+  if (!x || !peer_y || !ldy || !n_offset || !sync) return B200Q_ERR_NULL;
+  if (sync->n_peers < 1 || sync->n_peers > kMaxPeers || sync->self < 0 || sync->self >= sync->n_peers) return B200Q_ERR_SHAPE;
+  if (sync->n_peers > 1 && (!sync->counters || !sync->epoch)) return B200Q_ERR_NULL;
+  LinearArgs a[kMaxGroupLayers];
+  const int v = group_args(layers, n_layers, x, M, ldx, a);
+  if (v != B200Q_OK) return v;
+  PeerOut po[kMaxGroupLayers];
+  for (int i = 0; i < n_layers; ++i) {
+    if (n_offset[i] < 0 || ldy[i] < n_offset[i] + layers[i]->N) return B200Q_ERR_SHAPE;
+    po[i].n = sync->n_peers;
+    for (int r = 0; r < sync->n_peers; ++r) {
+      void* y = peer_y[(size_t)i * sync->n_peers + r];
+      if (!y) return B200Q_ERR_NULL;
+      po[i].y[r] = (__half*)y;
+    }
+    a[i].y = po[i].y[sync->self]; a[i].ldy = ldy[i]; a[i].n_offset = n_offset[i];
+    a[i].workspace = workspace; a[i].workspace_bytes = workspace_bytes; a[i].stream = (cudaStream_t)stream;
+  }
+  PeerSync ps = {};
+  ps.n_peers = sync->n_peers; ps.self = sync->self; ps.wait_slot = sync->wait_slot; ps.post_slot = sync->post_slot;
+  ps.wait_count = sync->wait_count; ps.epoch = (const unsigned long long*)sync->epoch;
+  ps.y_tagged = (sync->flags & B200Q_PEER_Y_TAGGED) ? 1 : 0;
+  ps.x_tagged = (sync->flags & B200Q_PEER_X_TAGGED) ? 1 : 0;
+  ps.tag_stride = sync->tag_stride; ps.y_seq = sync->y_seq; ps.x_seq = sync->x_seq;
+  if ((ps.y_tagged || ps.x_tagged) && !sync->epoch) return B200Q_ERR_NULL;
+  if (ps.x_tagged && ((uintptr_t)x & 15)) return B200Q_ERR_ALIGNMENT;
+  if ((ps.y_tagged || ps.x_tagged) && (!sync->counters || !sync->counters[sync->self])) return B200Q_ERR_NULL;   // slot 0: time-out poison
+  for (int r = 0; r < sync->n_peers && (sync->n_peers > 1 || ps.x_tagged || ps.y_tagged); ++r) {
+    if (!sync->counters[r]) return B200Q_ERR_NULL;
+    ps.counters[r] = (unsigned long long*)sync->counters[r];
+  }
+  // the hand-off lives in the streaming decode kernels; other kernels would need a separate barrier
+  if (g_use_stream && gemv_imma_supported(a, n_layers)) return cuda_status(launch_gemv_imma(a, n_layers, po, &ps));
+  if (ps.x_tagged) return B200Q_ERR_UNSUPPORTED;            // only the integer-path kernel reads tagged activations
+  if (g_use_stream && gemv_stream_supported(a, n_layers)) return cuda_status(launch_gemv_stream(a, n_layers, po, &ps));
+  return B200Q_ERR_UNSUPPORTED;
+}
+
+int b200q_prefetch_hint(const b200q_layer* const* next_layers, int32_t n_layers) {
+  g_hint.n = 0;
+  if (n_layers == 0) return B200Q_OK;
+  if (!next_layers) return B200Q_ERR_NULL;
+  if (n_layers < 0 || n_layers > kMaxGroupLayers) return B200Q_ERR_SHAPE;
+  PrefetchHint h = {};
+  for (int i = 0; i < n_layers; ++i) {
+    const int v = validate(next_layers[i]);
+    if (v != B200Q_OK) return v;
+    const b200q_layer& L = *next_layers[i];
+    const size_t G = (size_t)((L.K + L.group_size - 1) / L.group_size);
+    const size_t qw = (size_t)L.K * (size_t)L.N * (size_t)L.bits / 8;                  // every layout packs K N b / 8 bytes
+    const size_t sc = G * (size_t)L.N * 2;
+    const size_t qz = L.layout == B200Q_LAYOUT_MARLIN ? 0 : (L.layout == B200Q_LAYOUT_HQQ ? sc : G * (size_t)L.N * (size_t)L.bits / 8);
+    h.ptr[h.n] = (const char*)L.qweight; h.bytes[h.n++] = qw;
+    h.ptr[h.n] = (const char*)L.scales; h.bytes[h.n++] = sc;
+    if (qz) { h.ptr[h.n] = (const char*)L.qzeros; h.bytes[h.n++] = qz; }
+  }
+  g_hint = h;
+  return B200Q_OK;
+}
+
 int b200q_dequant(const b200q_layer* layer, void* w_out, b200q_stream_t stream) {
   const int v = validate(layer);
   if (v != B200Q_OK) return v;
@@ -328,6 +503,8 @@ int b200q_debug_set_option(const char* name, double value) {
   else if (n == "im_depth") gemv_imma_set_option(2, (int)value);
   else if (n == "im_tpc") gemv_imma_set_option(3, (int)value);
   else if (n == "im_target") gemv_imma_set_option(4, (int)value);
+  else if (n == "im_prefetch") gemv_imma_set_option(5, (int)value);
+  else if (n == "sync_flags") g_sync_flags = (int)value;
   else return B200Q_ERR_UNSUPPORTED;
   return B200Q_OK;
 }

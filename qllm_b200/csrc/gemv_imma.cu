@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
   const uint32_t* src = L.qw + ((size_t)(s_begin * 8) + (lane >> 4)) * (size_t)pitch + n0 + 4 * (lane & 15);
   bool pc = 4 * (lane & 15) < min(NT, L.N - n0);
   int irem = nsw, itiles = (nsw > 0) ? nt : 0;
-  auto issue = [&](uint32_t slot_wr) {
+  auto issue = [&](uint32_t slot_wr, bool in_loop) {
     if (itiles > 0) {
       if (pc) {
         const uint32_t* s1 = src + 2 * pitch;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
       src += 8 * pitch;
       if (--irem == 0) {                                                                     // next tile, back to this warp's first k
         irem = nsw;
-        --itiles;
+        if (--itiles == 0 && in_loop) st_prefetch_next(p, warp, lane);                       // own last load is out: start the next layer's stream
         src += NT - (ptrdiff_t)((size_t)nsw * 8 * (size_t)pitch);
         pc = 4 * (lane & 15) < L.N - (n0 + (nt - itiles) * NT);
       }
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
     cp_async_commit();
   };
 #pragma unroll 1
-  for (int d = 0; d < D; ++d) issue(wr_ + d * kIStepBytes);
+  for (int d = 0; d < D; ++d) issue(wr_ + d * kIStepBytes, false);
 
   // (scale, zero) table of the CTA's k-slice: [tile][group][NT] float2
   {
@@ -151,7 +151,14 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
   // ---- activations: wait for the upstream kernel, then split this warp's k-range into digits ----
   // parts: <= 128 k (4 sub-steps of 32 k), never across a group boundary; part table (per warp): {2^-E, sum(x)} per token
   pdl_wait();
+  if (p.sync.n_peers > 1) ST_STAMP(3);                                   // local upstream done; stamp 2 follows the peers' posts
+  st_sync_wait(p, lane);
   ST_STAMP(2);
+  // every CTA of this launch has sent its first D loads and the upstream layer is finished: a warp with nothing left to
+  // request starts the next layer's HBM -> L2 stream now, the others when their last load goes out (never earlier: the
+  // memory system serves requests roughly in order, and a prefetch queued ahead of demand loads delays them)
+  if (itiles == 0) st_prefetch_next(p, warp, lane);
+  const uint32_t xtag = p.sync.x_tagged ? st_step_tag(p, p.sync.x_seq) : 0u;
   char* xq = smem + p.off_x + (size_t)(s_begin - cta_s0) * (2 * XQ_SUB);   // this warp's digit sub-steps
   float2* part = reinterpret_cast<float2*>(smem + p.off_part) + (size_t)warp * (p.part_cap * MTOK);
   const int part_sub = min(4, p.group >> 5);                             // sub-steps per full part (2 or 4: group >= 64)
@@ -165,7 +172,9 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
       for (int m = 0; m < MTOK; ++m) {
         float xv[4] = {0.f, 0.f, 0.f, 0.f};
         if (4 * lane < len) {
-          const uint2 raw = *reinterpret_cast<const uint2*>(p.x + (size_t)m * p.ldx + (size_t)ks * 32 + 4 * lane);
+          const size_t xo = (size_t)m * p.ldx + (size_t)ks * 32 + 4 * lane;
+          const uint2 raw = p.sync.x_tagged ? st_load_tagged4(p, reinterpret_cast<const uint32_t*>(p.x) + xo, xtag)
+                                            : *reinterpret_cast<const uint2*>(p.x + xo);
           const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
           xv[0] = __low2float(h01); xv[1] = __high2float(h01); xv[2] = __low2float(h23); xv[3] = __high2float(h23);
         }
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
       imma_16832(acc[3], wb.z & NIB, wb.w & NIB, (wb.z >> 4) & NIB, (wb.w >> 4) & NIB, xb.x, xb.y);
     }
     __syncwarp();                                                        // every lane has read the slot
-    issue(wr_ + so);
+    issue(wr_ + so, true);
     ++kcur;
     --crem;
     if (--pleft == 0 || crem == 0) {                                     // part and / or tile boundary (warp-uniform)
@@ -315,7 +324,7 @@ struct ImPlan {
   int off_x, off_tab, off_red, off_rbuf, off_rbar, off_ring, off_zpad, off_part, off_mbar, smem_bytes;
 };
 
-static int g_im_on = 1, g_im_cluster = 0, g_im_depth = 0, g_im_tpc = 0, g_im_target = 296;
+static int g_im_on = 1, g_im_cluster = 0, g_im_depth = 0, g_im_tpc = 0, g_im_target = 296, g_im_prefetch = 0;
 static unsigned long long* g_im_dbg = nullptr;
 static size_t g_im_dbg_cap = 0, g_im_dbg_pos = 0;
 void gemv_imma_set_option(int which, int value) {
@@ -324,6 +333,7 @@ void gemv_imma_set_option(int which, int value) {
   else if (which == 2) g_im_depth = value;
   else if (which == 3) g_im_tpc = value;
   else if (which == 4) g_im_target = value;
+  else if (which == 5) g_im_prefetch = value;
 }
 void gemv_imma_set_debug(unsigned long long* buf, size_t cap_entries) { g_im_dbg = buf; g_im_dbg_cap = cap_entries; g_im_dbg_pos = 0; }
 
@@ -445,7 +455,12 @@ static cudaError_t im_launch_k(const StParams& p, const ImPlan& pl, cudaStream_t
   return cudaLaunchKernelEx(&cfg, gemv_imma_kernel<MTOK, D>, p);
 }
 
-cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers) {
+int gemv_imma_posts(const LinearArgs* a, int n) {
+  ImPlan pl;
+  return im_plan(a, n, pl) ? 1 : -1;                       // the last storing CTA posts for the whole launch
+}
+
+cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers, const PeerSync* sync) {
   ImPlan pl;
   if (!im_plan(a, n, pl)) return cudaErrorInvalidValue;
   const LayerView& L = a[0].L;
@@ -456,8 +471,15 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers) {
     StLayer& d = p.layer[i];
     d.qw = a[k].L.qw; d.qz = a[k].L.qz; d.s = a[k].L.s; d.bias = a[k].L.bias; d.N = a[k].L.N;
     d.cta0 = i < n ? pl.cta0[i] : (1 << 30);
-    if (peers && n == 1) d.out = *peers; else { d.out.n = 1; d.out.y[0] = a[k].y; }
+    if (peers) d.out = peers[k]; else { d.out.n = 1; d.out.y[0] = a[k].y; }
     d.ldy = a[k].ldy; d.n_offset = a[k].n_offset;
+  }
+  if (sync) {
+    p.sync = *sync;
+    p.arrive = reinterpret_cast<unsigned int*>(a[0].workspace) + 1000;   // inside the 4 KB counter region every kernel leaves zeroed
+    p.store_ctas = pl.ctas / pl.cluster;
+    p.sync_flags = decode_sync_flags();
+    if (sync->n_peers > 1 && sync->post_slot >= 0 && (!a[0].workspace || a[0].workspace_bytes < kCounterBytes)) return cudaErrorInvalidValue;
   }
   p.layout = L.layout; p.bits = L.bits; p.group = L.group; p.K = L.K; p.G = L.G; p.zero_bias = L.zero_bias;
   p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M;
@@ -466,6 +488,17 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers) {
   p.x_stride = 0; p.red_stride = pl.tpc * kINT * a[0].M;
   p.off_x = pl.off_x; p.off_tab = pl.off_tab; p.off_red = pl.off_red; p.off_rbuf = pl.off_rbuf; p.off_rbar = pl.off_rbar;
   p.off_ring = pl.off_ring; p.off_zpad = pl.off_zpad; p.off_part = pl.off_part; p.off_mbar = pl.off_mbar;
+  // next layers on this stream (one-shot hint): each of this launch's warps requests 1 / (8 ctas) of every range
+  const PrefetchHint h = take_prefetch_hint();
+  p.n_pf = 0;
+  for (int i = 0; i < h.n && g_im_prefetch; ++i) {
+    if (!h.ptr[i] || h.bytes[i] < 16 || h.bytes[i] >= (1ull << 32) || ((uintptr_t)h.ptr[i] & 15)) continue;
+    const uint32_t bytes = (uint32_t)(h.bytes[i] & ~(size_t)15), units = (uint32_t)pl.ctas * kWarps;
+    p.pf_ptr[p.n_pf] = h.ptr[i];
+    p.pf_bytes[p.n_pf] = bytes;
+    p.pf_chunk[p.n_pf] = ((bytes + units - 1) / units + 127u) & ~127u;
+    ++p.n_pf;
+  }
   p.dbg = nullptr;
   if (g_im_dbg) {
     const size_t need = (size_t)pl.ctas * 8;

@@ -29,14 +29,122 @@ struct StParams {
   int red_stride;                                // floats between two warps' partial-sum vectors
   int off_x, off_tab, off_red, off_rbuf, off_rbar, off_ring, off_zpad, off_part, off_mbar;
   unsigned long long* dbg;                       // optional per-CTA phase stamps (diagnostic)
+  // L2 prefetch of the layer(s) that will run next on this stream (b200q_prefetch_hint): byte ranges (16-byte
+  // aligned, multiples of 16 bytes) and the share of each range one warp of this launch requests
+  PeerSync sync;                                 // cross-GPU hand-off (n_peers == 0: none)
+  unsigned int* arrive;                          // local arrival counter of the storing CTAs (workspace, left zeroed)
+  int store_ctas;
+  int sync_flags;                                // diagnostic (B200Q_SYNC_FLAGS): 1 no remote stores, 2 no wait, 4 no post, 8 back-off polling, 16 one poller per CTA
+  const char* pf_ptr[kMaxPrefetch];
+  uint32_t pf_bytes[kMaxPrefetch], pf_chunk[kMaxPrefetch];
+  int n_pf;
 };
+
+// One warp's share of the next layers' packed bytes, requested from HBM into L2 with cp.async.bulk.prefetch.L2: issued
+// when the warp has sent its own last weight load, so the memory system never idles across the kernel boundary
+// (reduction, store, programmatic hand-off and the next launch's prologue all overlap the next layer's stream).
+__device__ __forceinline__ void st_prefetch_next(const StParams& p, int warp, int lane) {
+  if (lane < p.n_pf) {
+    const uint32_t bytes = p.pf_bytes[lane], chunk = p.pf_chunk[lane];
+    const uint32_t off = (blockIdx.x * kWarps + warp) * chunk;
+    if (off < bytes) {
+      const uint32_t len = min(chunk, bytes - off);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr[lane] + off), "r"(len) : "memory");
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long st_gtime();
+// Consumer side of the cross-GPU hand-off: x is complete once every peer's storing CTAs of this step have posted.
+// One lane per warp polls the local counter (acquire, system scope); the spin is bounded (2 s) so a dead peer
+// cannot hang the GPU -- the step's numbers are then garbage, and counter slot 0 of this rank is poisoned.
+__device__ __forceinline__ void st_sync_wait(const StParams& p, int lane) {
+  if (p.sync.n_peers > 1 && p.sync.wait_slot >= 0 && !p.sync.x_tagged && !(p.sync_flags & 2)) {
+    if (p.sync_flags & 16) {
+      if (threadIdx.x == 0) {
+        const unsigned long long target = *reinterpret_cast<const volatile unsigned long long*>(p.sync.epoch) * p.sync.wait_count;
+        const unsigned long long* c = p.sync.counters[p.sync.self] + p.sync.wait_slot;
+        unsigned long long v;
+        for (;;) {
+          asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(c) : "memory");
+          if (v >= target) break;
+          __nanosleep(64);
+        }
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+      }
+      __syncthreads();
+      return;
+    }
+    if (lane == 0) {
+      const unsigned long long target = *reinterpret_cast<const volatile unsigned long long*>(p.sync.epoch) * p.sync.wait_count;
+      const unsigned long long* c = p.sync.counters[p.sync.self] + p.sync.wait_slot;
+      unsigned long long v, t0 = 0;
+      unsigned spins = 0;
+      for (;;) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(c) : "memory");
+        if (v >= target) break;
+        if (p.sync_flags & 8) __nanosleep(64);
+        if ((++spins & 1023u) == 0) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 2000000000ull) { p.sync.counters[p.sync.self][0] = ~0ull; break; }
+        }
+      }
+      asm volatile("fence.acq_rel.sys;" ::: "memory");      // the peers' stores that preceded their posts are visible from here on
+    }
+    __syncwarp();
+  }
+}
+// Tagged activations: four consecutive elements (words) of x, spun on until every word carries this step's tag.
+// Each lane polls only the words it needs -- the hand-off is data-flow, not a barrier.  Same 2 s bound as st_sync_wait.
+__device__ __forceinline__ uint2 st_load_tagged4(const StParams& p, const uint32_t* w, uint32_t tag) {
+  uint32_t a, b, c, d, spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(w) : "memory");
+    if (((a >> 16) == tag) & ((b >> 16) == tag) & ((c >> 16) == tag) & ((d >> 16) == tag)) break;
+    if ((++spins & 1023u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) { p.sync.counters[p.sync.self][0] = ~0ull; break; }
+    }
+  }
+  return make_uint2((a & 0xffffu) | (b << 16), (c & 0xffffu) | (d << 16));
+}
+__device__ __forceinline__ uint32_t st_step_tag(const StParams& p, uint32_t seq) {
+  return ((uint32_t)(*reinterpret_cast<const volatile unsigned long long*>(p.sync.epoch)) * p.sync.tag_stride + seq) & 0xffffu;
+}
+
+// Producer side: called by every thread of a storing CTA after its stores to the peers' buffers.  The storing CTAs
+// arrive on a LOCAL counter; the last one posts once per peer (many system-scope atomics on one remote word
+// serialise at ~100 ns each over NVLink -- measured: 250 posts per call cost 24 us).
+__device__ __forceinline__ void st_sync_post(const StParams& p, int tid) {
+  if (p.sync.n_peers > 1 && p.sync.post_slot >= 0 && !p.sync.y_tagged && !(p.sync_flags & 4)) {
+    __syncthreads();                                        // all of the CTA's peer stores precede the fence below
+    if (tid == 0) {
+      __threadfence_system();                               // ... and are performed at the peers before the arrival
+      const unsigned int old = atomicAdd(p.arrive, 1u);
+      if (old == (unsigned int)p.store_ctas - 1u) {
+        *p.arrive = 0u;                                     // self-cleaning: the next call starts from zero
+        __threadfence_system();
+        for (int r = 0; r < p.sync.n_peers; ++r)
+          if (r != p.sync.self)
+            asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p.sync.counters[r] + p.sync.post_slot), "l"(1ull) : "memory");
+      }
+    }
+  }
+}
 
 __device__ __forceinline__ unsigned long long st_gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define ST_STAMP(i) do { if (p.dbg && tid == 0) p.dbg[(size_t)blockIdx.x * 8 + (i)] = st_gtime(); } while (0)
+// slot 7 of a CTA's row: (grid size << 32 | CTA index), written with the first stamp (lets a reader split launches)
+#define ST_STAMP(i) do { if (p.dbg && tid == 0) { p.dbg[(size_t)blockIdx.x * 8 + (i)] = st_gtime(); \
+    if ((i) == 0) p.dbg[(size_t)blockIdx.x * 8 + 7] = ((unsigned long long)gridDim.x << 32) | blockIdx.x; } } while (0)
 
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -89,6 +197,7 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
         for (int q = 0; q < cs - 1; ++q) v[r] += rbuf[(size_t)q * totalv + idx];
     }
   }
+  const uint32_t ytag = p.sync.y_tagged ? st_step_tag(p, p.sync.y_seq) << 16 : 0u;
 #pragma unroll
   for (int r = 0; r < NV; ++r) {
     const int idx = tid + r * kRpThreads;
@@ -97,9 +206,17 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
       float o = v[r];
       if (SL.bias) o += __half2float(__ldg(SL.bias + n0 + n));
       const __half h = __float2half_rn(o);
-      for (int q = 0; q < SL.out.n; ++q) SL.out.y[q][(size_t)m * SL.ldy + SL.n_offset + n0 + n] = h;
+      if (p.sync.y_tagged) {                                // one 4-byte store per element and replica: value and tag land together
+        const uint32_t w = ytag | (uint32_t)__half_as_ushort(h);
+        for (int q = 0; q < SL.out.n; ++q)
+          reinterpret_cast<uint32_t*>(SL.out.y[q])[(size_t)m * SL.ldy + SL.n_offset + n0 + n] = w;
+        continue;
+      }
+      for (int q = 0; q < SL.out.n; ++q)
+        if (!(p.sync_flags & 1) || q == p.sync.self) SL.out.y[q][(size_t)m * SL.ldy + SL.n_offset + n0 + n] = h;
     }
   }
+  st_sync_post(p, tid);
   ST_STAMP(6);
 }
 

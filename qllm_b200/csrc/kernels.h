@@ -31,6 +31,33 @@ struct PeerOut {
   int n;
 };
 
+// Cross-GPU hand-off fused into the decode kernels (b200q_linear_group_sharded): counters live in symmetric memory,
+// counters[r] = rank r's array mapped into this process.  Counters only ever grow: a consumer waits for
+// counter >= epoch * wait_count, a producer adds 1 per storing CTA on every peer, `epoch` is the step number kept
+// in local device memory (b200q_peer_epoch_advance), so nothing is ever reset and a CUDA graph can bake all of it.
+struct PeerSync {
+  unsigned long long* counters[kMaxPeers];
+  const unsigned long long* epoch;
+  int n_peers, self, wait_slot, post_slot;
+  unsigned int wait_count;                 // posts (summed over all peers) that complete one step of the awaited slot
+  // Tagged mode (flag-in-data, no fences / atomics / counters): an activation element is a 32-bit word
+  // fp16 | (epoch & 0xffff) << 16; 4-byte stores are single-copy atomic, so a reader that sees the step's tag sees the value.
+  // The tag of a buffer write is ((*epoch) * tag_stride + seq) & 0xffff with seq = the writer's call index inside the
+  // step: a buffer rewritten several times per step (once per decoder block) never shows a stale word with the awaited tag.
+  int y_tagged, x_tagged;
+  unsigned int tag_stride, y_seq, x_seq;
+};
+
+// api.cu: one-shot hint (b200q_prefetch_hint) consumed by the next decode launch of the calling thread
+static constexpr int kMaxPrefetch = 9;
+struct PrefetchHint {
+  const char* ptr[kMaxPrefetch];
+  size_t bytes[kMaxPrefetch];
+  int n;
+};
+PrefetchHint take_prefetch_hint();
+int decode_sync_flags();        // diagnostic switch (B200Q_SYNC_FLAGS / "sync_flags")
+
 // unpack.cu
 cudaError_t launch_unpack(const LayerView& L, int32_t* q_out, int32_t* z_out, cudaStream_t st);
 cudaError_t launch_dequant(const LayerView& L, __half* w_out, cudaStream_t st);
@@ -60,14 +87,16 @@ void gemv_rp_set_debug(unsigned long long* buf, size_t cap_entries);
 // gemv_stream.cu : streaming decode path (per-warp cp.async rings, sibling layers fused in one launch), M <= 8
 static constexpr int kMaxGroupLayers = 3;
 bool gemv_stream_supported(const LinearArgs* a, int n);
-cudaError_t launch_gemv_stream(const LinearArgs* a, int n, const PeerOut* peers);
+cudaError_t launch_gemv_stream(const LinearArgs* a, int n, const PeerOut* peers, const PeerSync* sync = nullptr);   // peers: NULL or one per layer
+int gemv_stream_posts(const LinearArgs* a, int n);    // storing CTAs of the launch (= posts per peer), -1 if unsupported
 bool gemv_stream_describe(const LinearArgs* a, int n, int out[6]);
 void gemv_stream_set_option(int which, int value);
 void gemv_stream_set_debug(unsigned long long* buf, size_t cap_entries);
 
 // gemv_imma.cu : integer-tensor-path decode kernel for K-packed 4-bit layers, M <= 2
 bool gemv_imma_supported(const LinearArgs* a, int n);
-cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers);
+cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers, const PeerSync* sync = nullptr);     // peers: NULL or one per layer
+int gemv_imma_posts(const LinearArgs* a, int n);
 bool gemv_imma_describe(const LinearArgs* a, int n, int out[6]);
 void gemv_imma_set_option(int which, int value);
 void gemv_imma_set_debug(unsigned long long* buf, size_t cap_entries);

@@ -10,7 +10,7 @@ import ctypes
 import torch
 import torch.nn as nn
 
-from ._lib import check, lib
+from ._lib import Layer, PeerSync, check, lib
 from .q_layers import (QuantLinearGPTQ, QuantLinearHQQ, QuantLinearMarlin, WQLinear_GEMM, _workspace)
 
 
@@ -109,3 +109,110 @@ def sharded_forward_into_peers(local, x, peer_outputs, n_offset: int):
                                   peer_outputs[0].stride(0), n_offset, ws.data_ptr(), ws.numel(),
                                   torch.cuda.current_stream(x.device).cuda_stream)
     check(st, "b200q_linear_sharded")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fused all-gather + cross-GPU hand-off (b200q_linear_group_sharded): no collective kernel between layers.
+
+class PeerArena:
+    """One symmetric-memory allocation per rank, mapped into every rank of the node over NVLink
+    (torch.distributed._symmetric_memory): `n_slots` u64 hand-off counters followed by caller-carved output replicas.
+    ptr(r, off) is the address of byte `off` of rank r's arena as seen from this process."""
+    COUNTER_BYTES = 8
+
+    def __init__(self, payload_bytes: int, n_slots: int = 1024, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.counter_bytes = (n_slots * self.COUNTER_BYTES + 255) & ~255
+        self.nbytes = self.counter_bytes + ((payload_bytes + 255) & ~255)
+        self.buf = symm.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        self.hdl = symm.rendezvous(self.buf, self.group.group_name if hasattr(self.group, "group_name") else self.group)
+        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(self.base) != self.world or self.base[self.rank] != self.buf.data_ptr():
+            raise RuntimeError("symmetric-memory rendezvous returned inconsistent buffer pointers")
+        self.buf.zero_()
+        torch.cuda.synchronize()
+        dist.barrier(self.group)
+        self._cursor = self.counter_bytes
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=self.device)          # local step number
+        self._counters = (ctypes.c_void_p * self.world)(*self.base)                 # counters sit at offset 0
+
+    def carve(self, nbytes: int) -> int:
+        """Reserve `nbytes` (256-byte aligned) of payload; returns the offset, identical on every rank."""
+        off = self._cursor
+        self._cursor += (nbytes + 255) & ~255
+        if self._cursor > self.nbytes:
+            raise MemoryError("PeerArena payload exhausted")
+        return off
+
+    def ptr(self, r: int, off: int) -> int:
+        return self.base[r] + off
+
+    def local_view(self, off: int, shape, dtype=torch.float16):
+        n = 1
+        for s in shape:
+            n *= s
+        return self.buf[off:off + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
+
+    def sync_desc(self, wait_slot: int = -1, wait_count: int = 0, post_slot: int = -1, flags: int = 0,
+                  tag_stride: int = 1, y_seq: int = 0, x_seq: int = 0) -> PeerSync:
+        s = PeerSync()
+        s.n_peers, s.self_rank = self.world, self.rank
+        s.counters = ctypes.cast(self._counters, ctypes.POINTER(ctypes.c_void_p))
+        s.epoch = self.epoch.data_ptr()
+        s.wait_slot, s.wait_count, s.post_slot, s.flags = wait_slot, wait_count, post_slot, flags
+        s.tag_stride, s.y_seq, s.x_seq = tag_stride, y_seq, x_seq
+        return s
+
+    def untag(self, off: int, M: int, N: int, out: torch.Tensor, tag_stride: int, seq: int, stream=None):
+        """out[M, N] fp16 = the tagged replica at arena offset `off`, once every word carries the tag of call `seq`."""
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        s = self.sync_desc(tag_stride=tag_stride, x_seq=seq)
+        check(lib.b200q_peer_untag(self.ptr(self.rank, off), N, out.data_ptr(), out.stride(0), M, N, ctypes.byref(s), st),
+              "b200q_peer_untag")
+
+    def advance(self, stream=None):
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        check(lib.b200q_peer_epoch_advance(self.epoch.data_ptr(), st), "b200q_peer_epoch_advance")
+
+    def wait(self, wait_slot: int, wait_count: int, stream=None):
+        """Make `stream` wait until the awaited output is complete locally (for consumers outside the engine)."""
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        s = self.sync_desc(wait_slot, wait_count, -1)
+        check(lib.b200q_peer_wait(ctypes.byref(s), st), "b200q_peer_wait")
+
+    def poisoned(self) -> bool:
+        """True when a kernel gave up waiting for a peer (2 s) -- the outputs of that step are invalid."""
+        return bool(self.buf[:8].view(torch.int64).item() != 0)
+
+
+def sharded_group_posts(local_layers, M: int) -> int:
+    """Storing CTAs (= posts per peer) of one fused call on this rank's shards."""
+    descs = [l._decode_descriptor(M) for l in local_layers]
+    arr = (ctypes.POINTER(Layer) * len(descs))(*[ctypes.pointer(d) for d in descs])
+    n = lib.b200q_sharded_posts(arr, len(descs), M)
+    check(min(n, 0), "b200q_sharded_posts")
+    return n
+
+
+def sharded_group_forward(arena: PeerArena, local_layers, x, out_offsets, full_ns, col0s, sync: PeerSync, ws, stream=None,
+                          x_ptr=None, M=None, ldx=None):
+    """One launch: this rank's column shards of sibling layers `local_layers` (shared x [M, K]) stored at column
+    col0s[i] of the replicas at arena offset out_offsets[i] ([M, full_ns[i]] fp16, or uint32 words with
+    PEER_Y_TAGGED) on EVERY rank, with the hand-off described by `sync` (PeerArena.sync_desc).  Tagged activations
+    (PEER_X_TAGGED) are passed as x_ptr / M / ldx (a uint32 [M, ldx] replica)."""
+    n, P = len(local_layers), arena.world
+    if x_ptr is None:                                       # plain fp16 activations
+        x2 = x.reshape(-1, x.shape[-1])
+        M, x_ptr, ldx = x2.shape[0], x2.data_ptr(), x2.stride(0)
+    descs = [l._decode_descriptor(M) for l in local_layers]
+    arr = (ctypes.POINTER(Layer) * n)(*[ctypes.pointer(d) for d in descs])
+    yp = (ctypes.c_void_p * (n * P))(*[arena.ptr(r, out_offsets[i]) for i in range(n) for r in range(P)])
+    ld = (ctypes.c_int64 * n)(*full_ns)
+    no = (ctypes.c_int64 * n)(*col0s)
+    st = torch.cuda.current_stream(arena.device).cuda_stream if stream is None else stream
+    check(lib.b200q_linear_group_sharded(arr, n, x_ptr, M, ldx, yp, ld, no, ctypes.byref(sync),
+                                         ws.data_ptr(), ws.numel(), st), "b200q_linear_group_sharded")

@@ -1,5 +1,5 @@
 #!/bin/bash
-O=gpurun_out/e30; mkdir -p $O
+O=gpurun_out/e31; mkdir -p $O
 echo "== pytest"; timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 | tee $O/pytest.txt
 echo "== microbench imma"; timeout 300 python tools/microbench.py --m 1 --graph --iters 400 --layouts GPTQ 2>&1 | tee $O/mb_imma.log | cut -c1-150
 echo "== timeline (graph) imma"; for sh in 4096x4096 4096x11008; do timeout 200 python tools/timeline.py --layout GPTQ --shape $sh --launches 5 2>&1 | tail -6 | tee -a $O/timeline_imma.txt; done
