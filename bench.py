@@ -175,7 +175,6 @@ class DecodeStep:
         import qllm_b200
         self.lib, self.blocks, self.M, self.world, self.rank = qllm_b200.lib, blocks, M, world, rank
         self.fuse = os.environ.get("B200Q_BENCH_NO_GROUP") is None
-        self.chain = os.environ.get("B200Q_BENCH_NO_CHAIN") is None
         f16 = dict(dtype=torch.float16, device=dev)
         self.h = torch.zeros(M, HIDDEN, **f16)
         self.bufs = {n: torch.zeros(M, N, **f16) for n, _, N in SHAPES}
@@ -226,28 +225,12 @@ class DecodeStep:
                                           self.ws.numel(), stream))
         return ys
 
-    def _hint(self, layers):
-        """b200q_prefetch_hint: the layers that follow the next call (what qllm_b200.link_decode_chain installs)."""
-        if not self.chain or self.world > 1:
-            return
-        from qllm_b200 import check, Layer
-        descs = [l._decode_descriptor(self.M) for l in layers]
-        arr = (ctypes.POINTER(Layer) * len(descs))(*[ctypes.pointer(d) for d in descs])
-        check(self.lib.b200q_prefetch_hint(arr, len(descs)))
-
     def run(self, stream):
         h = self.h
-        nb = len(self.blocks)
-        for i, b in enumerate(self.blocks):
-            self._hint([b["o"]])
+        for b in self.blocks:
             q, k, v = self._group([b["q"], b["k"], b["v"]], h, ["q", "k", "v"], stream)
-            self._hint([b["gate"], b["up"]])
             o = self._call(b["o"], v, "o", stream)
-            self._hint([b["down"]])
             gt, up = self._group([b["gate"], b["up"]], o, ["gate", "up"], stream)
-            if i + 1 < nb:
-                n = self.blocks[i + 1]
-                self._hint([n["q"], n["k"], n["v"]])
             h = self._call(b["down"], gt, "down", stream)
         return h
 
@@ -282,7 +265,7 @@ class FusedShardedStep:
         self.wait_counts = [sum(every[r][j] for r in range(world) if r != rank) for j in range(len(self.CALLS))]
         need = max(self.lib.b200q_workspace_bytes(ctypes.byref(l._decode_descriptor(M)), M) for l in blocks[0].values())
         self.ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=dev)
-        self.fuse, self.chain = True, False
+        self.fuse = True
         # load the kernels locally (lazy module loading can take seconds) before any rank waits on a peer (2 s bound)
         for l in blocks[0].values():
             l(torch.zeros(M, l.infeatures, dtype=torch.float16, device=dev))
@@ -427,7 +410,6 @@ def run_b200q(args, rank, world, local_rank):
         "config": {"workload": "Llama-2-7B int4 g128 AWQ pack_mode=GEMM, batch=1 decode: the 224 QuantLinear layers of one token "
                                "in LlamaDecoderLayer dependency order (q|k|v -> o -> gate|up -> down)",
                    "launches_per_step": int(launches_per_step), "sibling_groups": bool(step.fuse and world == 1),
-                   "next_layer_l2_prefetch": bool(step.chain and world == 1),
                    "M": M, "layers": n_layers, "parallelism": (f"column-shard x{world}, all-gather + hand-off fused into the decode kernels (NVLink peer stores, "
                                     + ("tagged activations" if getattr(step, "tagged", False) else "counter post/wait") + ")" if fused_sharded
                                    else f"column-shard x{world} + NCCL all-gather per layer") if world > 1 else "single GPU",
@@ -480,7 +462,7 @@ def prefill_tflops(dev, P, M=512, iters=20):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200q", choices=["b200q", "reference"])
     ap.add_argument("--no-cpu", action="store_true")

@@ -111,19 +111,6 @@ int b200q_linear_group(const b200q_layer* const* layers, int32_t n_layers, const
                        b200q_stream_t stream);
 
 /*
- * One-shot hint for decode chains: `next_layers` (n_layers <= 3, one sibling group) are the layers that will run
- * right AFTER the calling thread's next b200q_linear / _linear_group / _linear_sharded call on the same stream.
- * The decode kernel launched by that next call asks for their packed bytes to be brought from HBM into L2
- * (cp.async.bulk.prefetch.L2) as soon as its own last weight load has been issued, so HBM keeps streaming across
- * the kernel boundary (reduction, store, hand-off, the next launch's prologue).  Purely a performance hint:
- * results are unaffected; kernels without the mechanism ignore it; n_layers = 0 clears a pending hint.
- * No reference equivalent: the reference issues each QuantLinear.forward in isolation
- * (quant_linear_gptq.py:136-143, quant_linear_awq.py:142-148).  The host shim derives the order from the
- * model's module tree (qllm_b200.link_decode_chain).
- */
-int b200q_prefetch_hint(const b200q_layer* const* next_layers, int32_t n_layers);
-
-/*
  * Multi-GPU column-sharded forward with the all-gather fused into the epilogue: this rank computes
  * y[:, n_offset : n_offset + layer->N] and stores the tile into `n_peers` output buffers
  * (peer_y[r] = rank r's full [M, ldy] output, mapped through NVLink peer access / symmetric memory;
@@ -150,8 +137,9 @@ int b200q_linear_sharded(const b200q_layer* layer, const void* x, int64_t M, int
  * ever grow and *epoch is the step number (>= 1, local memory, b200q_peer_epoch_advance once per token), so the whole
  * token, advance included, is CUDA-graph capturable.  The caller keeps ranks in lock-step by construction: a rank
  * cannot run ahead of a peer by more than the layers between two waits.
- * Returns B200Q_ERR_UNSUPPORTED where no streaming decode kernel covers the layers (use b200q_linear_sharded plus
- * a collective there).  No reference equivalent (the reference is single-GPU).
+ * Returns B200Q_ERR_UNSUPPORTED where the integer-path decode kernel does not cover the layers (4-bit GPTQ / HQQ
+ * K-packed buffers -- AWQ / Marlin through b200q_repack_gptq4 -- no act-order, M <= 2): use b200q_linear_sharded
+ * plus a collective there.  No reference equivalent (the reference is single-GPU).
  */
 typedef struct b200q_peer_sync {
   int32_t n_peers;            /* ranks, 1..8 (1: plain local group call) */
@@ -175,8 +163,7 @@ typedef struct b200q_peer_sync {
  * atomic, so value and tag arrive together and neither side needs a fence, an atomic or a counter.
  *   B200Q_PEER_Y_TAGGED: peer_y[] are uint32 [M, ldy] buffers; the epilogue writes tagged words (post_slot is ignored).
  *   B200Q_PEER_X_TAGGED: x is a uint32 [M, ldx] tagged buffer (16-byte aligned); every lane spins on exactly the words
- *     it needs until they carry this step's tag (wait_slot is ignored).  Integer-path decode kernel only
- *     (4-bit K-packed layers, M <= 2); elsewhere B200Q_ERR_UNSUPPORTED.
+ *     it needs until they carry this step's tag (wait_slot is ignored).
  * A buffer must not already hold the awaited tag (zero-initialise, epoch starts at 1, tag_stride > 0; consecutive writes
  * of one buffer differ in seq).  b200q_peer_untag() converts a tagged buffer to plain fp16 for consumers outside the engine.
  */

@@ -5,7 +5,7 @@ if the library has not been built the import raises: there is no CPU or PyTorch 
 """
 from ._lib import lib, check, Layer  # noqa: F401  (raises ImportError when the .so is missing)
 from .q_layers import (QuantLinearGPTQ, QuantLinearHQQ, QuantLinearMarlin, WQLinear_GEMM,  # noqa: F401
-                       fuse_siblings, linear_group, link_decode_chain, make_mixbits_quant_linear, select_quant_linear)
+                       fuse_siblings, linear_group, make_mixbits_quant_linear, select_quant_linear)
 
 __version__ = "0.1.0"
 

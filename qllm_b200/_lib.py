@@ -29,7 +29,7 @@ class PeerSync(ctypes.Structure):
 
 EXPORTS = ["b200q_linear", "b200q_linear_group", "b200q_gemv", "b200q_gemm", "b200q_linear_sharded", "b200q_dequant", "b200q_unpack",
            "b200q_workspace_bytes", "b200q_gemv_max_m", "b200q_select_kernel", "b200q_launch_count",
-           "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4", "b200q_debug_decode_plan", "b200q_debug_set_option", "b200q_prefetch_hint", "b200q_linear_group_sharded", "b200q_sharded_posts",
+           "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4", "b200q_debug_decode_plan", "b200q_debug_set_option", "b200q_linear_group_sharded", "b200q_sharded_posts",
            "b200q_peer_epoch_advance", "b200q_peer_wait", "b200q_peer_untag"]
 
 
@@ -39,6 +39,15 @@ def _load():
             f"{LIB} not found: build it with `python -m qllm_b200._build` (nvcc, sm_100a). "
             "qllm_b200 has no CPU or PyTorch fallback.")
     lib = ctypes.CDLL(LIB)
+    if os.environ.get("B200Q_LIB"):                       # A/B run against an older build: stub what it lacks
+        class _Missing:
+            argtypes = restype = None
+
+            def __call__(self, *a):
+                raise RuntimeError("entry point missing from the B200Q_LIB build")
+        for name in EXPORTS:
+            if not hasattr(lib, name):
+                setattr(lib, name, _Missing())
     P, I64, SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
     LP = ctypes.POINTER(Layer)
     fwd = [LP, P, I64, I64, P, I64, P, SZ, P]
@@ -50,8 +59,6 @@ def _load():
     lib.b200q_linear_group.argtypes = [ctypes.POINTER(LP), ctypes.c_int32, P, I64, I64, ctypes.POINTER(P),
                                        ctypes.POINTER(I64), P, SZ, P]
     lib.b200q_linear_group.restype = ctypes.c_int
-    lib.b200q_prefetch_hint.argtypes = [ctypes.POINTER(LP), ctypes.c_int32]
-    lib.b200q_prefetch_hint.restype = ctypes.c_int
     lib.b200q_linear_group_sharded.argtypes = [ctypes.POINTER(LP), ctypes.c_int32, P, I64, I64, ctypes.POINTER(P),
                                                ctypes.POINTER(I64), ctypes.POINTER(I64), ctypes.POINTER(PeerSync), P, SZ, P]
     lib.b200q_linear_group_sharded.restype = ctypes.c_int

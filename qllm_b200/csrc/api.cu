@@ -23,13 +23,6 @@ int decode_sync_flags() {
   if (g_sync_flags < 0) { const char* e = getenv("B200Q_SYNC_FLAGS"); g_sync_flags = e ? atoi(e) : 0; }
   return g_sync_flags;
 }
-static thread_local PrefetchHint g_hint = {};
-PrefetchHint take_prefetch_hint() {
-  const PrefetchHint h = g_hint;
-  g_hint.n = 0;
-  return h;
-}
-
 static int cuda_status(cudaError_t e) {
   if (e == cudaSuccess) return B200Q_OK;
   g_last_cuda.store((int)e);
@@ -88,8 +81,8 @@ static int gemv_variant() {
       const char* sv = getenv(so[i]);
       if (sv) gemv_stream_set_option(i, atoi(sv));
     }
-    const char* io[6] = {"B200Q_IMMA", "B200Q_IM_CLUSTER", "B200Q_IM_DEPTH", "B200Q_IM_TPC", "B200Q_IM_TARGET", "B200Q_IM_PREFETCH"};
-    for (int i = 0; i < 6; ++i) {
+    const char* io[5] = {"B200Q_IMMA", "B200Q_IM_CLUSTER", "B200Q_IM_DEPTH", "B200Q_IM_TPC", "B200Q_IM_TARGET"};
+    for (int i = 0; i < 5; ++i) {
       const char* sv = getenv(io[i]);
       if (sv) gemv_imma_set_option(i, atoi(sv));
     }
@@ -356,7 +349,6 @@ int b200q_sharded_posts(const b200q_layer* const* layers, int32_t n_layers, int6
   const int v = group_args(layers, n_layers, (const void*)16, M, 1 << 30, a);
   if (v != B200Q_OK) return v;
   int n = gemv_imma_posts(a, n_layers);
-  if (n < 0) n = gemv_stream_posts(a, n_layers);
   return n < 0 ? B200Q_ERR_UNSUPPORTED : n;
 }
 
@@ -396,31 +388,7 @@ int b200q_linear_group_sharded(const b200q_layer* const* layers, int32_t n_layer
   }
   // the hand-off lives in the streaming decode kernels; other kernels would need a separate barrier
   if (g_use_stream && gemv_imma_supported(a, n_layers)) return cuda_status(launch_gemv_imma(a, n_layers, po, &ps));
-  if (ps.x_tagged) return B200Q_ERR_UNSUPPORTED;            // only the integer-path kernel reads tagged activations
-  if (g_use_stream && gemv_stream_supported(a, n_layers)) return cuda_status(launch_gemv_stream(a, n_layers, po, &ps));
-  return B200Q_ERR_UNSUPPORTED;
-}
-
-int b200q_prefetch_hint(const b200q_layer* const* next_layers, int32_t n_layers) {
-  g_hint.n = 0;
-  if (n_layers == 0) return B200Q_OK;
-  if (!next_layers) return B200Q_ERR_NULL;
-  if (n_layers < 0 || n_layers > kMaxGroupLayers) return B200Q_ERR_SHAPE;
-  PrefetchHint h = {};
-  for (int i = 0; i < n_layers; ++i) {
-    const int v = validate(next_layers[i]);
-    if (v != B200Q_OK) return v;
-    const b200q_layer& L = *next_layers[i];
-    const size_t G = (size_t)((L.K + L.group_size - 1) / L.group_size);
-    const size_t qw = (size_t)L.K * (size_t)L.N * (size_t)L.bits / 8;                  // every layout packs K N b / 8 bytes
-    const size_t sc = G * (size_t)L.N * 2;
-    const size_t qz = L.layout == B200Q_LAYOUT_MARLIN ? 0 : (L.layout == B200Q_LAYOUT_HQQ ? sc : G * (size_t)L.N * (size_t)L.bits / 8);
-    h.ptr[h.n] = (const char*)L.qweight; h.bytes[h.n++] = qw;
-    h.ptr[h.n] = (const char*)L.scales; h.bytes[h.n++] = sc;
-    if (qz) { h.ptr[h.n] = (const char*)L.qzeros; h.bytes[h.n++] = qz; }
-  }
-  g_hint = h;
-  return B200Q_OK;
+  return B200Q_ERR_UNSUPPORTED;                             // only the integer-path decode kernel carries the hand-off
 }
 
 int b200q_dequant(const b200q_layer* layer, void* w_out, b200q_stream_t stream) {
@@ -503,7 +471,6 @@ int b200q_debug_set_option(const char* name, double value) {
   else if (n == "im_depth") gemv_imma_set_option(2, (int)value);
   else if (n == "im_tpc") gemv_imma_set_option(3, (int)value);
   else if (n == "im_target") gemv_imma_set_option(4, (int)value);
-  else if (n == "im_prefetch") gemv_imma_set_option(5, (int)value);
   else if (n == "sync_flags") g_sync_flags = (int)value;
   else return B200Q_ERR_UNSUPPORTED;
   return B200Q_OK;

@@ -177,6 +177,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   const int tok0 = blockIdx.y * TT;
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
+  if (tid == 0) TC_STAMP(p.kblocks, 0);                                                        // kernel entry
   if (tid == 0) {
     for (int s = 0; s < kNSXMax; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }   // empty_x: unused
     for (int s = 0; s < kNSWMax; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], kDqWarps); }
@@ -192,6 +193,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   __syncthreads();                         // barriers initialised, TMEM allocated: the TMA producers start right away
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (tid == 0) TC_STAMP(p.kblocks, 1);                                                        // barriers + TMEM ready
   if (warp < kDqWarps * kDqPar) {
     // group tables for this CTA's 128 columns (all groups): only the dequant warps need them, so their load
     // latency overlaps the first TMA round trips instead of preceding them
@@ -216,6 +218,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       }
     }
     asm volatile("bar.sync 8, %0;" ::"n"(kDqWarps * kDqPar * 32) : "memory");
+    if (tid == 0) TC_STAMP(p.kblocks, 2);                                                      // group tables in shared memory
   }
 
   constexpr int P = 32 / BITS;                     // k values per packed word
@@ -387,6 +390,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     }
     // ---- epilogue: TMEM -> registers -> fp16 -> shared (transpose) -> 16-byte coalesced stores ----
     ok = __all_sync(0xffffffffu, ok && mbar_wait_bounded(acc_full, 0, p.err, 6));
+    if (tid == 0) TC_STAMP(p.kblocks, 3);                                                      // accumulators complete
     tc_fence_after();
     const float bias = (p.L.bias && (n0 + n) < p.L.N) ? __half2float(__ldg(p.L.bias + n0 + n)) : 0.f;
     __half* stg = reinterpret_cast<__half*>(xst) + (size_t)eidx * 32 * (kBN + 8);     // [32 tok][128+8 n], X stages are free now
@@ -423,6 +427,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     tc_fence_before();
   }
   __syncthreads();
+  if (tid == 0) TC_STAMP(p.kblocks, 4);                                                        // epilogue stored
   if (warp == kWAlloc) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");

@@ -43,7 +43,8 @@ __device__ __forceinline__ void imma_16832(int (&d)[4], uint32_t a0, uint32_t a1
 // Activation digits in shared memory, per 32-k sub-step: [column c < 4 MTOK][t = 0..3][8 B] -- the B fragment (b0, b1) of
 // lane (g = c, t): bytes 0..3 = digit at k = 8t + {0,2,4,6}, bytes 4..7 = k = 8t + {1,3,5,7} (the order the unpack yields).
 // Column 4m + d holds digit d (most significant first) of token m; column 4m + 3 is absent (lanes read a zero pad).
-template <int MTOK, int D>
+// PEER: the cross-GPU hand-off (counter wait / post, tagged activations) is compiled in; the single-GPU instantiation carries none of it.
+template <int MTOK, int D, bool PEER>
 __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_constant__ StParams p) {
   extern __shared__ __align__(128) char smem[];
   using T = RpGptq<4>;                                                   // table_entries8: (scale, zero) decode of the K-packed layout
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
   const uint32_t* src = L.qw + ((size_t)(s_begin * 8) + (lane >> 4)) * (size_t)pitch + n0 + 4 * (lane & 15);
   bool pc = 4 * (lane & 15) < min(NT, L.N - n0);
   int irem = nsw, itiles = (nsw > 0) ? nt : 0;
-  auto issue = [&](uint32_t slot_wr, bool in_loop) {
+  auto issue = [&](uint32_t slot_wr) {
     if (itiles > 0) {
       if (pc) {
         const uint32_t* s1 = src + 2 * pitch;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
       src += 8 * pitch;
       if (--irem == 0) {                                                                     // next tile, back to this warp's first k
         irem = nsw;
-        if (--itiles == 0 && in_loop) st_prefetch_next(p, warp, lane);                       // own last load is out: start the next layer's stream
+        --itiles;
         src += NT - (ptrdiff_t)((size_t)nsw * 8 * (size_t)pitch);
         pc = 4 * (lane & 15) < L.N - (n0 + (nt - itiles) * NT);
       }
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
     cp_async_commit();
   };
 #pragma unroll 1
-  for (int d = 0; d < D; ++d) issue(wr_ + d * kIStepBytes, false);
+  for (int d = 0; d < D; ++d) issue(wr_ + d * kIStepBytes);
 
   // (scale, zero) table of the CTA's k-slice: [tile][group][NT] float2
   {
@@ -151,14 +152,12 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
   // ---- activations: wait for the upstream kernel, then split this warp's k-range into digits ----
   // parts: <= 128 k (4 sub-steps of 32 k), never across a group boundary; part table (per warp): {2^-E, sum(x)} per token
   pdl_wait();
-  if (p.sync.n_peers > 1) ST_STAMP(3);                                   // local upstream done; stamp 2 follows the peers' posts
-  st_sync_wait(p, lane);
+  if (PEER) {
+    ST_STAMP(3);                                                         // local upstream done; stamp 2 follows the peers' posts
+    st_sync_wait(p, lane);
+  }
   ST_STAMP(2);
-  // every CTA of this launch has sent its first D loads and the upstream layer is finished: a warp with nothing left to
-  // request starts the next layer's HBM -> L2 stream now, the others when their last load goes out (never earlier: the
-  // memory system serves requests roughly in order, and a prefetch queued ahead of demand loads delays them)
-  if (itiles == 0) st_prefetch_next(p, warp, lane);
-  const uint32_t xtag = p.sync.x_tagged ? st_step_tag(p, p.sync.x_seq) : 0u;
+  const uint32_t xtag = (PEER && p.sync.x_tagged) ? st_step_tag(p, p.sync.x_seq) : 0u;
   char* xq = smem + p.off_x + (size_t)(s_begin - cta_s0) * (2 * XQ_SUB);   // this warp's digit sub-steps
   float2* part = reinterpret_cast<float2*>(smem + p.off_part) + (size_t)warp * (p.part_cap * MTOK);
   const int part_sub = min(4, p.group >> 5);                             // sub-steps per full part (2 or 4: group >= 64)
@@ -173,7 +172,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
         float xv[4] = {0.f, 0.f, 0.f, 0.f};
         if (4 * lane < len) {
           const size_t xo = (size_t)m * p.ldx + (size_t)ks * 32 + 4 * lane;
-          const uint2 raw = p.sync.x_tagged ? st_load_tagged4(p, reinterpret_cast<const uint32_t*>(p.x) + xo, xtag)
+          const uint2 raw = (PEER && p.sync.x_tagged) ? st_load_tagged4(p, reinterpret_cast<const uint32_t*>(p.x) + xo, xtag)
                                             : *reinterpret_cast<const uint2*>(p.x + xo);
           const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
           xv[0] = __low2float(h01); xv[1] = __high2float(h01); xv[2] = __low2float(h23); xv[3] = __high2float(h23);
@@ -281,7 +280,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
       imma_16832(acc[3], wb.z & NIB, wb.w & NIB, (wb.z >> 4) & NIB, (wb.w >> 4) & NIB, xb.x, xb.y);
     }
     __syncwarp();                                                        // every lane has read the slot
-    issue(wr_ + so, true);
+    issue(wr_ + so);
     ++kcur;
     --crem;
     if (--pleft == 0 || crem == 0) {                                     // part and / or tile boundary (warp-uniform)
@@ -314,7 +313,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
     for (int idx = lane; idx < nt * NT * ms; idx += 32) redw[idx] = 0.f;
   }
   ST_STAMP(4);
-  st_reduce_store<MC, 256>(p, SL, red, rbuf, rbar, nt * NT, ncols_cta, n0, cs, rank, tid);
+  st_reduce_store<MC, 256, PEER>(p, SL, red, rbuf, rbar, nt * NT, ncols_cta, n0, cs, rank, tid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -324,7 +323,7 @@ struct ImPlan {
   int off_x, off_tab, off_red, off_rbuf, off_rbar, off_ring, off_zpad, off_part, off_mbar, smem_bytes;
 };
 
-static int g_im_on = 1, g_im_cluster = 0, g_im_depth = 0, g_im_tpc = 0, g_im_target = 296, g_im_prefetch = 0;
+static int g_im_on = 1, g_im_cluster = 0, g_im_depth = 0, g_im_tpc = 0, g_im_target = 296;
 static unsigned long long* g_im_dbg = nullptr;
 static size_t g_im_dbg_cap = 0, g_im_dbg_pos = 0;
 void gemv_imma_set_option(int which, int value) {
@@ -333,7 +332,6 @@ void gemv_imma_set_option(int which, int value) {
   else if (which == 2) g_im_depth = value;
   else if (which == 3) g_im_tpc = value;
   else if (which == 4) g_im_target = value;
-  else if (which == 5) g_im_prefetch = value;
 }
 void gemv_imma_set_debug(unsigned long long* buf, size_t cap_entries) { g_im_dbg = buf; g_im_dbg_cap = cap_entries; g_im_dbg_pos = 0; }
 
@@ -426,15 +424,15 @@ bool gemv_imma_describe(const LinearArgs* a, int n, int out[6]) {
   return true;
 }
 
-template <int MTOK, int D>
+template <int MTOK, int D, bool PEER>
 static cudaError_t im_launch_k(const StParams& p, const ImPlan& pl, cudaStream_t st) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(gemv_imma_kernel<MTOK, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemv_imma_kernel<MTOK, D, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
     if (e != cudaSuccess) return e;
-    if (decode_carveout_max()) cudaFuncSetAttribute(gemv_imma_kernel<MTOK, D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (decode_carveout_max()) cudaFuncSetAttribute(gemv_imma_kernel<MTOK, D, PEER>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     attr_done[dev & 63] = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -452,7 +450,7 @@ static cudaError_t im_launch_k(const StParams& p, const ImPlan& pl, cudaStream_t
   cfg.attrs = at;
   cfg.numAttrs = 2;
   count_launch();
-  return cudaLaunchKernelEx(&cfg, gemv_imma_kernel<MTOK, D>, p);
+  return cudaLaunchKernelEx(&cfg, gemv_imma_kernel<MTOK, D, PEER>, p);
 }
 
 int gemv_imma_posts(const LinearArgs* a, int n) {
@@ -488,24 +486,17 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers, c
   p.x_stride = 0; p.red_stride = pl.tpc * kINT * a[0].M;
   p.off_x = pl.off_x; p.off_tab = pl.off_tab; p.off_red = pl.off_red; p.off_rbuf = pl.off_rbuf; p.off_rbar = pl.off_rbar;
   p.off_ring = pl.off_ring; p.off_zpad = pl.off_zpad; p.off_part = pl.off_part; p.off_mbar = pl.off_mbar;
-  // next layers on this stream (one-shot hint): each of this launch's warps requests 1 / (8 ctas) of every range
-  const PrefetchHint h = take_prefetch_hint();
-  p.n_pf = 0;
-  for (int i = 0; i < h.n && g_im_prefetch; ++i) {
-    if (!h.ptr[i] || h.bytes[i] < 16 || h.bytes[i] >= (1ull << 32) || ((uintptr_t)h.ptr[i] & 15)) continue;
-    const uint32_t bytes = (uint32_t)(h.bytes[i] & ~(size_t)15), units = (uint32_t)pl.ctas * kWarps;
-    p.pf_ptr[p.n_pf] = h.ptr[i];
-    p.pf_bytes[p.n_pf] = bytes;
-    p.pf_chunk[p.n_pf] = ((bytes + units - 1) / units + 127u) & ~127u;
-    ++p.n_pf;
-  }
   p.dbg = nullptr;
   if (g_im_dbg) {
     const size_t need = (size_t)pl.ctas * 8;
     if (g_im_dbg_pos + need <= g_im_dbg_cap) { p.dbg = g_im_dbg + g_im_dbg_pos; g_im_dbg_pos += need; }
   }
-  if (p.M == 1) return pl.depth == 2 ? im_launch_k<1, 2>(p, pl, a[0].stream) : im_launch_k<1, 4>(p, pl, a[0].stream);
-  return pl.depth == 2 ? im_launch_k<2, 2>(p, pl, a[0].stream) : im_launch_k<2, 4>(p, pl, a[0].stream);
+  if (sync && (sync->n_peers > 1 || sync->x_tagged || sync->y_tagged)) {
+    if (p.M == 1) return pl.depth == 2 ? im_launch_k<1, 2, true>(p, pl, a[0].stream) : im_launch_k<1, 4, true>(p, pl, a[0].stream);
+    return pl.depth == 2 ? im_launch_k<2, 2, true>(p, pl, a[0].stream) : im_launch_k<2, 4, true>(p, pl, a[0].stream);
+  }
+  if (p.M == 1) return pl.depth == 2 ? im_launch_k<1, 2, false>(p, pl, a[0].stream) : im_launch_k<1, 4, false>(p, pl, a[0].stream);
+  return pl.depth == 2 ? im_launch_k<2, 2, false>(p, pl, a[0].stream) : im_launch_k<2, 4, false>(p, pl, a[0].stream);
 }
 
 }  // namespace b200q

@@ -128,8 +128,6 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_stream_kernel(const __grid
 
   // ---- 2. activations of this warp's k-range (produced by the upstream kernel) ----
   pdl_wait();
-  if (p.sync.n_peers > 1) ST_STAMP(3);                                   // local upstream done; stamp 2 follows the peers' posts
-  st_sync_wait(p, lane);
   ST_STAMP(2);
   {
     const int kw0 = s_begin * T::KSTEP, nv = (nsw * T::KSTEP) >> 3;
@@ -303,8 +301,6 @@ __global__ void __launch_bounds__(kRpThreads, 2) gemv_awq_lean_kernel(const __gr
 
   // ---- activations of this warp's k-range ----
   pdl_wait();
-  if (p.sync.n_peers > 1) ST_STAMP(3);                                   // local upstream done; stamp 2 follows the peers' posts
-  st_sync_wait(p, lane);
   ST_STAMP(2);
   {
     const int kw0 = s_begin * KSTEP, nv = (nsw * KSTEP) >> 3;
@@ -586,12 +582,7 @@ static cudaError_t st_launch_t(const StParams& p, const StPlan& pl, cudaStream_t
   return p.M == 1 ? st_launch_k<T, 1>(p, pl, st) : st_launch_k<T, 2>(p, pl, st);
 }
 
-int gemv_stream_posts(const LinearArgs* a, int n) {
-  StPlan pl;
-  return st_plan(a, n, pl) ? 1 : -1;                       // the last storing CTA posts for the whole launch
-}
-
-cudaError_t launch_gemv_stream(const LinearArgs* a, int n, const PeerOut* peers, const PeerSync* sync) {
+cudaError_t launch_gemv_stream(const LinearArgs* a, int n, const PeerOut* peers) {
   StPlan pl;
   if (!st_plan(a, n, pl)) return cudaErrorInvalidValue;
   const LayerView& L = a[0].L;
@@ -602,15 +593,8 @@ cudaError_t launch_gemv_stream(const LinearArgs* a, int n, const PeerOut* peers,
     StLayer& d = p.layer[i];
     d.qw = a[k].L.qw; d.qz = a[k].L.qz; d.s = a[k].L.s; d.bias = a[k].L.bias; d.N = a[k].L.N;
     d.cta0 = i < n ? pl.cta0[i] : (1 << 30);
-    if (peers) d.out = peers[k]; else { d.out.n = 1; d.out.y[0] = a[k].y; }
+    if (peers && n == 1) d.out = *peers; else { d.out.n = 1; d.out.y[0] = a[k].y; }
     d.ldy = a[k].ldy; d.n_offset = a[k].n_offset;
-  }
-  if (sync) {
-    p.sync = *sync;
-    p.arrive = reinterpret_cast<unsigned int*>(a[0].workspace) + 1000;   // inside the 4 KB counter region every kernel leaves zeroed
-    p.store_ctas = pl.ctas / pl.cluster;
-    p.sync_flags = decode_sync_flags();
-    if (sync->n_peers > 1 && sync->post_slot >= 0 && (!a[0].workspace || a[0].workspace_bytes < kCounterBytes)) return cudaErrorInvalidValue;
   }
   p.layout = L.layout; p.bits = L.bits; p.group = L.group; p.K = L.K; p.G = L.G; p.zero_bias = L.zero_bias;
   p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M;

@@ -29,30 +29,12 @@ struct StParams {
   int red_stride;                                // floats between two warps' partial-sum vectors
   int off_x, off_tab, off_red, off_rbuf, off_rbar, off_ring, off_zpad, off_part, off_mbar;
   unsigned long long* dbg;                       // optional per-CTA phase stamps (diagnostic)
-  // L2 prefetch of the layer(s) that will run next on this stream (b200q_prefetch_hint): byte ranges (16-byte
-  // aligned, multiples of 16 bytes) and the share of each range one warp of this launch requests
-  PeerSync sync;                                 // cross-GPU hand-off (n_peers == 0: none)
+  // cross-GPU hand-off (PEER instantiations only; n_peers == 0: none)
+  PeerSync sync;
   unsigned int* arrive;                          // local arrival counter of the storing CTAs (workspace, left zeroed)
   int store_ctas;
-  int sync_flags;                                // diagnostic (B200Q_SYNC_FLAGS): 1 no remote stores, 2 no wait, 4 no post, 8 back-off polling, 16 one poller per CTA
-  const char* pf_ptr[kMaxPrefetch];
-  uint32_t pf_bytes[kMaxPrefetch], pf_chunk[kMaxPrefetch];
-  int n_pf;
+  int sync_flags;                                // diagnostic (B200Q_SYNC_FLAGS): 2 no wait, 4 no post, 8 back-off polling, 16 one poller per CTA
 };
-
-// One warp's share of the next layers' packed bytes, requested from HBM into L2 with cp.async.bulk.prefetch.L2: issued
-// when the warp has sent its own last weight load, so the memory system never idles across the kernel boundary
-// (reduction, store, programmatic hand-off and the next launch's prologue all overlap the next layer's stream).
-__device__ __forceinline__ void st_prefetch_next(const StParams& p, int warp, int lane) {
-  if (lane < p.n_pf) {
-    const uint32_t bytes = p.pf_bytes[lane], chunk = p.pf_chunk[lane];
-    const uint32_t off = (blockIdx.x * kWarps + warp) * chunk;
-    if (off < bytes) {
-      const uint32_t len = min(chunk, bytes - off);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr[lane] + off), "r"(len) : "memory");
-    }
-  }
-}
 
 __device__ __forceinline__ unsigned long long st_gtime();
 // Consumer side of the cross-GPU hand-off: x is complete once every peer's storing CTAs of this step have posted.
@@ -159,7 +141,7 @@ __device__ __forceinline__ void cp_async_wait_ring(int depth) {
 // Final reduction shared by the stream kernels: the 8 warps' partial sums (red[warp][ncols_alloc * M], idx = n * M + m)
 // -> one vector per CTA; CTAs of a cluster send theirs to rank 0 through st.async (fixed order); rank 0 adds bias,
 // rounds to fp16 and stores (to every peer buffer when sharded).  MAXCOLS: columns a CTA may own.
-template <int MC, int MAXCOLS>
+template <int MC, int MAXCOLS, bool PEER = false>
 __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer& SL, const float* red, float* rbuf, uint64_t* rbar,
                                                 int ncols_alloc, int ncols_cta, int n0, int cs, int rank, int tid) {
   __syncthreads();
@@ -197,7 +179,7 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
         for (int q = 0; q < cs - 1; ++q) v[r] += rbuf[(size_t)q * totalv + idx];
     }
   }
-  const uint32_t ytag = p.sync.y_tagged ? st_step_tag(p, p.sync.y_seq) << 16 : 0u;
+  const uint32_t ytag = (PEER && p.sync.y_tagged) ? st_step_tag(p, p.sync.y_seq) << 16 : 0u;
 #pragma unroll
   for (int r = 0; r < NV; ++r) {
     const int idx = tid + r * kRpThreads;
@@ -206,17 +188,16 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
       float o = v[r];
       if (SL.bias) o += __half2float(__ldg(SL.bias + n0 + n));
       const __half h = __float2half_rn(o);
-      if (p.sync.y_tagged) {                                // one 4-byte store per element and replica: value and tag land together
+      if (PEER && p.sync.y_tagged) {                        // one 4-byte store per element and replica: value and tag land together
         const uint32_t w = ytag | (uint32_t)__half_as_ushort(h);
         for (int q = 0; q < SL.out.n; ++q)
           reinterpret_cast<uint32_t*>(SL.out.y[q])[(size_t)m * SL.ldy + SL.n_offset + n0 + n] = w;
         continue;
       }
-      for (int q = 0; q < SL.out.n; ++q)
-        if (!(p.sync_flags & 1) || q == p.sync.self) SL.out.y[q][(size_t)m * SL.ldy + SL.n_offset + n0 + n] = h;
+      for (int q = 0; q < SL.out.n; ++q) SL.out.y[q][(size_t)m * SL.ldy + SL.n_offset + n0 + n] = h;
     }
   }
-  st_sync_post(p, tid);
+  if (PEER) st_sync_post(p, tid);
   ST_STAMP(6);
 }
 

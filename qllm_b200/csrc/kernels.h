@@ -48,14 +48,6 @@ struct PeerSync {
   unsigned int tag_stride, y_seq, x_seq;
 };
 
-// api.cu: one-shot hint (b200q_prefetch_hint) consumed by the next decode launch of the calling thread
-static constexpr int kMaxPrefetch = 9;
-struct PrefetchHint {
-  const char* ptr[kMaxPrefetch];
-  size_t bytes[kMaxPrefetch];
-  int n;
-};
-PrefetchHint take_prefetch_hint();
 int decode_sync_flags();        // diagnostic switch (B200Q_SYNC_FLAGS / "sync_flags")
 
 // unpack.cu
@@ -87,8 +79,7 @@ void gemv_rp_set_debug(unsigned long long* buf, size_t cap_entries);
 // gemv_stream.cu : streaming decode path (per-warp cp.async rings, sibling layers fused in one launch), M <= 8
 static constexpr int kMaxGroupLayers = 3;
 bool gemv_stream_supported(const LinearArgs* a, int n);
-cudaError_t launch_gemv_stream(const LinearArgs* a, int n, const PeerOut* peers, const PeerSync* sync = nullptr);   // peers: NULL or one per layer
-int gemv_stream_posts(const LinearArgs* a, int n);    // storing CTAs of the launch (= posts per peer), -1 if unsupported
+cudaError_t launch_gemv_stream(const LinearArgs* a, int n, const PeerOut* peers);
 bool gemv_stream_describe(const LinearArgs* a, int n, int out[6]);
 void gemv_stream_set_option(int which, int value);
 void gemv_stream_set_debug(unsigned long long* buf, size_t cap_entries);

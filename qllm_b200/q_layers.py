@@ -133,15 +133,6 @@ class _B200QuantLinearBase(nn.Module):
             return self._gemm_descriptor()
         return self._descriptor()
 
-    def _hint_next(self, M):
-        """Decode chains (link_decode_chain): tell the engine which layers run after this call, so that this call's
-        kernel starts their HBM -> L2 stream when its own last load is out (b200q_prefetch_hint)."""
-        nxt = getattr(self, "_next_call", None)
-        if nxt and M <= 2:
-            descs = [l._decode_descriptor(M) for l in nxt]
-            arr = (ctypes.POINTER(Layer) * len(descs))(*[ctypes.pointer(d) for d in descs])
-            check(lib.b200q_prefetch_hint(arr, len(descs)), "b200q_prefetch_hint")
-
     # -- forward ------------------------------------------------------------------------------
     def __call__(self, x):
         grp = getattr(self, "_sibling_group", None)
@@ -166,7 +157,6 @@ class _B200QuantLinearBase(nn.Module):
                 desc = self._decode_descriptor(M)
             need = lib.b200q_workspace_bytes(ctypes.byref(desc), M)
             ws = _workspace(x.device, need)
-            self._hint_next(M)
             st = lib.b200q_linear(ctypes.byref(desc), x2.data_ptr(), M, x2.stride(0), y.data_ptr(), y.stride(0),
                                   ws.data_ptr(), ws.numel(), torch.cuda.current_stream(x.device).cuda_stream)
             check(st, type(self).__name__ + ".forward")
@@ -411,7 +401,6 @@ def linear_group(layers, x):
     ld = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
     need = max(lib.b200q_workspace_bytes(ctypes.byref(d), M) for d in descs)
     ws = _workspace(x.device, need)
-    layers[0]._hint_next(M)
     check(lib.b200q_linear_group(arr, n, x2.data_ptr(), M, x2.stride(0), yp, ld, ws.data_ptr(), ws.numel(),
                                  torch.cuda.current_stream(x.device).cuda_stream), "b200q_linear_group")
     outs = []
@@ -467,29 +456,6 @@ def fuse_siblings(model, sibling_sets=SIBLING_SETS):
                 m._sibling_group = grp
             n += 1
     return n
-
-
-def link_decode_chain(model_or_calls):
-    """Record the order in which a model's QuantLinears run during decode, so that every call can hand the engine the
-    layers that follow it (b200q_prefetch_hint: their packed bytes stream from HBM into L2 across the kernel
-    boundary).  `model_or_calls`: an nn.Module -- order = module registration order, which is the execution order of
-    the HF Llama/Mixtral blocks (q,k,v,o, gate,up,down); call after fuse_siblings so a sibling set counts as one
-    call -- or an explicit list of calls, each a list of layers.  Returns the number of links.  A wrong order only
-    costs performance (a useless prefetch), never correctness."""
-    if isinstance(model_or_calls, nn.Module):
-        calls, seen = [], set()
-        for m in model_or_calls.modules():
-            if isinstance(m, _B200QuantLinearBase) and id(m) not in seen:
-                grp = getattr(m, "_sibling_group", None)
-                layers = list(grp.layers) if grp is not None else [m]
-                seen.update(id(l) for l in layers)
-                calls.append(layers)
-    else:
-        calls = [list(c) for c in model_or_calls]
-    for a, b in zip(calls, calls[1:]):
-        for l in a:
-            l._next_call = b[:3]
-    return max(0, len(calls) - 1)
 
 
 def select_quant_linear(pack_mode: str, wbits: int, quant_method: str):

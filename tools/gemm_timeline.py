@@ -14,8 +14,11 @@ qllm_b200.lib.b200q_debug_set_timeline(buf.data_ptr(), buf.numel() * 8)
 l(x); torch.cuda.synchronize()
 qllm_b200.lib.b200q_debug_set_timeline(None, 0)
 nkb = K // 64
-t = buf.cpu().numpy().reshape(-1, 8)[:nkb].astype(np.float64)
+tall = buf.cpu().numpy().reshape(-1, 8).astype(np.float64)
+t, ends = tall[:nkb], tall[nkb]
 t0 = t[t > 0].min()
+print("whole-kernel stamps of CTA (0,0), cycles relative to the first k-block stamp: entry %.0f | barriers+TMEM %.0f | tables %.0f | "
+      "accumulators complete %.0f | epilogue stored %.0f" % tuple(ends[j] - t0 for j in range(5)))
 names = ["dq:w_landed", "dq:alu_done", "dq:a_free", "dq:signalled", "mma:x_landed", "mma:a_landed", "mma:issued", "mma:committed"]
 print("kb  " + "  ".join(f"{n:>13s}" for n in names) + "   (SM cycles since first stamp)")
 for kb in list(range(0, 16)) + list(range(nkb // 2, nkb // 2 + 8)) + list(range(nkb - 6, nkb)):

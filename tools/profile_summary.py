@@ -30,8 +30,11 @@ with open(out, "w") as f:
                 f.write(f"{k:75s} {r[j]:>18s} {units[j]}\n")
         try:
             rd, wr = float(r[hdr.index('dram__bytes_read.sum')].replace(',', '')), float(r[hdr.index('dram__bytes_write.sum')].replace(',', ''))
-            un = units[hdr.index('dram__bytes_read.sum')]
-            mult = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(un, 1.0)
+            UM = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+            # ncu's raw page scales every column by the unit that suits its first row: convert both columns to bytes
+            rd *= UM.get(units[hdr.index('dram__bytes_read.sum')], 1.0)
+            wr *= UM.get(units[hdr.index('dram__bytes_write.sum')], 1.0)
+            mult = 1.0
             dur = float(r[hdr.index('gpu__time_duration.sum')].replace(',', ''))
             du = units[hdr.index('gpu__time_duration.sum')]
             dmult = {"us": 1e-6, "ns": 1e-9, "ms": 1e-3}.get(du, 1e-6)
