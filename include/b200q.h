@@ -70,6 +70,8 @@ typedef struct b200q_layer {
   const void* scales;  /* fp16 [G,N] (MARLIN: in the reference's permuted order) */
   const int32_t* g_idx;/* int32 [K] act-order group map, or NULL for k / group_size (GPTQ only) */
   const void* bias;    /* fp16 [N] or NULL */
+  const int32_t* x_perm; /* NULL, or int32 [K]: packed row j multiplies x[:, x_perm[j]] -- the run-time half of the
+                          act-order re-layout (b200q_repack_actorder); GPTQ/HQQ layouts with g_idx == NULL only */
 } b200q_layer;
 
 /*
@@ -206,6 +208,18 @@ int b200q_unpack(const b200q_layer* layer, int32_t* q_out, int32_t* z_out, b200q
  * the fp16 dequant/requant in the middle.
  */
 int b200q_repack_gptq4(const b200q_layer* layer, void* qweight_out, void* qzeros_out, void* scales_out, b200q_stream_t stream);
+
+/*
+ * Act-order (desc_act) checkpoints: qweight_out[K*b/32, N] = the layer's packed rows re-ordered so that packed row j
+ * holds original row perm[j] (exact integer re-layout, bits 2/4/8).  With perm = a stable argsort of g_idx the groups
+ * become contiguous, so {qweight_out, the ORIGINAL qzeros and scales, g_idx = NULL, x_perm = perm} is an ordinary
+ * grouped layer whose activations are gathered through x_perm: inside the x-load stage of the integer-path decode
+ * kernel (M <= 2), by a small gather pass into the workspace ahead of every other kernel (b200q_workspace_bytes accounts
+ * for it).  Replaces the per-element g_idx look-ups of Gemv_g / DequantizeAndUnpackWeight*_g
+ * (csrc/ort_cuda/dq_gemv.cu:459-541, :189-273).  Requires every group to own exactly group_size rows (true for GPTQ
+ * act-order, static or not: gptq.py:230-237); other g_idx maps stay on the generic kernel.
+ */
+int b200q_repack_actorder(const b200q_layer* layer, const int32_t* perm, void* qweight_out, b200q_stream_t stream);
 
 /* Bytes of zero-initialised workspace b200q_linear/gemv/gemm need for this layer at batch M. */
 size_t b200q_workspace_bytes(const b200q_layer* layer, int64_t M);

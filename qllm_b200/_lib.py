@@ -16,7 +16,7 @@ class Layer(ctypes.Structure):
     _fields_ = [("layout", ctypes.c_int32), ("bits", ctypes.c_int32), ("group_size", ctypes.c_int32),
                 ("K", ctypes.c_int32), ("N", ctypes.c_int32), ("zero_bias", ctypes.c_int32),
                 ("qweight", ctypes.c_void_p), ("qzeros", ctypes.c_void_p), ("scales", ctypes.c_void_p),
-                ("g_idx", ctypes.c_void_p), ("bias", ctypes.c_void_p)]
+                ("g_idx", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("x_perm", ctypes.c_void_p)]
 
 
 class PeerSync(ctypes.Structure):
@@ -30,7 +30,7 @@ class PeerSync(ctypes.Structure):
 EXPORTS = ["b200q_linear", "b200q_linear_group", "b200q_gemv", "b200q_gemm", "b200q_linear_sharded", "b200q_dequant", "b200q_unpack",
            "b200q_workspace_bytes", "b200q_gemv_max_m", "b200q_select_kernel", "b200q_launch_count",
            "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4", "b200q_debug_decode_plan", "b200q_debug_set_option", "b200q_linear_group_sharded", "b200q_sharded_posts",
-           "b200q_peer_epoch_advance", "b200q_peer_wait", "b200q_peer_untag"]
+           "b200q_peer_epoch_advance", "b200q_peer_wait", "b200q_peer_untag", "b200q_repack_actorder"]
 
 
 def _load():
@@ -74,6 +74,8 @@ def _load():
     lib.b200q_dequant.restype = ctypes.c_int
     lib.b200q_unpack.argtypes = [LP, P, P, P]
     lib.b200q_unpack.restype = ctypes.c_int
+    lib.b200q_repack_actorder.argtypes = [LP, P, P, P]
+    lib.b200q_repack_actorder.restype = ctypes.c_int
     lib.b200q_repack_gptq4.argtypes = [LP, P, P, P, P]
     lib.b200q_repack_gptq4.restype = ctypes.c_int
     lib.b200q_workspace_bytes.argtypes = [LP, I64]

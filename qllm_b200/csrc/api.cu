@@ -58,6 +58,10 @@ static int validate(const b200q_layer* L) {
       return B200Q_ERR_UNSUPPORTED;
   }
   if (((uintptr_t)L->qweight & 3) || ((uintptr_t)L->scales & 1)) return B200Q_ERR_ALIGNMENT;
+  if (L->x_perm) {
+    if ((L->layout != B200Q_LAYOUT_GPTQ && L->layout != B200Q_LAYOUT_HQQ) || L->g_idx) return B200Q_ERR_UNSUPPORTED;
+    if (((uintptr_t)L->x_perm & 15) || (L->K & 1)) return B200Q_ERR_ALIGNMENT;
+  }
   return B200Q_OK;
 }
 
@@ -147,6 +151,10 @@ static size_t workspace_for(const LayerView& V, int64_t M) {
   if (g > w) w = g;
   return (w + 255) & ~(size_t)255;
 }
+// act-order re-layout: the gathered activations x[:, x_perm] sit behind the kernels' own scratch (no zero contract there)
+static size_t gather_bytes(const LayerView& V, int64_t M) {
+  return V.x_perm ? (((size_t)M * (size_t)V.K * 2 + 255) & ~(size_t)255) : 0;
+}
 
 static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, const PeerOut* peers, void* y,
                int64_t ldy, int64_t n_offset, void* ws, size_t ws_bytes, b200q_stream_t stream, int force) {
@@ -154,12 +162,25 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   if (v != B200Q_OK) return v;
   if (!x || (!y && !peers)) return B200Q_ERR_NULL;
   if (M < 1 || ldx < layer->K || ldy < n_offset + layer->N) return B200Q_ERR_SHAPE;
-  const LayerView V = make_view(layer);
-  const int kern = select(V, M, (const __half*)x, ldx, force);
-  if (kern < 0) return kern;
-  const size_t need = workspace_for(V, M);
+  LayerView V = make_view(layer);
+  const size_t base = workspace_for(V, M), need = base + gather_bytes(V, M);
   if (need > 0 && (!ws || ws_bytes < need)) return B200Q_ERR_WORKSPACE;
   if (ws && ((uintptr_t)ws & 15)) return B200Q_ERR_ALIGNMENT;
+  if (V.x_perm) {
+    // the integer-path decode kernel gathers x through x_perm in its own load stage; everything else reads a gathered copy
+    LinearArgs probe = {};
+    probe.L = V; probe.x = (const __half*)x; probe.ldx = ldx; probe.M = (int)M;
+    const bool folded = force != KERNEL_GEMM_TC && M <= kGemvMaxM && g_use_stream && (gemv_variant(), true) && gemv_imma_supported(&probe, 1);
+    if (!folded) {
+      if (M > 0x7fffffff / 2) return B200Q_ERR_SHAPE;
+      __half* xg = (__half*)((char*)ws + base);
+      const cudaError_t e = launch_gather_x((const __half*)x, ldx, V.x_perm, xg, (int)M, V.K, (cudaStream_t)stream);
+      if (e != cudaSuccess) return cuda_status(e);
+      x = xg; ldx = V.K; V.x_perm = nullptr;
+    }
+  }
+  const int kern = select(V, M, (const __half*)x, ldx, force);
+  if (kern < 0) return kern;
   LinearArgs a;
   a.L = V; a.x = (const __half*)x; a.ldx = ldx; a.M = (int)M; a.y = (__half*)y; a.ldy = ldy; a.n_offset = n_offset;
   a.workspace = ws; a.workspace_bytes = ws_bytes; a.stream = (cudaStream_t)stream;
@@ -391,6 +412,15 @@ int b200q_linear_group_sharded(const b200q_layer* const* layers, int32_t n_layer
   return B200Q_ERR_UNSUPPORTED;                             // only the integer-path decode kernel carries the hand-off
 }
 
+int b200q_repack_actorder(const b200q_layer* layer, const int32_t* perm, void* qweight_out, b200q_stream_t stream) {
+  const int v = validate(layer);
+  if (v != B200Q_OK) return v;
+  if (!perm || !qweight_out) return B200Q_ERR_NULL;
+  if (layer->layout != B200Q_LAYOUT_GPTQ && layer->layout != B200Q_LAYOUT_HQQ) return B200Q_ERR_UNSUPPORTED;
+  if (layer->bits != 2 && layer->bits != 4 && layer->bits != 8) return B200Q_ERR_UNSUPPORTED;
+  return cuda_status(launch_repack_actorder(make_view(layer), perm, (uint32_t*)qweight_out, (cudaStream_t)stream));
+}
+
 int b200q_dequant(const b200q_layer* layer, void* w_out, b200q_stream_t stream) {
   const int v = validate(layer);
   if (v != B200Q_OK) return v;
@@ -418,7 +448,8 @@ int b200q_repack_gptq4(const b200q_layer* layer, void* qweight_out, void* qzeros
 
 size_t b200q_workspace_bytes(const b200q_layer* layer, int64_t M) {
   if (validate(layer) != B200Q_OK || M < 1) return 0;
-  return workspace_for(make_view(layer), M);
+  const LayerView V = make_view(layer);
+  return workspace_for(V, M) + gather_bytes(V, M);
 }
 
 int b200q_gemv_max_m(void) { return kGemvMaxM; }
@@ -427,7 +458,14 @@ int b200q_select_kernel(const b200q_layer* layer, int64_t M) {
   const int v = validate(layer);
   if (v != B200Q_OK) return v;
   // alignment-independent answer: assume a 16-byte aligned, densely strided x
-  return select(make_view(layer), M, (const __half*)nullptr, layer->K, 0);
+  LayerView V = make_view(layer);
+  if (V.x_perm) {                          // as in run(): only the integer-path decode kernel reads through x_perm itself
+    LinearArgs probe = {};
+    probe.L = V; probe.ldx = layer->K; probe.M = (int)(M < kGemvMaxM ? M : kGemvMaxM);
+    gemv_variant();
+    if (!(M <= kGemvMaxM && g_use_stream && gemv_imma_supported(&probe, 1))) V.x_perm = nullptr;
+  }
+  return select(V, M, (const __half*)nullptr, layer->K, 0);
 }
 
 uint64_t b200q_launch_count(void) { return g_launches.load(); }

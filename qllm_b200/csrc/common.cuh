@@ -17,6 +17,7 @@ struct LayerView {
   const __half* __restrict__ s;
   const int* __restrict__ g_idx;     // nullptr -> k / group
   const __half* __restrict__ bias;
+  const int* __restrict__ x_perm;    // nullptr, or [K]: packed row j multiplies x[:, x_perm[j]] (act-order re-layout)
 };
 
 __host__ inline LayerView make_view(const b200q_layer* L) {
@@ -24,7 +25,7 @@ __host__ inline LayerView make_view(const b200q_layer* L) {
   v.layout = L->layout; v.bits = L->bits; v.group = L->group_size; v.K = L->K; v.N = L->N;
   v.G = (L->K + L->group_size - 1) / L->group_size; v.zero_bias = L->zero_bias;
   v.qw = (const uint32_t*)L->qweight; v.qz = L->qzeros; v.s = (const __half*)L->scales;
-  v.g_idx = L->g_idx; v.bias = (const __half*)L->bias;
+  v.g_idx = L->g_idx; v.bias = (const __half*)L->bias; v.x_perm = L->x_perm;
   return v;
 }
 

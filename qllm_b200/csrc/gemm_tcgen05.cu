@@ -467,7 +467,7 @@ void gemm_tc_set_tt256_min_m(int m) { g_tc_tt256_min_m = m; }
 static int pick_tt(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : (M >= g_tc_tt256_min_m ? 256 : 128)); }
 
 bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t ldx) {
-  if (!(L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) || L.g_idx) return false;
+  if (!(L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) || L.g_idx || L.x_perm) return false;
   if (L.bits != 2 && L.bits != 4 && L.bits != 8) return false;
   if (L.group % (32 / L.bits) != 0) return false;                         // a packed word never straddles two groups
   if (L.K % kBK != 0 || L.N % 8 != 0 || L.group % 8 != 0 || L.K % L.group != 0) return false;

@@ -364,7 +364,7 @@ void gemv_fma_set_max_m(int m) { g_fma_max_m = m; }
 
 static bool fma_plan(const LayerView& L, int M, FmaPlan& pl) {
   pl.kind = 0;
-  if (M < 1 || M > 2 || M > g_fma_max_m || L.g_idx != nullptr || L.bits != 4) return false;
+  if (M < 1 || M > 2 || M > g_fma_max_m || L.g_idx != nullptr || L.x_perm != nullptr || L.bits != 4) return false;
   if (L.layout == B200Q_LAYOUT_GPTQ) { pl.kind = 1; pl.NT = FGptq4::NT; pl.KROW = 8; pl.MAXLD = FGptq4::MAXLD; pl.FLUSH = 2; pl.XDUP = 1; pl.RPL = 1; }
   else if (L.layout == B200Q_LAYOUT_AWQ_GEMM) { pl.kind = 2; pl.NT = FAwq4::NT; pl.KROW = 1; pl.MAXLD = FAwq4::MAXLD; pl.FLUSH = 8; pl.XDUP = 2; pl.RPL = 2; }
   else return false;

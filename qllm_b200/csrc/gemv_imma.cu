@@ -172,8 +172,16 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
         float xv[4] = {0.f, 0.f, 0.f, 0.f};
         if (4 * lane < len) {
           const size_t xo = (size_t)m * p.ldx + (size_t)ks * 32 + 4 * lane;
-          const uint2 raw = (PEER && p.sync.x_tagged) ? st_load_tagged4(p, reinterpret_cast<const uint32_t*>(p.x) + xo, xtag)
-                                            : *reinterpret_cast<const uint2*>(p.x + xo);
+          uint2 raw;
+          if (PEER && p.sync.x_tagged) {
+            raw = st_load_tagged4(p, reinterpret_cast<const uint32_t*>(p.x) + xo, xtag);
+          } else if (p.xperm) {                                          // act-order re-layout: packed row j multiplies x[x_perm[j]]
+            const int4 pi = *reinterpret_cast<const int4*>(p.xperm + (size_t)ks * 32 + 4 * lane);
+            const unsigned short* xr = reinterpret_cast<const unsigned short*>(p.x + (size_t)m * p.ldx);
+            raw = make_uint2((uint32_t)xr[pi.x] | ((uint32_t)xr[pi.y] << 16), (uint32_t)xr[pi.z] | ((uint32_t)xr[pi.w] << 16));
+          } else {
+            raw = *reinterpret_cast<const uint2*>(p.x + xo);
+          }
           const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
           xv[0] = __low2float(h01); xv[1] = __high2float(h01); xv[2] = __low2float(h23); xv[3] = __high2float(h23);
         }
@@ -344,7 +352,7 @@ static bool im_plan(const LinearArgs* a, int n, ImPlan& pl) {
   for (int i = 1; i < n; ++i) {
     const LayerView& B = a[i].L;
     if (B.layout != L.layout || B.bits != L.bits || B.group != L.group || B.K != L.K || B.zero_bias != L.zero_bias ||
-        B.g_idx != nullptr || a[i].M != M || a[i].x != a[0].x || a[i].ldx != a[0].ldx)
+        B.g_idx != nullptr || B.x_perm != L.x_perm || a[i].M != M || a[i].x != a[0].x || a[i].ldx != a[0].ldx)
       return false;
   }
   // a step (64 k) lies inside one group; groups are powers of two (count-down bookkeeping by shifts)
@@ -480,7 +488,8 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers, c
     if (sync->n_peers > 1 && sync->post_slot >= 0 && (!a[0].workspace || a[0].workspace_bytes < kCounterBytes)) return cudaErrorInvalidValue;
   }
   p.layout = L.layout; p.bits = L.bits; p.group = L.group; p.K = L.K; p.G = L.G; p.zero_bias = L.zero_bias;
-  p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M;
+  p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M; p.xperm = L.x_perm;
+  if (L.x_perm && sync && sync->x_tagged) return cudaErrorInvalidValue;    // gather through x_perm reads plain fp16 activations
   p.cluster = pl.cluster; p.tpc = pl.tpc; p.depth = pl.depth; p.steps_total = pl.steps_total; p.group_shift = pl.group_shift;
   p.gcap = pl.gcap; p.split_q = pl.split_q; p.split_r = pl.split_r; p.part_cap = pl.part_cap;
   p.x_stride = 0; p.red_stride = pl.tpc * kINT * a[0].M;

@@ -563,7 +563,7 @@ static void fill_traits(Plan& pl) {
 
 static bool make_plan(const LayerView& L, int M, Plan& pl) {
   pl.kind = 0;
-  if (M < 1 || M > kMB || L.g_idx != nullptr) return false;
+  if (M < 1 || M > kMB || L.g_idx != nullptr || L.x_perm != nullptr) return false;
   const bool fz = (L.layout == B200Q_LAYOUT_HQQ);
   if (L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) {
     if (L.bits == 2) { pl.kind = 1; fz ? fill_traits<GptqTraits<2, true>>(pl) : fill_traits<GptqTraits<2, false>>(pl); }

@@ -283,7 +283,7 @@ static size_t g_rp_dbg_cap = 0, g_rp_dbg_pos = 0;   // in u64 entries; consecuti
 static bool rp_plan(const LayerView& L, int M, RpPlan& pl) {
   pl.kind = 0;
   pl.sm = g_rp_smem;
-  if (M < 1 || M > kMB || L.g_idx != nullptr) return false;
+  if (M < 1 || M > kMB || L.g_idx != nullptr || L.x_perm != nullptr) return false;
   if (L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) {
     if (L.bits == 2) { pl.kind = 1; rp_fill<RpGptq<2>>(pl); }
     else if (L.bits == 4) { pl.kind = 2; rp_fill<RpGptq<4>>(pl); }

@@ -419,11 +419,11 @@ static bool st_plan(const LinearArgs* a, int n, StPlan& pl) {
   if (n < 1 || n > kMaxGroupLayers) return false;
   const LayerView& L = a[0].L;
   const int M = a[0].M;
-  if (M < 1 || M > kMB || L.g_idx != nullptr) return false;
+  if (M < 1 || M > kMB || L.g_idx != nullptr || L.x_perm != nullptr) return false;
   for (int i = 1; i < n; ++i) {
     const LayerView& B = a[i].L;
     if (B.layout != L.layout || B.bits != L.bits || B.group != L.group || B.K != L.K || B.zero_bias != L.zero_bias ||
-        B.g_idx != nullptr || a[i].M != M || a[i].x != a[0].x || a[i].ldx != a[0].ldx)
+        B.g_idx != nullptr || B.x_perm != nullptr || a[i].M != M || a[i].x != a[0].x || a[i].ldx != a[0].ldx)
       return false;
   }
   if (L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) {

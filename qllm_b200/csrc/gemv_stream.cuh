@@ -22,6 +22,7 @@ struct StParams {
   int n_layers;
   int layout, bits, group, K, G, zero_bias;      // shared by the layers of a group
   const __half* x;
+  const int* xperm;                              // act-order re-layout: x is read through this map (integer-path kernel only)
   int64_t ldx;
   int M;
   int cluster, tpc, depth, steps_total, group_shift, gcap, split_q, split_r, part_cap;

@@ -53,6 +53,8 @@ int decode_sync_flags();        // diagnostic switch (B200Q_SYNC_FLAGS / "sync_f
 // unpack.cu
 cudaError_t launch_unpack(const LayerView& L, int32_t* q_out, int32_t* z_out, cudaStream_t st);
 cudaError_t launch_dequant(const LayerView& L, __half* w_out, cudaStream_t st);
+cudaError_t launch_repack_actorder(const LayerView& L, const int* perm, uint32_t* qw_out, cudaStream_t st);
+cudaError_t launch_gather_x(const __half* x, int64_t ldx, const int* perm, __half* out, int M, int K, cudaStream_t st);
 cudaError_t launch_repack_gptq4(const LayerView& L, uint32_t* qw_out, uint32_t* qz_out, __half* s_out, cudaStream_t st);
 
 // gemv_generic.cu : any layout / bits / group / g_idx, M <= 16, CUDA cores

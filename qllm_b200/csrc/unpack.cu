@@ -73,6 +73,43 @@ cudaError_t launch_repack_gptq4(const LayerView& L, uint32_t* qw_out, uint32_t* 
   return cudaGetLastError();
 }
 
+// Act-order re-layout: packed row-block kw of the output holds original rows perm[P kw .. P kw + P - 1] (P = 32 / bits).
+__global__ void __launch_bounds__(256) repack_actorder_kernel(LayerView L, const int* __restrict__ perm, uint32_t* __restrict__ qw_out) {
+  const int P = 32 / L.bits;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)(L.K / P) * L.N) return;
+  const int kw = (int)(idx / L.N), n = (int)(idx % L.N);
+  const uint32_t mask = (1u << L.bits) - 1u;
+  uint32_t w = 0;
+  for (int i = 0; i < P; ++i) w |= (load_q(L, perm[P * kw + i], n) & mask) << (L.bits * i);
+  qw_out[idx] = w;
+}
+
+cudaError_t launch_repack_actorder(const LayerView& L, const int* perm, uint32_t* qw_out, cudaStream_t st) {
+  const size_t total = (size_t)(L.K * L.bits / 32) * L.N;
+  repack_actorder_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, perm, qw_out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// x_out[m, j] = x[m, perm[j]]: the activation half of the act-order re-layout for the kernels that stage x with bulk copies
+__global__ void __launch_bounds__(256) gather_x_kernel(const __half* __restrict__ x, int64_t ldx, const int* __restrict__ perm,
+                                                       __half* __restrict__ out, int M, int K) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)M * (K >> 1)) return;
+  const int m = (int)(idx / (K >> 1)), j = (int)(idx % (K >> 1)) << 1;
+  const int2 pi = *reinterpret_cast<const int2*>(perm + j);
+  const __half* row = x + (size_t)m * ldx;
+  *reinterpret_cast<__half2*>(out + (size_t)m * K + j) = __halves2half2(row[pi.x], row[pi.y]);
+}
+
+cudaError_t launch_gather_x(const __half* x, int64_t ldx, const int* perm, __half* out, int M, int K, cudaStream_t st) {
+  const size_t total = (size_t)M * (K >> 1);
+  gather_x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, ldx, perm, out, M, K);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_unpack(const LayerView& L, int32_t* q_out, int32_t* z_out, cudaStream_t st) {
   const size_t total = (size_t)L.K * (L.N >> 3);
   unpack_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, q_out, nullptr);

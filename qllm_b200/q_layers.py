@@ -29,6 +29,9 @@ _workspaces = {}
 # Decode (M <= 2) on AWQ-GEMM / Marlin layers runs on the layer's exact K-packed re-layout (the integer-tensor-path
 # kernel, csrc/gemv_imma.cu); B200Q_DECODE_RELAYOUT=0 keeps decode on the checkpoint bytes (fp16-path kernels).
 DECODE_RELAYOUT = os.environ.get("B200Q_DECODE_RELAYOUT", "1") != "0"
+# Act-order (desc_act) GPTQ layers run on their exact row-permuted re-layout with activations gathered through the
+# permutation (b200q_repack_actorder + b200q_layer.x_perm); B200Q_ACTORDER_RELAYOUT=0 keeps them on the generic kernel.
+ACTORDER_RELAYOUT = os.environ.get("B200Q_ACTORDER_RELAYOUT", "1") != "0"
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
@@ -104,13 +107,41 @@ class _B200QuantLinearBase(nn.Module):
             self._desc_key = tuple(0 if t is None else t.data_ptr() for t in self._tensors())
         return self._desc
 
+    # -- act-order: groups made contiguous once, activations gathered at run time ------------------
+    def _fast_descriptor(self):
+        """The descriptor forward() hands to the engine for GPTQ/HQQ layers: the checkpoint buffers, or -- act-order
+        checkpoints whose groups all own exactly `groupsize` rows -- {row-permuted qweight, original qzeros/scales,
+        g_idx = NULL, x_perm = stable argsort(g_idx)}, built once (exact integer re-layout on the GPU)."""
+        desc = self._descriptor()
+        if not (ACTORDER_RELAYOUT and self.act_order and self._layout == LAYOUT_GPTQ and self.bits in (2, 4, 8)):
+            return desc
+        key = self._desc_key
+        if getattr(self, "_ao_key", None) != key:
+            dev = self.qweight.device
+            g = self.g_idx.to(device=dev, dtype=torch.int64)
+            perm = torch.argsort(g, stable=True)
+            K, gs = self.infeatures, self.groupsize
+            regular = K % gs == 0 and K % 2 == 0 and bool((g[perm] == torch.arange(K, device=dev) // gs).all().item())
+            self._ao_desc = None
+            if regular:
+                perm32 = perm.to(torch.int32).contiguous()
+                qw = torch.empty_like(self.qweight)
+                check(lib.b200q_repack_actorder(ctypes.byref(desc), perm32.data_ptr(), qw.data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream), "b200q_repack_actorder")
+                d = Layer()
+                d.layout, d.bits, d.group_size, d.K, d.N, d.zero_bias = desc.layout, desc.bits, desc.group_size, desc.K, desc.N, desc.zero_bias
+                d.qweight, d.qzeros, d.scales, d.g_idx, d.bias, d.x_perm = qw.data_ptr(), desc.qzeros, desc.scales, None, desc.bias, perm32.data_ptr()
+                self._ao, self._ao_desc = (qw, perm32), d
+            self._ao_key = key
+        return self._ao_desc if self._ao_desc is not None else desc
+
     # -- K-packed shadow for the tensor-core GEMM (AWQ / Marlin until their native producers exist) --
     def _gemm_descriptor(self):
         """b200q_layer the tcgen05 GEMM can take.  GPTQ/HQQ: the checkpoint buffers themselves.  AWQ/Marlin:
         a one-time exact integer re-layout (b200q_repack_gptq4) kept beside the native buffers."""
         desc = self._descriptor()
         if self._layout not in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN):
-            return desc
+            return self._fast_descriptor()
         key = self._desc_key
         if getattr(self, "_shadow_key", None) != key:
             dev = self.qweight.device
@@ -131,7 +162,7 @@ class _B200QuantLinearBase(nn.Module):
         M <= 2 -- the one-time exact K-packed re-layout that the integer-tensor-path kernel consumes."""
         if DECODE_RELAYOUT and M <= 2 and self._layout in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN):
             return self._gemm_descriptor()
-        return self._descriptor()
+        return self._fast_descriptor()
 
     # -- forward ------------------------------------------------------------------------------
     def __call__(self, x):
@@ -141,7 +172,7 @@ class _B200QuantLinearBase(nn.Module):
         return super().__call__(x)
 
     def forward(self, x):
-        desc = self._descriptor()
+        desc = self._fast_descriptor()
         out_shape = x.shape[:-1] + (self.outfeatures,)
         x2 = x.reshape(-1, x.shape[-1])
         if x2.dtype != torch.float16:

@@ -455,3 +455,74 @@ def test_imma_kernel_matches_fp16_path_and_handles_extremes():
     ref = oracle_forward(L, x)
     assert rel_err(y_int, ref) < TOL and rel_err(y_f16, ref) < TOL
     assert rel_err(y_int, ref) <= rel_err(y_f16, ref) + 2e-4        # the fixed-point split loses nothing against fp16 MMA inputs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# act-order (desc_act) checkpoints: exact row-permuted re-layout + activations gathered through x_perm
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,gs,K,N", [(4, 128, 1024, 512), (4, 64, 512, 256), (8, 128, 512, 256), (2, 64, 512, 256)])
+@pytest.mark.parametrize("M", [1, 2, 5, 16, 64, 300])
+def test_act_order_relayout_vs_oracle(bits, gs, K, N, M):
+    import ctypes
+    import qllm_b200
+    L = O.make_layer("GPTQ", bits, gs, K, N, seed=7 * K + N + bits, act_order=True, bias=(M == 2))
+    layer = layer_from_dict(L)
+    x = np.random.default_rng(M + 3).standard_normal((M, K)).astype(np.float16)
+    y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+    assert rel_err(y, oracle_forward(L, x)) < TOL
+    fast = layer._fast_descriptor()
+    assert fast.x_perm and not fast.g_idx                       # the re-layout is in use, not the generic g_idx kernel
+    want = 1 if M <= 8 else 2
+    assert qllm_b200.lib.b200q_select_kernel(ctypes.byref(fast), M) == want
+
+
+@pytest.mark.gpu
+def test_act_order_repack_is_the_exact_row_permutation():
+    K, N, gs = 512, 256, 128
+    L = O.make_layer("GPTQ", 4, gs, K, N, seed=99, act_order=True)
+    layer = layer_from_dict(L)
+    layer._fast_descriptor()
+    qw_perm, perm = layer._ao
+    perm = perm.cpu().numpy()
+    assert np.array_equal(L["g_idx"][perm], np.arange(K) // gs)               # groups contiguous after the permutation
+    q_perm = O.unpack_rows(qw_perm.cpu().numpy(), 4, K) if hasattr(O, "unpack_rows") else None
+    if q_perm is None:
+        from qllm_b200 import codec
+        q_perm = codec.unpack_rows(qw_perm.cpu(), 4, K).numpy()
+    assert np.array_equal(q_perm, L["q"][perm])                                # bit-exact
+    # one-hot activations read single rows of W back through the gather: row k of W = y(e_k)
+    for k in (0, 17, K - 1):
+        e = torch.zeros(1, K, dtype=torch.float16, device="cuda")
+        e[0, k] = 1.0
+        W = O.dequant(L["q"], L["z"], L["s"], L["g_idx"], "engine")
+        assert np.array_equal(layer(e).cpu().numpy()[0], W[k].astype(np.float16))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [1, 12])
+def test_irregular_g_idx_stays_on_the_generic_kernel(M):
+    """g_idx maps whose groups do not all own group_size rows cannot be made contiguous: generic kernel, same answer."""
+    K, N, gs = 256, 64, 32
+    L = O.make_layer("GPTQ", 4, gs, K, N, seed=5, act_order=True)
+    g = L["g_idx"].copy()
+    g[g == 1] = 0                                                              # group 0 now owns 64 rows, group 1 none
+    L = O.make_layer("GPTQ", 4, gs, K, N, seed=5, act_order=True)
+    L["g_idx"] = g.astype(np.int32)
+    layer = layer_from_dict(L)
+    x = np.random.default_rng(1).standard_normal((M, K)).astype(np.float16)
+    y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+    assert rel_err(y, oracle_forward(L, x)) < TOL
+    assert not layer._fast_descriptor().x_perm
+
+
+@pytest.mark.gpu
+def test_generic_g_idx_kernel_still_agrees(monkeypatch):
+    from qllm_b200 import q_layers
+    monkeypatch.setattr(q_layers, "ACTORDER_RELAYOUT", False)
+    L = O.make_layer("GPTQ", 4, 128, 512, 256, seed=3, act_order=True)
+    layer = layer_from_dict(L)
+    for M in (1, 9):
+        x = np.random.default_rng(M).standard_normal((M, 512)).astype(np.float16)
+        assert rel_err(layer(torch.from_numpy(x).cuda()).float().cpu().numpy(), oracle_forward(L, x)) < TOL
+    assert not layer._fast_descriptor().x_perm

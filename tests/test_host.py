@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_descriptor_struct_matches_header_layout():
     from qllm_b200._lib import Layer
-    assert ctypes.sizeof(Layer) == 6 * 4 + 5 * 8
+    assert ctypes.sizeof(Layer) == 6 * 4 + 6 * 8
     assert Layer.qweight.offset == 24 and Layer.bias.offset == 56
 
 

@@ -40,6 +40,8 @@ def rand_layer(layout, bits, gs, K, N, dev, seed):
         l = qllm_b200.QuantLinearGPTQ(bits, gs, K, N, False, dtype=torch.float16)
         l.qweight, l.qzeros = ri(K * bits // 32, N), ri(G, N * bits // 32)
         l.g_idx = l.g_idx.to(dev)
+        if layout == "GPTQ_ACT":                          # desc_act checkpoint: rows of every group scattered over K
+            l.g_idx = l.g_idx[torch.randperm(K, device=dev, generator=g)].contiguous()
     l.scales = sc.to(torch.float16)
     return l.to(dev)
 
@@ -47,7 +49,7 @@ def rand_layer(layout, bits, gs, K, N, dev, seed):
 def alg_bytes(layout, bits, gs, K, N, M):
     G = K // gs
     z = 0 if layout == "MARLIN" else (G * N * 2 if layout == "HQQ" else G * N * bits // 8)
-    return K * N * bits // 8 + G * N * 2 + z + M * K * 2 + M * N * 2
+    return K * N * bits // 8 + G * N * 2 + z + M * K * 2 + M * N * 2 + (K * 4 if layout == "GPTQ_ACT" else 0)
 
 
 def time_shape(layout, bits, gs, K, N, M, iters=200, use_graph=False, force=None):
