@@ -100,6 +100,8 @@ static int gemv_variant() {
     if (ms) gemv_rp_set_min_steps(atoi(ms));
     const char* t = getenv("B200Q_TT256_MIN_M");
     if (t) gemm_tc_set_tt256_min_m(atoi(t));
+    const char* gp = getenv("B200Q_GEMM_PDL");
+    if (gp) gemm_tc_set_pdl(atoi(gp));
     const char* c = getenv("B200Q_MAX_CLUSTER");
     if (c) gemv_rp_set_max_cluster(atoi(c));
     const char* fc = getenv("B200Q_FORCE_CLUSTER");
@@ -510,6 +512,7 @@ int b200q_debug_set_option(const char* name, double value) {
   else if (n == "im_tpc") gemv_imma_set_option(3, (int)value);
   else if (n == "im_target") gemv_imma_set_option(4, (int)value);
   else if (n == "sync_flags") g_sync_flags = (int)value;
+  else if (n == "gemm_pdl") gemm_tc_set_pdl((int)value);
   else return B200Q_ERR_UNSUPPORTED;
   return B200Q_OK;
 }

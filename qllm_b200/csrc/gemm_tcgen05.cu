@@ -178,6 +178,10 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (tid == 0) TC_STAMP(p.kblocks, 0);                                                        // kernel entry
+  // Programmatic dependent launch: the next kernel of the stream may start its prologue (barriers, TMEM, group tables,
+  // packed-weight TMA + dequant -- none of which depends on this kernel) on every SM this grid has left; only its
+  // activation loads and its stores wait for this grid to finish (griddepcontrol.wait below).
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < kNSXMax; ++s) { mbar_init(&full_x[s], 1); mbar_init(&empty_x[s], 1); }   // empty_x: unused
     for (int s = 0; s < kNSWMax; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], kDqWarps); }
@@ -230,6 +234,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 
   if (warp == kWXProd) {                   // X producer: the ring only spans TMA latency + MMA lag
     if (lane == 0) {
+      pdl_wait();                          // x may be the previous kernel's output
       int s = 0;
       for (int kb = 0; kb < p.kblocks; ++kb) {
         // X stage s was last read by the MMAs of k-block kb - nsx, whose completion is signalled on that k-block's
@@ -391,6 +396,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     // ---- epilogue: TMEM -> registers -> fp16 -> shared (transpose) -> 16-byte coalesced stores ----
     ok = __all_sync(0xffffffffu, ok && mbar_wait_bounded(acc_full, 0, p.err, 6));
     if (tid == 0) TC_STAMP(p.kblocks, 3);                                                      // accumulators complete
+    pdl_wait();                                     // stores follow the previous kernel's last reads (returns at once by now)
     tc_fence_after();
     const float bias = (p.L.bias && (n0 + n) < p.L.N) ? __half2float(__ldg(p.L.bias + n0 + n)) : 0.f;
     __half* stg = reinterpret_cast<__half*>(xst) + (size_t)eidx * 32 * (kBN + 8);     // [32 tok][128+8 n], X stages are free now
@@ -462,6 +468,8 @@ int gemm_tc_last_error() {
   return v;
 }
 
+static int g_tc_pdl = 1;                  // B200Q_GEMM_PDL=0 / option "gemm_pdl": plain stream-ordered launches
+void gemm_tc_set_pdl(int on) { g_tc_pdl = on; }
 static int g_tc_tt256_min_m = 1024;
 void gemm_tc_set_tt256_min_m(int m) { g_tc_tt256_min_m = m; }
 static int pick_tt(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : (M >= g_tc_tt256_min_m ? 256 : 128)); }
@@ -551,8 +559,17 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   if ((a.ldy % 8) != 0 || (a.n_offset % 8) != 0) return cudaErrorInvalidValue;     // 16-byte epilogue stores
   dim3 grid((L.N + kBN - 1) / kBN, (a.M + TT - 1) / TT);
   count_launch();
-  gemm_tc_gptq_kernel<TT, BITS, FZ, DBG><<<grid, kTcThreads, smem_bytes, a.stream>>>(xmap, wmap, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_tc_pdl ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_gptq_kernel<TT, BITS, FZ, DBG>, xmap, wmap, p);
 }
 
 cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers) {

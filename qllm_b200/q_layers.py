@@ -128,6 +128,7 @@ class _B200QuantLinearBase(nn.Module):
                 qw = torch.empty_like(self.qweight)
                 check(lib.b200q_repack_actorder(ctypes.byref(desc), perm32.data_ptr(), qw.data_ptr(),
                                                 torch.cuda.current_stream(dev).cuda_stream), "b200q_repack_actorder")
+                torch.cuda.current_stream(dev).synchronize()    # one-time: the kernels prefetch weights ahead of their stream dependency
                 d = Layer()
                 d.layout, d.bits, d.group_size, d.K, d.N, d.zero_bias = desc.layout, desc.bits, desc.group_size, desc.K, desc.N, desc.zero_bias
                 d.qweight, d.qzeros, d.scales, d.g_idx, d.bias, d.x_perm = qw.data_ptr(), desc.qzeros, desc.scales, None, desc.bias, perm32.data_ptr()
@@ -151,6 +152,7 @@ class _B200QuantLinearBase(nn.Module):
             sc = torch.empty((G, N), dtype=torch.float16, device=dev)
             check(lib.b200q_repack_gptq4(ctypes.byref(desc), qw.data_ptr(), qz.data_ptr(), sc.data_ptr(),
                                          torch.cuda.current_stream(dev).cuda_stream), "b200q_repack_gptq4")
+            torch.cuda.current_stream(dev).synchronize()        # one-time: the kernels prefetch weights ahead of their stream dependency
             d = Layer()
             d.layout, d.bits, d.group_size, d.K, d.N, d.zero_bias = LAYOUT_GPTQ, 4, self.groupsize, K, N, 0
             d.qweight, d.qzeros, d.scales, d.g_idx, d.bias = qw.data_ptr(), qz.data_ptr(), sc.data_ptr(), None, desc.bias

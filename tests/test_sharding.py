@@ -121,7 +121,8 @@ class _VirtualArena:
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("layout,M,Ns", [("GPTQ", 1, (1024, 1024, 1024)), ("GEMM", 2, (1536, 1536)), ("GPTQ", 1, (512,))])
+@pytest.mark.parametrize("layout,M,Ns", [("GPTQ", 1, (1024, 1024, 1024)), ("GEMM", 2, (1536, 1536)), ("GPTQ", 1, (512,)),
+                                         ("GPTQ", 1, (192, 192))])         # 96-column shards: one and a half tiles
 def test_fused_handoff_group_sharded_virtual_ranks(layout, M, Ns):
     """b200q_linear_group_sharded: shards of sibling layers land in every replica, every storing CTA posts once on
     every peer, a consumer that waits on the slot sees epoch * posts, counters only grow across steps, slot 0 (the
