@@ -46,6 +46,7 @@ struct TcParams {
   PeerOut out;
   int64_t ldy, n_offset;
   int kblocks, gshift, group32, nsx, nsw;   // nsx / nsw: X and W ring depths actually used
+  int kbc, nchunks, gcap;                   // group tables are staged per chunk of kbc k-blocks (<= gcap groups): long-K / small-group layers
   float inv_group;   // ns: input stages actually used (<= kNSMax, sized to fit shared memory)
   int off_x, off_w, off_sc, off_zq, off_bar;
   int* err;
@@ -198,33 +199,6 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (tid == 0) TC_STAMP(p.kblocks, 1);                                                        // barriers + TMEM ready
-  if (warp < kDqWarps * kDqPar) {
-    // group tables for this CTA's 128 columns (all groups): only the dequant warps need them, so their load
-    // latency overlaps the first TMA round trips instead of preceding them
-    constexpr int kDqThreads = kDqWarps * kDqPar * 32;
-    for (int idx = tid; idx < p.L.G * kBN; idx += kDqThreads) {
-      const int g = idx / kBN, n = idx % kBN;
-      sc[idx] = (n0 + n < p.L.N) ? __ldg(p.L.s + (size_t)g * p.L.N + n0 + n) : __float2half(0.f);
-    }
-    if (FZ) {
-      for (int idx = tid; idx < p.L.G * kBN; idx += kDqThreads) {
-        const int g = idx / kBN, n = idx % kBN;
-        reinterpret_cast<__half*>(zq)[idx] =
-            (n0 + n < p.L.N) ? __ldg(reinterpret_cast<const __half*>(p.L.qz) + (size_t)g * p.L.N + n0 + n) : __float2half(0.f);
-      }
-    } else {
-      constexpr int ZW = kBN * BITS / 32;                                 // packed zero words of this tile per group
-      const size_t zrow = ((size_t)p.L.N * BITS) >> 5;
-      for (int idx = tid; idx < p.L.G * ZW; idx += kDqThreads) {
-        const int g = idx / ZW, wv = idx % ZW;
-        reinterpret_cast<uint32_t*>(zq)[idx] =
-            ((n0 * BITS) / 32 + wv < (int)zrow) ? __ldg(reinterpret_cast<const uint32_t*>(p.L.qz) + (size_t)g * zrow + (n0 * BITS) / 32 + wv) : 0u;
-      }
-    }
-    asm volatile("bar.sync 8, %0;" ::"n"(kDqWarps * kDqPar * 32) : "memory");
-    if (tid == 0) TC_STAMP(p.kblocks, 2);                                                      // group tables in shared memory
-  }
-
   constexpr int P = 32 / BITS;                     // k values per packed word
   constexpr int RS = kBK / P;                      // packed rows per stage
   constexpr int WH = RS / 2;                       // words per column per half-stage (32 k)
@@ -312,7 +286,9 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     const uint32_t* zq_lane = reinterpret_cast<const uint32_t*>(zq) + (zbit >> 5);
     // group constants of this lane's column: s2 = (s,s); integer zeros folded into the magic constants,
     // (h - (1024+z)) * s  [h = 1024+q];  float zeros (HQQ): ((h - 1024) - z) * s
-    auto load_group = [&](int gi) {
+    int gbase = 0;                              // first group held by the shared-memory tables (current chunk)
+    auto load_group = [&](int gabs) {
+      const int gi = gabs - gbase;
       s2 = dup_half(sc[gi * kBN + n]);
       if (FZ) {
         z2 = dup_half(reinterpret_cast<const __half*>(zq)[gi * kBN + n]);
@@ -355,7 +331,39 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     const int kNS = p.nsw;
     int s = par % kNS;
     uint32_t ph = (uint32_t)((par / kNS) & 1);
-    for (int kb = par; kb < p.kblocks; kb += kDqPar) {
+    constexpr int kDqThreads = kDqWarps * kDqPar * 32;
+    for (int c = 0; c < p.nchunks; ++c) {
+    // ---- group tables of this chunk's k-blocks for the CTA's 128 columns: loaded by the dequant warps only, so the first
+    // chunk's load latency overlaps the first TMA round trips; later chunks cost one pipeline bubble each ----
+    const int kb0 = c * p.kbc, kb1 = min(p.kblocks, kb0 + p.kbc);
+    {
+      gbase = (kb0 * kBK) / p.L.group;
+      const int gcount = ((kb1 * kBK - 1) / p.L.group) - gbase + 1;
+      if (c > 0) asm volatile("bar.sync 8, %0;" ::"n"(kDqThreads) : "memory");       // every warp is done with the previous tables
+      for (int idx = tid; idx < gcount * kBN; idx += kDqThreads) {
+        const int g = gbase + idx / kBN, nn = idx % kBN;
+        sc[idx] = (n0 + nn < p.L.N) ? __ldg(p.L.s + (size_t)g * p.L.N + n0 + nn) : __float2half(0.f);
+      }
+      if (FZ) {
+        for (int idx = tid; idx < gcount * kBN; idx += kDqThreads) {
+          const int g = gbase + idx / kBN, nn = idx % kBN;
+          reinterpret_cast<__half*>(zq)[idx] =
+              (n0 + nn < p.L.N) ? __ldg(reinterpret_cast<const __half*>(p.L.qz) + (size_t)g * p.L.N + n0 + nn) : __float2half(0.f);
+        }
+      } else {
+        constexpr int ZW = kBN * BITS / 32;                                 // packed zero words of this tile per group
+        const size_t zrow = ((size_t)p.L.N * BITS) >> 5;
+        for (int idx = tid; idx < gcount * ZW; idx += kDqThreads) {
+          const int g = gbase + idx / ZW, wv = idx % ZW;
+          reinterpret_cast<uint32_t*>(zq)[idx] =
+              ((n0 * BITS) / 32 + wv < (int)zrow) ? __ldg(reinterpret_cast<const uint32_t*>(p.L.qz) + (size_t)g * zrow + (n0 * BITS) / 32 + wv) : 0u;
+        }
+      }
+      asm volatile("bar.sync 8, %0;" ::"n"(kDqThreads) : "memory");
+      if (tid == 0 && c == 0) TC_STAMP(p.kblocks, 2);                                  // first group tables in shared memory
+      gcur = -1;
+    }
+    for (int kb = kb0 + ((par - kb0 % kDqPar) + kDqPar) % kDqPar; kb < kb1; kb += kDqPar) {
       const int sa = kb % kNA;
       mbar_wait_bounded(&full_w[s], ph, p.err, 4);
       if ((warp & 7) == 0 && lane == 0) TC_STAMP(kb, 0);
@@ -392,6 +400,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       if ((warp & 7) == 0 && lane == 0) TC_STAMP(kb, 3);
       s += kDqPar;
       while (s >= kNS) { s -= kNS; ph ^= 1u; }
+    }
     }
     // ---- epilogue: TMEM -> registers -> fp16 -> shared (transpose) -> 16-byte coalesced stores ----
     ok = __all_sync(0xffffffffu, ok && mbar_wait_bounded(acc_full, 0, p.err, 6));
@@ -480,9 +489,6 @@ bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t l
   if (L.group % (32 / L.bits) != 0) return false;                         // a packed word never straddles two groups
   if (L.K % kBK != 0 || L.N % 8 != 0 || L.group % 8 != 0 || L.K % L.group != 0) return false;
   if (((uintptr_t)x & 15) != 0 || (ldx % 8) != 0 || ((uintptr_t)L.qw & 15) != 0 || (L.N % 8) != 0) return false;
-  const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN * L.bits / 8;
-  const size_t tables = (size_t)L.G * (kBN * 2 + zq_row);
-  if (tables > 60 * 1024) return false;
   return get_encode() != nullptr && M >= 1;
 }
 
@@ -528,9 +534,18 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   p.err = g_err_flag;
   p.dbg = g_tc_dbg;
   const int zq_row = (L.layout == B200Q_LAYOUT_HQQ) ? kBN * 2 : kBN * BITS / 8;
+  // group tables: all groups when they fit in 56 KB, else per chunk of kbc k-blocks
+  const int max_groups = (56 * 1024) / (kBN * 2 + zq_row);
+  if (L.G <= max_groups) { p.kbc = p.kblocks; p.nchunks = 1; p.gcap = L.G; }
+  else {
+    p.kbc = (int)(((long long)(max_groups - 1) * L.group) / kBK);
+    if (p.kbc < 1) return cudaErrorInvalidValue;
+    p.nchunks = (p.kblocks + p.kbc - 1) / p.kbc;
+    p.gcap = (p.kbc * kBK + L.group - 1) / L.group + 1;
+  }
   int off = 0;
   const int stage_bytes = TT * kBK * 2 + (kBK * BITS / 32) * kBN * 4;
-  const int fixed_bytes = L.G * (kBN * 2 + zq_row) + 64 + 1024 + 1024;
+  const int fixed_bytes = p.gcap * (kBN * 2 + zq_row) + 64 + 1024 + 1024;
   const int xb = TT * kBK * 2, wb = (kBK * BITS / 32) * kBN * 4, budget = 220 * 1024 - fixed_bytes;
   int nsx = tc_stages(TT), nsw = kNSWMax;
   while (nsw > 6 && nsx * xb + nsw * wb > budget) --nsw;
@@ -540,9 +555,9 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   p.nsx = nsx; p.nsw = nsw;
   p.off_x = off; off += nsx * xb;
   p.off_w = off; off += nsw * wb;
-  p.off_sc = off; off += L.G * kBN * 2;
+  p.off_sc = off; off += p.gcap * kBN * 2;
   off = (off + 15) & ~15;
-  p.off_zq = off; off += L.G * zq_row;
+  p.off_zq = off; off += p.gcap * zq_row;
   off = (off + 15) & ~15;
   p.off_bar = off; off += 1024;
   const int smem_bytes = off + 1024;   // slack for 1024-byte alignment of the dynamic window

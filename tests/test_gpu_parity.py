@@ -526,3 +526,20 @@ def test_generic_g_idx_kernel_still_agrees(monkeypatch):
         x = np.random.default_rng(M).standard_normal((M, 512)).astype(np.float16)
         assert rel_err(layer(torch.from_numpy(x).cuda()).float().cpu().numpy(), oracle_forward(L, x)) < TOL
     assert not layer._fast_descriptor().x_perm
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout,bits,gs,K,N", [("HQQ", 4, 64, 14336, 256), ("GPTQ", 4, 32, 8192, 384), ("HQQ", 2, 64, 14336, 128),
+                                                ("GPTQ", 8, 64, 14336, 128)])
+@pytest.mark.parametrize("M", [16, 200])
+def test_tcgen05_gemm_long_k_small_groups_chunked_tables(layout, bits, gs, K, N, M):
+    """More group constants than fit in shared memory (Mixtral w2: K = 14336, g64): the GEMM stages its (scale, zero)
+    tables per chunk of k-blocks instead of falling back to the generic kernel."""
+    import ctypes
+    import qllm_b200
+    L = O.make_layer(layout, bits, gs, K, N, seed=K + N + bits + M, float_zeros=(layout == "HQQ"))
+    layer = layer_from_dict(L)
+    assert qllm_b200.lib.b200q_select_kernel(ctypes.byref(layer._descriptor()), M) == 2
+    x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+    y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+    assert rel_err(y, oracle_forward(L, x)) < TOL

@@ -246,3 +246,40 @@ def test_tagged_activation_chain_virtual_ranks(layout, M):
         assert torch.equal(outs[0], outs[1])
         assert rel_err(outs[0].float().cpu().numpy(), ref) < 1e-3
         assert A.counter(0, 0) == 0 and A.counter(1, 0) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,N,world", [(4096, 4096, 8), (4096, 11008, 8), (11008, 4096, 8), (4096, 11008, 4)])
+def test_tagged_shards_at_llama7b_shapes_all_ranks_on_one_gpu(K, N, world):
+    """The column shards bench.py --gpus 8 / 4 runs (512-, 1376- = 21.5-tile and 2752-column shards, K up to 11008), every
+    rank executed in turn on one GPU: all shards land tagged in both checked replicas and equal the oracle."""
+    import ctypes
+    from qllm_b200 import Layer, check, lib
+    from qllm_b200._lib import PEER_Y_TAGGED
+    gs, M = 128, 1
+    L = O.make_layer("GEMM", 4, gs, K, N, seed=K + N + world)
+    full = layer_from_dict(L, device="cpu")
+    x = np.random.default_rng(9).standard_normal((M, K)).astype(np.float16)
+    xd = torch.from_numpy(x).cuda()
+    A = _VirtualArena(world, M * N * 4 + 256)
+    ws = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(world):
+        check(lib.b200q_peer_epoch_advance(A.epochs[r].data_ptr(), st))
+    for r in range(world):
+        shard = sharding.shard_layer(full, r, world).cuda()
+        d = shard._decode_descriptor(M)
+        arr = (ctypes.POINTER(Layer) * 1)(ctypes.pointer(d))
+        yp = (ctypes.c_void_p * world)(*[A.bufs[q].data_ptr() + 2048 for q in range(world)])
+        ld, no = (ctypes.c_int64 * 1)(N), (ctypes.c_int64 * 1)(shard.col0)
+        s = A.sync(r, -1, 0, -1)
+        s.flags, s.tag_stride, s.y_seq = PEER_Y_TAGGED, 5, 2
+        check(lib.b200q_linear_group_sharded(arr, 1, xd.data_ptr(), M, xd.stride(0), yp, ld, no, ctypes.byref(s),
+                                             ws.data_ptr(), ws.numel(), st))
+        del shard
+    torch.cuda.synchronize()
+    ref = oracle_forward(L, x)
+    for q in (0, world - 1):
+        words = A.bufs[q][2048:2048 + M * N * 4].view(torch.int32).cpu().numpy().astype(np.uint32)
+        assert np.all(words >> 16 == 7)
+        assert rel_err((words & 0xffff).astype(np.uint16).view(np.float16).reshape(M, N), ref) < 1e-3
