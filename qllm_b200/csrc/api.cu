@@ -102,6 +102,8 @@ static int gemv_variant() {
     if (t) gemm_tc_set_tt256_min_m(atoi(t));
     const char* gp = getenv("B200Q_GEMM_PDL");
     if (gp) gemm_tc_set_pdl(atoi(gp));
+    const char* gk = getenv("B200Q_GEMM_SPLITK");
+    if (gk) gemm_tc_set_splitk(atoi(gk));
     const char* c = getenv("B200Q_MAX_CLUSTER");
     if (c) gemv_rp_set_max_cluster(atoi(c));
     const char* fc = getenv("B200Q_FORCE_CLUSTER");
@@ -164,6 +166,7 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   if (v != B200Q_OK) return v;
   if (!x || (!y && !peers)) return B200Q_ERR_NULL;
   if (M < 1 || ldx < layer->K || ldy < n_offset + layer->N) return B200Q_ERR_SHAPE;
+  gemv_variant();                          // one-time parse of the B200Q_* switches
   LayerView V = make_view(layer);
   const size_t base = workspace_for(V, M), need = base + gather_bytes(V, M);
   if (need > 0 && (!ws || ws_bytes < need)) return B200Q_ERR_WORKSPACE;
@@ -450,6 +453,7 @@ int b200q_repack_gptq4(const b200q_layer* layer, void* qweight_out, void* qzeros
 
 size_t b200q_workspace_bytes(const b200q_layer* layer, int64_t M) {
   if (validate(layer) != B200Q_OK || M < 1) return 0;
+  gemv_variant();
   const LayerView V = make_view(layer);
   return workspace_for(V, M) + gather_bytes(V, M);
 }
@@ -513,6 +517,7 @@ int b200q_debug_set_option(const char* name, double value) {
   else if (n == "im_target") gemv_imma_set_option(4, (int)value);
   else if (n == "sync_flags") g_sync_flags = (int)value;
   else if (n == "gemm_pdl") gemm_tc_set_pdl((int)value);
+  else if (n == "gemm_splitk") gemm_tc_set_splitk((int)value);
   else return B200Q_ERR_UNSUPPORTED;
   return B200Q_OK;
 }

@@ -46,6 +46,9 @@ struct TcParams {
   PeerOut out;
   int64_t ldy, n_offset;
   int kblocks, gshift, group32, nsx, nsw;   // nsx / nsw: X and W ring depths actually used
+  int ksplit, kb_per;                       // split-K over gridDim.z (small M): k-blocks per split; partial tiles + last-arriver reduction
+  float* partial;                           // [ksplit][M][N] fp32 (workspace, behind the counter region)
+  unsigned int* counters;                   // arrival counter per output tile (workspace head, left zeroed)
   int kbc, nchunks, gcap;                   // group tables are staged per chunk of kbc k-blocks (<= gcap groups): long-K / small-group layers
   float inv_group;   // ns: input stages actually used (<= kNSMax, sized to fit shared memory)
   int off_x, off_w, off_sc, off_zq, off_bar;
@@ -176,6 +179,8 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * kBN;
   const int tok0 = blockIdx.y * TT;
+  const int kbz0 = blockIdx.z * p.kb_per;                              // this CTA's k-blocks: kbz0 + [0, nkb)
+  const int nkb = min(p.kblocks, kbz0 + p.kb_per) - kbz0;
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
   if (tid == 0) TC_STAMP(p.kblocks, 0);                                                        // kernel entry
@@ -210,7 +215,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     if (lane == 0) {
       pdl_wait();                          // x may be the previous kernel's output
       int s = 0;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
+      for (int kb = 0; kb < nkb; ++kb) {
         // X stage s was last read by the MMAs of k-block kb - nsx, whose completion is signalled on that k-block's
         // A-stage barrier (one commit per k-block releases both)
         if (kb >= p.nsx) {
@@ -218,7 +223,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
           if (!mbar_wait_bounded(&a_empty[kp % kNA], (uint32_t)((kp / kNA) & 1), p.err, 1)) break;
         }
         mbar_expect_tx(&full_x[s], X_BYTES);
-        tma_load_2d(xst + (size_t)s * X_BYTES, &xmap, &full_x[s], kb * kBK, tok0);
+        tma_load_2d(xst + (size_t)s * X_BYTES, &xmap, &full_x[s], (kbz0 + kb) * kBK, tok0);
         if (++s == p.nsx) s = 0;
       }
     }
@@ -226,10 +231,10 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
+      for (int kb = 0; kb < nkb; ++kb) {
         if (!mbar_wait_bounded(&empty_w[s], ph ^ 1u, p.err, 7)) break;
         mbar_expect_tx(&full_w[s], W_BYTES);
-        tma_load_2d(wst + (size_t)s * (W_BYTES / 4), &wmap, &full_w[s], n0, kb * RS);
+        tma_load_2d(wst + (size_t)s * (W_BYTES / 4), &wmap, &full_w[s], n0, (kbz0 + kb) * RS);
         if (++s == p.nsw) { s = 0; ph ^= 1u; }
       }
     }
@@ -248,7 +253,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       // ring cursors advance NI stages per iteration (no runtime division on the issuing thread)
       int s = me % p.nsx, sa = me;
       uint32_t ph = (uint32_t)((me / p.nsx) & 1), pha = 0;
-      for (int kb = me; kb < p.kblocks && ok; kb += NI) {
+      for (int kb = me; kb < nkb && ok; kb += NI) {
         ok = mbar_wait_bounded(&full_x[s], ph, p.err, 2);
         TC_STAMP(kb, 4);
         ok = ok && mbar_wait_bounded(&a_full[sa], pha, p.err, 3);
@@ -332,13 +337,14 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     int s = par % kNS;
     uint32_t ph = (uint32_t)((par / kNS) & 1);
     constexpr int kDqThreads = kDqWarps * kDqPar * 32;
-    for (int c = 0; c < p.nchunks; ++c) {
+    const int nchunks = (nkb + p.kbc - 1) / p.kbc;
+    for (int c = 0; c < nchunks; ++c) {
     // ---- group tables of this chunk's k-blocks for the CTA's 128 columns: loaded by the dequant warps only, so the first
     // chunk's load latency overlaps the first TMA round trips; later chunks cost one pipeline bubble each ----
-    const int kb0 = c * p.kbc, kb1 = min(p.kblocks, kb0 + p.kbc);
+    const int kb0 = c * p.kbc, kb1 = min(nkb, kb0 + p.kbc);
     {
-      gbase = (kb0 * kBK) / p.L.group;
-      const int gcount = ((kb1 * kBK - 1) / p.L.group) - gbase + 1;
+      gbase = ((kbz0 + kb0) * kBK) / p.L.group;
+      const int gcount = (((kbz0 + kb1) * kBK - 1) / p.L.group) - gbase + 1;
       if (c > 0) asm volatile("bar.sync 8, %0;" ::"n"(kDqThreads) : "memory");       // every warp is done with the previous tables
       for (int idx = tid; idx < gcount * kBN; idx += kDqThreads) {
         const int g = gbase + idx / kBN, nn = idx % kBN;
@@ -374,7 +380,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       __syncwarp();
       mbar_arrive_lane0(&empty_w[s], lane);
       uint32_t a[16];
-      const int k0 = kb * kBK + 32 * half;
+      const int k0 = (kbz0 + kb) * kBK + 32 * half;
       if (p.group32) {                                   // the 32 k of this half-stage share one group (warp-uniform)
         const int gi = group_at(k0);
         if (gi != gcur) { gcur = gi; load_group(gi); }
@@ -414,7 +420,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     for (int c0 = eidx * 32; c0 < TT && ok; c0 += 64 * kDqPar) {
       uint32_t v[32];
       tc_ld32(tmem + lane_addr + c0, v);
-      if (NI == 2 && p.kblocks > 1) {             // the second issuer's accumulator exists only if it had a k-block
+      if (NI == 2 && nkb > 1) {                   // the second issuer's accumulator exists only if it had a k-block
         uint32_t v2[32];
         tc_ld32(tmem + lane_addr + TT + c0, v2);
         tc_wait_ld();
@@ -422,6 +428,15 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
       } else {
         tc_wait_ld();
+      }
+      if (p.ksplit > 1) {                         // split-K: fp32 partial tile of this split, coalesced along n
+        float* slab = p.partial + (size_t)blockIdx.z * (size_t)p.M * p.L.N;
+        if (n0 + n < p.L.N) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (tok0 + c0 + i < p.M) slab[(size_t)(tok0 + c0 + i) * p.L.N + n0 + n] = __uint_as_float(v[i]);
+        }
+        continue;
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) stg[(size_t)i * (kBN + 8) + n] = __float2half_rn(__uint_as_float(v[i]) + bias);
@@ -438,6 +453,38 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         }
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + eidx) : "memory");
+    }
+    if (p.ksplit > 1) {
+      // last-arriving split of this output tile sums the slabs in split order (deterministic), adds bias, stores fp16
+      constexpr int kDqT = kDqWarps * kDqPar * 32;
+      __threadfence();
+      asm volatile("bar.sync 8, %0;" ::"n"(kDqT) : "memory");
+      unsigned int* cnt = p.counters + (blockIdx.y * gridDim.x + blockIdx.x);
+      if (tid == 0) {
+        const unsigned int old = atomicAdd(cnt, 1u);
+        tmem_slot[1] = (old == (unsigned int)p.ksplit - 1u) ? 1u : 0u;
+        if (old == (unsigned int)p.ksplit - 1u) *cnt = 0u;
+      }
+      asm volatile("bar.sync 8, %0;" ::"n"(kDqT) : "memory");
+      if (tmem_slot[1]) {
+        __threadfence();
+        const int rows = min(TT, p.M - tok0);
+        // nvcc hoists a __ldg above its null check (seen as an unpredicated LDG.CONSTANT): read through a pointer that is
+        // always valid (row 0 of the scales when there is no bias) and select afterwards
+        const bool has_bias = p.L.bias != nullptr;
+        const __half* bsrc = has_bias ? p.L.bias : p.L.s;
+        for (int idx = tid; idx < rows * kBN; idx += kDqT) {
+          const int tok = tok0 + idx / kBN, nn = n0 + idx % kBN;
+          if (nn < p.L.N) {
+            float acc = 0.f;
+            for (int z = 0; z < p.ksplit; ++z) acc += __ldcg(p.partial + ((size_t)z * p.M + tok) * p.L.N + nn);
+            const float bv = __half2float(bsrc[nn]);
+            if (has_bias) acc += bv;
+            const __half h = __float2half_rn(acc);
+            for (int qd = 0; qd < p.out.n; ++qd) p.out.y[qd][(size_t)tok * p.ldy + p.n_offset + nn] = h;
+          }
+        }
+      }
     }
     tc_fence_before();
   }
@@ -492,7 +539,24 @@ bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t l
   return get_encode() != nullptr && M >= 1;
 }
 
-size_t gemm_tc_workspace(const LayerView&, int64_t) { return 0; }
+// Split-K for small M (one token tile): a 128-column CTA is bound by its own dequant rate (~8192 weights per ~400
+// cycles), so N / 128 CTAs leave most SMs idle; splitting K fills them (K = 14336, N = 4096, M = 16: 67 -> ~17 us).
+static int g_tc_splitk = 1;               // B200Q_GEMM_SPLITK=0 / option "gemm_splitk"
+void gemm_tc_set_splitk(int on) { g_tc_splitk = on; }
+static int tc_ksplit(const LayerView& L, int64_t M) {
+  if (!g_tc_splitk || M > 64) return 1;
+  const int tiles = (L.N + kBN - 1) / kBN, kblocks = L.K / kBK;
+  int ks = 148 / tiles;
+  if (ks > 8) ks = 8;
+  if (ks > kblocks / 8) ks = kblocks / 8;
+  while (ks > 1 && (ks - 1) * ((kblocks + ks - 1) / ks) >= kblocks) --ks;
+  if (tiles > (int)(kCounterBytes / 4)) return 1;
+  return ks < 2 ? 1 : ks;
+}
+size_t gemm_tc_workspace(const LayerView& L, int64_t M) {
+  const int ks = tc_ksplit(L, M);
+  return ks > 1 ? kCounterBytes + (size_t)ks * (size_t)M * (size_t)L.N * sizeof(float) : 0;
+}
 
 template <int TT, int BITS, bool FZ, bool DBG = false>
 static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
@@ -527,6 +591,14 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   if (peers) p.out = *peers; else { p.out.n = 1; p.out.y[0] = a.y; }
   p.ldy = a.ldy; p.n_offset = a.n_offset;
   p.kblocks = L.K / kBK;
+  p.ksplit = tc_ksplit(L, a.M);
+  p.kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;
+  p.partial = nullptr; p.counters = nullptr;
+  if (p.ksplit > 1) {
+    if (!a.workspace || a.workspace_bytes < gemm_tc_workspace(L, a.M)) return cudaErrorInvalidValue;
+    p.counters = reinterpret_cast<unsigned int*>(a.workspace);
+    p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + kCounterBytes);
+  }
   p.gshift = -1;
   p.group32 = (L.group % 32 == 0) ? 1 : 0;
   if ((L.group & (L.group - 1)) == 0) { int sh = 0; while ((1 << sh) < L.group) ++sh; p.gshift = sh; }
@@ -572,7 +644,7 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   for (int i = 0; i < p.out.n; ++i)
     if (((uintptr_t)p.out.y[i] & 15) != 0) return cudaErrorInvalidValue;
   if ((a.ldy % 8) != 0 || (a.n_offset % 8) != 0) return cudaErrorInvalidValue;     // 16-byte epilogue stores
-  dim3 grid((L.N + kBN - 1) / kBN, (a.M + TT - 1) / TT);
+  dim3 grid((L.N + kBN - 1) / kBN, (a.M + TT - 1) / TT, p.ksplit);
   count_launch();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;

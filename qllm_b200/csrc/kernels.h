@@ -108,6 +108,7 @@ size_t gemm_tc_workspace(const LayerView& L, int64_t M);
 cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers);
 void gemm_tc_set_tt256_min_m(int m);
 void gemm_tc_set_pdl(int on);
+void gemm_tc_set_splitk(int on);
 void gemm_tc_set_debug(unsigned long long* buf);
 
 }  // namespace b200q

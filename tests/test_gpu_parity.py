@@ -543,3 +543,35 @@ def test_tcgen05_gemm_long_k_small_groups_chunked_tables(layout, bits, gs, K, N,
     x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
     y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
     assert rel_err(y, oracle_forward(L, x)) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout,bits,gs,K,N", [("GPTQ", 4, 128, 4096, 512), ("GPTQ", 4, 128, 11008, 512), ("HQQ", 4, 64, 8192, 256),
+                                                ("GPTQ", 8, 128, 4096, 384), ("MARLIN", 4, 128, 4096, 512)])
+@pytest.mark.parametrize("M", [9, 33, 64])
+def test_tcgen05_gemm_split_k_small_m(layout, bits, gs, K, N, M):
+    """M <= 64: K is split over gridDim.z so that every SM dequantises (partial fp32 tiles, last-arriver reduction in
+    split order): same answer as the oracle, bit-identical run to run, arrival counters left zeroed, and equal (to
+    fp32 summation order) to the unsplit kernel."""
+    import qllm_b200
+    from qllm_b200 import q_layers
+    L = O.make_layer(layout, bits, gs, K, N, seed=K + N + M, bias=(M == 33), float_zeros=(layout == "HQQ"))
+    layer = layer_from_dict(L)
+    x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+    xd = torch.from_numpy(x).cuda()
+    y1 = layer(xd)
+    y2 = layer(xd)
+    torch.cuda.synchronize()
+    ref = oracle_forward(L, x)
+    assert rel_err(y1.float().cpu().numpy(), ref) < TOL
+    assert torch.equal(y1, y2)
+    for ws in q_layers._workspaces.values():
+        assert int(ws[:4096].count_nonzero()) == 0
+    qllm_b200.lib.b200q_debug_set_option(b"gemm_splitk", 0.0)
+    try:
+        y0 = layer(xd)
+        torch.cuda.synchronize()
+    finally:
+        qllm_b200.lib.b200q_debug_set_option(b"gemm_splitk", 1.0)
+    assert rel_err(y0.float().cpu().numpy(), ref) < TOL
+    assert (y0.float() - y1.float()).abs().max().item() <= 2e-3 * float(np.abs(ref).max())
