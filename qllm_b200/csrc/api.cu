@@ -141,7 +141,9 @@ static int select(const LayerView& V, int64_t M, const __half* x, int64_t ldx, i
   }
   if (M <= kGemvMaxM && decode_supported(V, (int)M, x, ldx)) return KERNEL_GEMV_MMA;
   if (M > kGemvMaxM && gemm_tc_supported(V, M, x, ldx)) return KERNEL_GEMM_TC;
-  if (M <= kGemvMaxM) return KERNEL_GENERIC;
+  // no decode kernel for this (layout, bits, group): the split-K GEMM streams the weights with every SM, the generic
+  // kernel is the per-element fallback (3-bit, M = 1: 542 us generic vs the GEMM's tens of us)
+  if (M <= kGemvMaxM) return (force == 0 && gemm_tc_supported(V, M, x, ldx)) ? KERNEL_GEMM_TC : KERNEL_GENERIC;
   if (gemm_tc_supported(V, M, x, ldx)) return KERNEL_GEMM_TC;
   return KERNEL_GENERIC;   // chunked over 16-row slabs: slow, but no configuration is refused
 }

@@ -204,8 +204,8 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (tid == 0) TC_STAMP(p.kblocks, 1);                                                        // barriers + TMEM ready
-  constexpr int P = 32 / BITS;                     // k values per packed word
-  constexpr int RS = kBK / P;                      // packed rows per stage
+  constexpr int P = 32 / BITS;                     // k values per packed word (3-bit: 32 values straddle three words)
+  constexpr int RS = kBK * BITS / 32;              // packed rows per stage
   constexpr int WH = RS / 2;                       // words per column per half-stage (32 k)
   constexpr uint32_t X_BYTES = TT * kBK * 2, W_BYTES = RS * kBN * 4;
   constexpr int NI = (TT <= 128) ? 2 : 1;           // MMA-issuing threads (k-blocks i, i + NI, ...), one accumulator each
@@ -299,7 +299,9 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         z2 = dup_half(reinterpret_cast<const __half*>(zq)[gi * kBN + n]);
         c_lo = MAGIC; c_hi = 0xD400D400u;
       } else {
-        const uint32_t z = (((zq_lane[gi * (kBN * BITS / 32)] >> (zbit & 31)) & ZMASK) + (uint32_t)p.L.zero_bias) & ZMASK;
+        uint32_t zraw = zq_lane[gi * (kBN * BITS / 32)] >> (zbit & 31);
+        if (BITS == 3 && (zbit & 31) > 29) zraw |= zq_lane[gi * (kBN * BITS / 32) + 1] << (32 - (zbit & 31));   // field straddles two words
+        const uint32_t z = ((zraw & ZMASK) + (uint32_t)p.L.zero_bias) & ZMASK;
         c_lo = (0x6400u | z) * 0x00010001u;
         c_hi = (0xD400u + (z << 4)) * 0x00010001u;
       }
@@ -381,7 +383,18 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
       mbar_arrive_lane0(&empty_w[s], lane);
       uint32_t a[16];
       const int k0 = (kbz0 + kb) * kBK + 32 * half;
-      if (p.group32) {                                   // the 32 k of this half-stage share one group (warp-uniform)
+      if (BITS == 3) {
+        // 32 values in three words, LSB-first bit-stream (compress_weight.py:27-43): pair j = (k_2j, k_2j+1) starts at bit 6 j;
+        // (v & 7) | ((v << 13) & 0x70000) | 0x64006400 = the fp16 pair (1024 + q_2j, 1024 + q_2j+1); group % 32 == 0
+        const int gi = group_at(k0);
+        if (gi != gcur) { gcur = gi; load_group(gi); }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int b = 6 * j, wi = b >> 5, o = b & 31;
+          const uint32_t v = (o > 26) ? __funnelshift_r(w[wi], w[wi < WH - 1 ? wi + 1 : wi], o) : (w[wi] >> o);
+          a[j] = fin_lo((v & 7u) | ((v << 13) & 0x00070000u) | MAGIC);
+        }
+      } else if (p.group32) {                            // the 32 k of this half-stage share one group (warp-uniform)
         const int gi = group_at(k0);
         if (gi != gcur) { gcur = gi; load_group(gi); }
 #pragma unroll
@@ -532,8 +545,8 @@ static int pick_tt(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : (M >= g_tc
 
 bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t ldx) {
   if (!(L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) || L.g_idx || L.x_perm) return false;
-  if (L.bits != 2 && L.bits != 4 && L.bits != 8) return false;
-  if (L.group % (32 / L.bits) != 0) return false;                         // a packed word never straddles two groups
+  if (L.bits != 2 && L.bits != 3 && L.bits != 4 && L.bits != 8) return false;
+  if (L.bits == 3 ? (L.group % 32 != 0 || L.N % 32 != 0) : (L.group % (32 / L.bits) != 0)) return false;   // a packed word (3-bit: a 32-value pack) never straddles two groups
   if (L.K % kBK != 0 || L.N % 8 != 0 || L.group % 8 != 0 || L.K % L.group != 0) return false;
   if (((uintptr_t)x & 15) != 0 || (ldx % 8) != 0 || ((uintptr_t)L.qw & 15) != 0 || (L.N % 8) != 0) return false;
   return get_encode() != nullptr && M >= 1;
@@ -672,6 +685,7 @@ cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers) {
     default: return (fz ? tc_launch<128, BITS, true>(a, peers) : tc_launch<128, BITS, false>(a, peers));             \
   }
   if (a.L.bits == 2) { B200Q_TC_DISPATCH(2) }
+  if (a.L.bits == 3) { B200Q_TC_DISPATCH(3) }
   if (a.L.bits == 8) { B200Q_TC_DISPATCH(8) }
   B200Q_TC_DISPATCH(4)
 #undef B200Q_TC_DISPATCH

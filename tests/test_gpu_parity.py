@@ -575,3 +575,27 @@ def test_tcgen05_gemm_split_k_small_m(layout, bits, gs, K, N, M):
         qllm_b200.lib.b200q_debug_set_option(b"gemm_splitk", 1.0)
     assert rel_err(y0.float().cpu().numpy(), ref) < TOL
     assert (y0.float() - y1.float()).abs().max().item() <= 2e-3 * float(np.abs(ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout,gs,K,N", [("GPTQ", 64, 1024, 256), ("GPTQ", 128, 4096, 384), ("HQQ", 64, 2048, 256), ("GPTQ", 32, 512, 160)])
+@pytest.mark.parametrize("M", [1, 5, 16, 200])
+def test_three_bit_layers_run_on_the_tensor_core_gemm(layout, gs, K, N, M):
+    """3-bit (32 values straddling three words) has a tcgen05 producer; with no 3-bit decode kernel, M <= 8 takes the
+    split-K GEMM as well instead of the per-element generic kernel."""
+    import ctypes
+    import qllm_b200
+    L = O.make_layer(layout, 3, gs, K, N, seed=K + N + M, bias=(M == 5), float_zeros=(layout == "HQQ"))
+    layer = layer_from_dict(L)
+    assert qllm_b200.lib.b200q_select_kernel(ctypes.byref(layer._descriptor()), M) == 2
+    x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+    y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+    assert rel_err(y, oracle_forward(L, x)) < TOL
+    if M == 1:                                    # one-hot rows read W back bit-exactly through the 3-bit unpack
+        W = O.dequant(L["q"], L["z"], L["s"], L["g_idx"], "engine").astype(np.float16)
+        for k in (0, 31, 32, K - 1):
+            e = torch.zeros(1, K, dtype=torch.float16, device="cuda")
+            e[0, k] = 1.0
+            got = layer(e).cpu().numpy()[0]
+            want = W[k] if L["bias"] is None else (W[k].astype(np.float32) + L["bias"].astype(np.float32)).astype(np.float16)
+            assert np.array_equal(got, want)
