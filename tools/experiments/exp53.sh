@@ -1,0 +1,13 @@
+#!/bin/bash
+# N=8 check of the fused sharded bench (run with gpurun --gpus 8)
+O=gpurun_out/e53; mkdir -p $O
+fmt='
+import sys, json
+for l in sys.stdin:
+    l = l.strip()
+    if not l.startswith("{"): continue
+    try:
+        d = json.loads(l); c = d["config"]; print(d["n_gpus"], "GPUs", round(d["value"],1), "tok/s", round(d["ms_per_step"],3), "ms  e2e", round(d["e2e"]["value"],1), "|", c.get("parallelism"), "| eq", c.get("replicas_equal"), "timeouts", c.get("peer_wait_timeouts"), "err", c.get("fused_sharded_error"))
+    except Exception as e: print("ERR", l[:300])
+'
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 100 --warmup 3 > $O/n8.log 2>&1; grep -i "error\|Traceback" $O/n8.log | head -5; python -c "$fmt" < $O/n8.log | tee -a $O/scale.txt
