@@ -114,3 +114,19 @@ def test_autogptq_zero_fixup_host():
     layer.qzeros = torch.from_numpy(d["autogptq_stored"].copy())
     layer.handle_qzeros_for_autogptq()
     assert np.array_equal(layer.qzeros.numpy(), d["autogptq_fixed"])
+
+
+def test_bench_accounting_matches_the_survey_figures():
+    """bench.py's algorithmic bytes are SURVEY section 8(d)'s: 0.51953 B/weight at int4 g128, 8,732,672 B for 4096^2 at M = 1,
+    3.3645e9 B per Llama-2-7B token; column shards tile the output exactly."""
+    import bench
+    assert bench.alg_bytes(4096, 4096, 1) == 8732672
+    assert bench.alg_bytes(4096, 11008, 1) == 23455232
+    total = bench.BLOCKS * sum(bench.alg_bytes(K, N, 1) for _, K, N in bench.SHAPES)
+    assert abs(total - 3.3645e9) / 3.3645e9 < 1e-3
+    for world in (1, 2, 4, 8):
+        for _, _, N in bench.SHAPES:
+            cuts = [bench.shard_cols(N, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == N
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            assert all((c1 - c0) % 32 == 0 and c1 > c0 for c0, c1 in cuts)
