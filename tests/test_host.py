@@ -130,3 +130,21 @@ def test_bench_accounting_matches_the_survey_figures():
             assert cuts[0][0] == 0 and cuts[-1][1] == N
             assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
             assert all((c1 - c0) % 32 == 0 and c1 > c0 for c0, c1 in cuts)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/b200q.h compiles as C99 (no C++-isms, no torch types) and a C program links
+    against libb200q.so -- what a cgo / JNI / ctypes binding relies on."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_b200q.c"
+    src.write_text('#include "b200q.h"\n'
+                   "int main(void) { b200q_layer l; b200q_peer_sync s; (void)l; (void)s;\n"
+                   "  return (b200q_version() == B200Q_VERSION && b200q_gemv_max_m() > 0 && b200q_strerror(B200Q_ERR_SHAPE) != 0) ? 0 : 1; }\n")
+    libdir = os.path.join(ROOT, "qllm_b200")
+    exe = tmp_path / "use_b200q"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-L", libdir, "-lb200q", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
