@@ -235,6 +235,37 @@ class DecodeStep:
         return h
 
 
+class ChainDecodeStep:
+    """The same 224 QuantLinear calls as DecodeStep, recorded once as b200q decode chains (b200q_chain_plan) and replayed
+    with b200q_chain_run: one persistent launch per `span` decoder blocks (span = 32: the whole token is one launch).
+    Every layer's fp16 output is still written to its buffer, exactly as the per-call path does."""
+
+    def __init__(self, blocks, dev, M, span):
+        import torch
+        import qllm_b200
+        self.M, self.fuse = M, True
+        f16 = dict(dtype=torch.float16, device=dev)
+        self.h = torch.zeros(M, HIDDEN, **f16)
+        # per-block output buffers (a real model's activations are distinct tensors per block as well)
+        self.chains, steps, x = [], [], self.h
+        for i, b in enumerate(blocks):
+            y = {n: torch.zeros(M, N, **f16) for n, _, N in SHAPES}
+            steps.append(([b["q"], b["k"], b["v"]], x, [y["q"], y["k"], y["v"]]))
+            steps.append(([b["o"]], y["v"], [y["o"]]))
+            steps.append(([b["gate"], b["up"]], y["o"], [y["gate"], y["up"]]))
+            steps.append(([b["down"]], y["gate"], [y["down"]]))
+            x = y["down"]
+            if (i + 1) % span == 0 or i + 1 == len(blocks):
+                self.chains.append(qllm_b200.DecodeChain(steps, M=M))
+                steps = []
+        self.out = x
+
+    def run(self, stream):
+        for c in self.chains:
+            c.run(stream)
+        return self.out
+
+
 class FusedShardedStep:
     """N > 1: every call is one b200q_linear_group_sharded launch -- this rank's column shards, stored into every
     rank's replica over NVLink, with the cross-GPU hand-off inside the kernels: tagged activations (flag-in-data:
@@ -330,6 +361,10 @@ def run_b200q(args, rank, world, local_rank):
         if ok.item() == 0:
             step = None
     fused_sharded = step is not None
+    chain_span = 0
+    if step is None and world == 1 and args.chain > 0:
+        step = ChainDecodeStep(blocks, dev, M, args.chain)
+        chain_span = args.chain
     if step is None:
         step = DecodeStep(blocks, dev, M, rank, world)
     h0 = (torch.randn(M, HIDDEN, generator=torch.Generator().manual_seed(7)) * 1.0).to(torch.float16)
@@ -396,7 +431,7 @@ def run_b200q(args, rank, world, local_rank):
     achieved = total_bytes * world / world / (ms_per_step * 1e-3) / 1e9      # whole-job algorithmic GB/s
     roofline = {"bound": "hbm", "achieved": achieved / world, "peak": P["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / world / P["hbm_gbs"], "traffic": None, "peak_source": P["source"],
-                "kernel": "gemv_imma_kernel (decode, IMMA.16832 on the K-packed re-layout)", "bytes_per_launch": total_bytes / launches_per_step,
+                "kernel": ("decode_chain_kernel (persistent, TMA ring + IMMA.16832)" if chain_span else "gemv_imma_kernel (decode, IMMA.16832 on the K-packed re-layout)"), "bytes_per_launch": total_bytes / launches_per_step,
                 "us_per_launch": ms_per_step * 1e3 / launches_per_step, "per_gpu": True}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -409,7 +444,7 @@ def run_b200q(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": "Llama-2-7B int4 g128 AWQ pack_mode=GEMM, batch=1 decode: the 224 QuantLinear layers of one token "
                                "in LlamaDecoderLayer dependency order (q|k|v -> o -> gate|up -> down)",
-                   "launches_per_step": int(launches_per_step), "sibling_groups": bool(step.fuse and world == 1),
+                   "launches_per_step": int(launches_per_step), "chain_blocks_per_launch": chain_span, "sibling_groups": bool(step.fuse and world == 1),
                    "M": M, "layers": n_layers, "parallelism": (f"column-shard x{world}, all-gather + hand-off fused into the decode kernels (NVLink peer stores, "
                                     + ("tagged activations" if getattr(step, "tagged", False) else "counter post/wait") + ")" if fused_sharded
                                    else f"column-shard x{world} + NCCL all-gather per layer") if world > 1 else "single GPU",
@@ -465,6 +500,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200q", choices=["b200q", "reference"])
+    ap.add_argument("--chain", type=int, default=32,
+                    help="decoder blocks per decode-chain launch (b200q_chain_run); 0 = one launch per sibling group (b200q_linear_group)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prefill", action="store_true")
     args = ap.parse_args()

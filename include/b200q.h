@@ -185,6 +185,36 @@ int b200q_peer_wait(const b200q_peer_sync* sync, b200q_stream_t stream);
 int b200q_peer_epoch_advance(uint64_t* epoch, b200q_stream_t stream);
 
 /*
+ * Decode chain (M <= 2): a recorded run of b200q_linear_group calls executed by ONE persistent launch.
+ * In the reference every QuantLinear.forward of a decode step is its own kernel launch (quant_linear_awq.py:142-148,
+ * quant_linear_gptq.py:55-85); at batch 1 a Llama-sized layer is 1-7 us of HBM streaming and a launch boundary costs as
+ * much again.  A chain keeps one CTA per SM alive across the layers: the packed weights of ALL steps stream through one
+ * shared-memory ring (TMA) without draining at layer boundaries, layers are separated by a grid-wide barrier, and a
+ * step whose x points into an output of the PREVIOUS step reads it without a round trip through a finished y.
+ * Each step has exactly the semantics of b200q_linear_group(layers, n_layers, x, M, ldx, y, ldy): every y[i] is
+ * written as fp16 (bias added) and is bit-identical to what a consumer inside the chain read.
+ *   plan:  host-side, once per (steps, M): fills `plan_host` (b200q_chain_plan_bytes() bytes: tensor maps, schedule)
+ *          and reports the workspace size; the caller copies the blob to device memory (64-byte aligned).
+ *   run:   one kernel launch on `stream`; `workspace` zero on first use and left with its first 4 KB zeroed.
+ * Supported: 4-bit K-packed layers (GPTQ / HQQ layouts with g_idx == NULL, optionally x_perm; AWQ-GEMM / Marlin through
+ * b200q_repack_gptq4), group 64, 128 or a multiple of 256, K % 256 == 0, N % 32 == 0.  b200q_chain_plan returns
+ * B200Q_ERR_UNSUPPORTED otherwise (run the steps through b200q_linear_group instead).
+ */
+typedef struct b200q_chain_step {
+  const b200q_layer* const* layers; /* [n_layers] sibling layers sharing x (same K, group, layout) */
+  int32_t n_layers;                 /* 1..3 */
+  const void* x;                    /* fp16 [M, ldx] */
+  int64_t ldx;
+  void* const* y;                   /* [n_layers] fp16 [M, ldy[i]] */
+  const int64_t* ldy;
+} b200q_chain_step;
+size_t b200q_chain_plan_bytes(const b200q_chain_step* steps, int32_t n_steps, int64_t M); /* 0: unsupported / invalid */
+int b200q_chain_plan(const b200q_chain_step* steps, int32_t n_steps, int64_t M, void* plan_host, size_t plan_bytes,
+                     size_t* workspace_bytes);
+int b200q_chain_run(const void* plan_host, const void* plan_device, void* workspace, size_t workspace_bytes,
+                    b200q_stream_t stream);
+
+/*
  * W_out[K, N] (fp16, row-major, ld = N) = dequant(layer), rounded once: fp16((q - z) * s).
  * Replaces ort_ops.dequant (csrc/ort_cuda/ort_ops.cc:58-92 -> dq_gemv.cu:696-725) for every
  * layout and bit width, with or without g_idx.
@@ -237,6 +267,11 @@ uint64_t b200q_launch_count(void);
  * stamps (start, prefetch issued, upstream done, operands in smem, math done, cluster reduced, stored, -)
  * appended launch after launch until `bytes` are used.  NULL (default) disables. */
 void b200q_debug_set_timeline(void* device_buf, size_t bytes);
+
+/* Diagnostic only: decode-chain phase stamps, 16 x u64 per (step, CTA): consumer warp 0 {step start, x ready, digits done,
+ * own units done, all warps done, partial sums stored}, sync warp {grid barrier passed, y written}, producer {first slab
+ * issued, last slab issued, ns stalled on a full ring}.  device_buf: n_steps * SMs * 128 bytes, or NULL to disable. */
+void b200q_debug_set_chain_timeline(void* device_buf);
 
 /* Diagnostic only: the decode kernel's launch plan for this layer at batch M (host-side, no CUDA call):
  * out = {cluster size (CTAs that split K), column tiles, dynamic shared memory bytes per CTA, k-steps}. */

@@ -16,6 +16,8 @@ def dequantize_blockwise(qweight, scales, qzeros, groupsize, bits, in_features):
     """int32 [K*b/32, N], scales [G,N], qzeros int32 [G, N*b/32] -> W [K, N] in scales.dtype.
     Same arithmetic as the reference: W = s*q - s*z with q, z unpacked by shift/and (2/4/8-bit)."""
     assert bits in (2, 4, 8)
+    if groupsize == -1:                              # per-channel: one group spans K (quant_linear_gptq.py:98)
+        groupsize = in_features
     per = 32 // bits
     shifts = torch.arange(0, 32, bits, dtype=torch.int32)
     mask = (1 << bits) - 1

@@ -7,6 +7,7 @@ from ._lib import lib, check, Layer  # noqa: F401  (raises ImportError when the 
 from .q_layers import (QuantLinearGPTQ, QuantLinearHQQ, QuantLinearMarlin, WQLinear_GEMM,  # noqa: F401
                        fuse_siblings, linear_group, make_mixbits_quant_linear, select_quant_linear)
 
+from .chain import DecodeChain  # noqa: F401,E402
 from .loader import from_quantized, load_quant_config, save_quantized  # noqa: F401,E402  (qllm --load for this engine)
 
 __version__ = "0.1.0"

@@ -19,6 +19,12 @@ class Layer(ctypes.Structure):
                 ("g_idx", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("x_perm", ctypes.c_void_p)]
 
 
+class ChainStep(ctypes.Structure):
+    """struct b200q_chain_step"""
+    _fields_ = [("layers", ctypes.POINTER(ctypes.POINTER(Layer))), ("n_layers", ctypes.c_int32), ("x", ctypes.c_void_p),
+                ("ldx", ctypes.c_int64), ("y", ctypes.POINTER(ctypes.c_void_p)), ("ldy", ctypes.POINTER(ctypes.c_int64))]
+
+
 class PeerSync(ctypes.Structure):
     """struct b200q_peer_sync"""
     _fields_ = [("n_peers", ctypes.c_int32), ("self_rank", ctypes.c_int32), ("counters", ctypes.POINTER(ctypes.c_void_p)),
@@ -30,7 +36,8 @@ class PeerSync(ctypes.Structure):
 EXPORTS = ["b200q_linear", "b200q_linear_group", "b200q_gemv", "b200q_gemm", "b200q_linear_sharded", "b200q_dequant", "b200q_unpack",
            "b200q_workspace_bytes", "b200q_gemv_max_m", "b200q_select_kernel", "b200q_launch_count",
            "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4", "b200q_debug_decode_plan", "b200q_debug_set_option", "b200q_linear_group_sharded", "b200q_sharded_posts",
-           "b200q_peer_epoch_advance", "b200q_peer_wait", "b200q_peer_untag", "b200q_repack_actorder"]
+           "b200q_peer_epoch_advance", "b200q_peer_wait", "b200q_peer_untag", "b200q_repack_actorder",
+           "b200q_chain_plan_bytes", "b200q_chain_plan", "b200q_chain_run", "b200q_debug_set_chain_timeline"]
 
 
 def _load():
@@ -70,6 +77,12 @@ def _load():
     lib.b200q_peer_wait.restype = ctypes.c_int
     lib.b200q_peer_epoch_advance.argtypes = [P, P]
     lib.b200q_peer_epoch_advance.restype = ctypes.c_int
+    lib.b200q_chain_plan_bytes.argtypes = [ctypes.POINTER(ChainStep), ctypes.c_int32, I64]
+    lib.b200q_chain_plan_bytes.restype = SZ
+    lib.b200q_chain_plan.argtypes = [ctypes.POINTER(ChainStep), ctypes.c_int32, I64, P, SZ, ctypes.POINTER(SZ)]
+    lib.b200q_chain_plan.restype = ctypes.c_int
+    lib.b200q_chain_run.argtypes = [P, P, P, SZ, P]
+    lib.b200q_chain_run.restype = ctypes.c_int
     lib.b200q_dequant.argtypes = [LP, P, P]
     lib.b200q_dequant.restype = ctypes.c_int
     lib.b200q_unpack.argtypes = [LP, P, P, P]
@@ -92,6 +105,8 @@ def _load():
     lib.b200q_debug_decode_plan.restype = ctypes.c_int
     lib.b200q_debug_set_option.argtypes = [ctypes.c_char_p, ctypes.c_double]
     lib.b200q_debug_set_option.restype = ctypes.c_int
+    lib.b200q_debug_set_chain_timeline.argtypes = [P]
+    lib.b200q_debug_set_chain_timeline.restype = None
     lib.b200q_debug_set_timeline.argtypes = [P, SZ]
     lib.b200q_debug_set_timeline.restype = None
     return lib

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -28,6 +29,21 @@ static int cuda_status(cudaError_t e) {
   g_last_cuda.store((int)e);
   (void)cudaGetLastError();
   return B200Q_ERR_CUDA;
+}
+
+// tcgen05 / TMA / cluster kernels exist for sm_100 only: checked once per device, B200Q_ERR_ARCH otherwise
+static int check_arch() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cuda_status(cudaGetLastError());
+  int c = cached[dev & 63].load(std::memory_order_relaxed);
+  if (c == 0) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return cuda_status(cudaGetLastError());
+    c = (major == 10) ? 1 : 2;
+    cached[dev & 63].store(c, std::memory_order_relaxed);
+  }
+  return c == 1 ? B200Q_OK : B200Q_ERR_ARCH;
 }
 
 static int validate(const b200q_layer* L) {
@@ -167,6 +183,8 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   const int v = validate(layer);
   if (v != B200Q_OK) return v;
   if (!x || (!y && !peers)) return B200Q_ERR_NULL;
+  const int arch = check_arch();
+  if (arch != B200Q_OK) return arch;
   if (M < 1 || ldx < layer->K || ldy < n_offset + layer->N) return B200Q_ERR_SHAPE;
   gemv_variant();                          // one-time parse of the B200Q_* switches
   LayerView V = make_view(layer);
@@ -419,6 +437,64 @@ int b200q_linear_group_sharded(const b200q_layer* const* layers, int32_t n_layer
   return B200Q_ERR_UNSUPPORTED;                             // only the integer-path decode kernel carries the hand-off
 }
 
+// ---- decode chain: a recorded run of b200q_linear_group calls as one persistent launch (decode_chain.cu) ----
+static int chain_collect(const b200q_chain_step* steps, int32_t n_steps, int64_t M, std::vector<LinearArgs>& flat,
+                         std::vector<const LinearArgs*>& ptrs, std::vector<int>& counts) {
+  if (!steps) return B200Q_ERR_NULL;
+  if (n_steps < 1 || n_steps > 4096 || M < 1 || M > 2) return B200Q_ERR_SHAPE;
+  flat.resize((size_t)n_steps * kMaxGroupLayers);
+  ptrs.resize(n_steps);
+  counts.resize(n_steps);
+  for (int g = 0; g < n_steps; ++g) {
+    const b200q_chain_step& S = steps[g];
+    if (!S.layers || !S.x || !S.y || !S.ldy) return B200Q_ERR_NULL;
+    if (S.n_layers < 1 || S.n_layers > kMaxGroupLayers) return B200Q_ERR_SHAPE;
+    for (int j = 0; j < S.n_layers; ++j) {
+      const int v = validate(S.layers[j]);
+      if (v != B200Q_OK) return v;
+      if (!S.y[j]) return B200Q_ERR_NULL;
+      if (S.ldx < S.layers[j]->K || S.ldy[j] < S.layers[j]->N) return B200Q_ERR_SHAPE;
+      LinearArgs& a = flat[(size_t)g * kMaxGroupLayers + j];
+      a = {};
+      a.L = make_view(S.layers[j]); a.x = (const __half*)S.x; a.ldx = S.ldx; a.M = (int)M; a.y = (__half*)S.y[j]; a.ldy = S.ldy[j];
+    }
+    ptrs[g] = &flat[(size_t)g * kMaxGroupLayers];
+    counts[g] = S.n_layers;
+  }
+  return B200Q_OK;
+}
+
+size_t b200q_chain_plan_bytes(const b200q_chain_step* steps, int32_t n_steps, int64_t M) {
+  std::vector<LinearArgs> flat;
+  std::vector<const LinearArgs*> ptrs;
+  std::vector<int> counts;
+  if (chain_collect(steps, n_steps, M, flat, ptrs, counts) != B200Q_OK) return 0;
+  size_t bytes = 0;
+  if (decode_chain_plan(ptrs.data(), counts.data(), n_steps, (int)M, nullptr, 0, &bytes, nullptr) != B200Q_OK) return 0;
+  return bytes;
+}
+
+int b200q_chain_plan(const b200q_chain_step* steps, int32_t n_steps, int64_t M, void* plan_host, size_t plan_bytes,
+                     size_t* workspace_bytes) {
+  if (!plan_host) return B200Q_ERR_NULL;
+  const int arch = check_arch();
+  if (arch != B200Q_OK) return arch;
+  std::vector<LinearArgs> flat;
+  std::vector<const LinearArgs*> ptrs;
+  std::vector<int> counts;
+  const int v = chain_collect(steps, n_steps, M, flat, ptrs, counts);
+  if (v != B200Q_OK) return v;
+  return decode_chain_plan(ptrs.data(), counts.data(), n_steps, (int)M, plan_host, plan_bytes, nullptr, workspace_bytes);
+}
+
+int b200q_chain_run(const void* plan_host, const void* plan_device, void* workspace, size_t workspace_bytes, b200q_stream_t stream) {
+  if (!plan_host || !plan_device || !workspace) return B200Q_ERR_NULL;
+  if (((uintptr_t)plan_device & 63) || ((uintptr_t)workspace & 15)) return B200Q_ERR_ALIGNMENT;
+  const cudaError_t e = launch_decode_chain(plan_host, plan_device, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) return B200Q_ERR_WORKSPACE;
+  return cuda_status(e);
+}
+
 int b200q_repack_actorder(const b200q_layer* layer, const int32_t* perm, void* qweight_out, b200q_stream_t stream) {
   const int v = validate(layer);
   if (v != B200Q_OK) return v;
@@ -520,6 +596,8 @@ int b200q_debug_set_option(const char* name, double value) {
   else if (n == "sync_flags") g_sync_flags = (int)value;
   else if (n == "gemm_pdl") gemm_tc_set_pdl((int)value);
   else if (n == "gemm_splitk") gemm_tc_set_splitk((int)value);
+  else if (n == "chain_ctas") decode_chain_set_option(0, (int)value);
+  else if (n == "chain_slots") decode_chain_set_option(1, (int)value);
   else return B200Q_ERR_UNSUPPORTED;
   return B200Q_OK;
 }
@@ -546,7 +624,11 @@ void b200q_debug_set_timeline(void* device_buf, size_t bytes) {
   gemv_rp_set_debug((unsigned long long*)device_buf, bytes / 8);
   gemv_stream_set_debug((unsigned long long*)device_buf, bytes / 8);
   gemv_imma_set_debug((unsigned long long*)device_buf, bytes / 8);
-  gemm_tc_set_debug(bytes >= 64 * 1024 ? (unsigned long long*)device_buf : nullptr);   // GEMM: CTA(0,0), 8 stamps per k-block
+  gemm_tc_set_debug(bytes >= 64 * 1024 ? (unsigned long long*)device_buf : nullptr);
+}
+/* diagnostic: per-(group, CTA) phase stamps of the decode chain kernel: 16 x u64 each, caller sizes the buffer (n_steps * SMs * 128 B) */
+void b200q_debug_set_chain_timeline(void* device_buf) {
+  decode_chain_set_debug((unsigned long long*)device_buf);   // GEMM: CTA(0,0), 8 stamps per k-block
 }
 int b200q_version(void) { return B200Q_VERSION; }
 

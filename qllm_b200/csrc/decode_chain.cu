@@ -1,0 +1,783 @@
+// Decode CHAIN kernel (M <= 2): a recorded sequence of b200q_linear_group calls executed by ONE persistent launch.
+//
+// Why: at batch 1 a Llama-sized QuantLinear is 1.3-7 us of HBM streaming, and the round-1 launch-per-layer kernels lose
+// as much again per launch to the serial chain "previous layer stored -> kernel boundary -> x loaded and split into
+// digits -> first weights consumed -> reduced -> stored" during which HBM idles (profiles/r1_decode_timeline_bench.txt),
+// plus 2-3 CTAs per SM of uneven work.  Here one CTA per SM lives for the whole chain:
+//
+//   * ONE producer thread per SM streams the packed weights of every layer of the chain, in order, through ONE
+//     shared-memory ring with TMA (3-D boxes: 64 columns x 256 k = 8 KB, 128-byte swizzle; the slab's scales and packed
+//     zeros ride behind it as two small boxes).  The ring does not drain at layer boundaries: while the consumers wait
+//     for a layer's activations, the next layer's weights keep arriving (~150 KB per SM, ~3.5 us of HBM time in flight);
+//   * the work of a group (sibling layers sharing x) is cut into slabs and every CTA takes an equal CONTIGUOUS range
+//     of (tile, k) slabs -- balanced to one slab (1-2 %) for any N, no cluster, no tail wave;
+//   * 16 consumer warps run the integer tensor path of gemv_imma.cu (IMMA.16832 on nibbles, activations as three
+//     base-128 digits, exact int32 accumulation per <= 128-k part, fp32 scale/zero fix-up per group);
+//   * split-K partial sums go to a small fp32 scratch (L2 resident); layers are separated by ONE grid-wide barrier
+//     (red.release.gpu + ld.acquire.gpu poll, ~1 us); the NEXT layer's x-load stage sums the partials, adds the bias and
+//     rounds to fp16 itself (same fixed order everywhere -> deterministic), so no reduction pass sits on the critical path.
+//     A finalizer warp writes the fp16 outputs y (what QuantLinear.forward returns) off the critical path.
+//
+// Replaces a run of ort_ops.gemv / gemm_forward_cuda calls (dq_gemv.cu:40-177, gemm_cuda_gen.cu:1102-1161) at M <= 2.
+#include <cuda.h>
+
+#include <cstring>
+#include <vector>
+
+#include "gemv_stream.cuh"
+
+namespace b200q {
+
+static constexpr int kChWarps = 16;                       // consumer warps
+static constexpr int kChThreads = 32 * (kChWarps + 2);    // + producer warp + sync/finalizer warp
+static constexpr int kSlabK = 256, kTileN = 64, kSlabBytes = 8192, kAuxBytes = 1024;
+static constexpr uint32_t kChMagic = 0xB2C4A117u;
+static constexpr uint32_t NIBM = 0x0f0f0f0fu;
+static constexpr int kCtrWord = 512, kExitWord = 513, kErrWord = 514;   // u32 words inside the 4 KB counter region
+
+struct alignas(64) ChLayer {
+  CUtensorMap wmap, smap, zmap;
+  const __half* bias;
+  __half* y;
+  int64_t ldy;
+  int32_t N, tile0, ntiles, pad_;
+};
+struct alignas(64) ChGroup {
+  ChLayer layer[kMaxGroupLayers];
+  int32_t n_layers, K, tiles, kc, U, group, pk, pps, gps, zfp16, zero_bias, tx_bytes;
+  int32_t ncta;                                // CTAs that share this group's slabs: min(grid, U)
+  int32_t region, smax, ncols;                 // this group's partial sums: P[region][smax][M][ncols] fp32
+  int32_t xmode;                               // 0: plain fp16 x; 1: partial sums of the previous group
+  const __half* x;
+  int64_t ldx;
+  const int32_t* xperm;
+  int32_t src_region, src_smax, src_ncols, src_pcol0;
+  const __half* src_bias;                      // bias of the source columns (already offset), or NULL
+  uint32_t src_tab_off, tab_off;               // byte offsets (from the plan base) of u32 [tiles] tables: c0 | cnt << 16
+  int32_t pad_[1];
+};
+struct ChHeader {
+  uint32_t magic, n_groups, M, n_cta, slots, max_tiles, smem_bytes, total_bytes;
+  uint32_t off_bars, off_digits, off_parts, off_red, off_tab, off_zpad, off_aux, off_ring;
+  uint32_t groups_off, region_floats, pad_[2];
+  uint64_t ws_bytes;
+};
+struct ChParams {
+  const char* plan;       // device copy of the plan blob
+  char* ws;
+  ChHeader h;
+  unsigned long long* dbg;
+};
+
+__device__ __forceinline__ void tma_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// every wait in this kernel is bounded (4 s): a wedged chain traps instead of hanging the GPU
+__device__ __noinline__ void ch_fail(char* ws, uint32_t code) {
+  reinterpret_cast<volatile uint32_t*>(ws)[kErrWord] = code;
+  __threadfence_system();
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity, char* ws, uint32_t code) {
+  if (mbar_try_a(bar, parity)) return;
+  unsigned long long t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_a(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      const unsigned long long now = st_gtime();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) ch_fail(ws, code);
+    }
+  }
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ldcg4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldcg2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldcg1(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldcg_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned short ldcg_u16(const void* p) {
+  unsigned short v;
+  asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kChWarps * 32) : "memory"); }
+
+__device__ __forceinline__ void imma_acc(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// fp16(sum of the source group's partials + bias) for 4 consecutive source columns (pc % 4 == 0): exactly what the
+// finalizer stores as y, summed in the same (slot) order
+__device__ __forceinline__ void ch_src4(const ChGroup* G, const char* plan, const float* P, int m, int M, int pc, float (&o)[4]) {
+  const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(plan + G->src_tab_off) + (pc >> 6));
+  const int cnt = (int)(e >> 16);
+  const float* base = P + (size_t)m * G->src_ncols + pc;
+  float4 a = ldcg4(base);
+  for (int s = 1; s < cnt; ++s) {
+    const float4 b = ldcg4(base + (size_t)s * M * G->src_ncols);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+}
+__device__ __forceinline__ float ch_src1(const ChGroup* G, const char* plan, const float* P, int m, int M, int pc) {
+  const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(plan + G->src_tab_off) + (pc >> 6));
+  const int cnt = (int)(e >> 16);
+  const float* base = P + (size_t)m * G->src_ncols + pc;
+  float a = ldcg1(base);
+  for (int s = 1; s < cnt; ++s) a += ldcg1(base + (size_t)s * M * G->src_ncols);
+  return a;
+}
+
+// diagnostic: 16 x u64 per (group, CTA): consumer warp 0 phases 0..5, sync warp 6..7, producer 8..10
+#define CH_STAMP(g, i) do { if (p.dbg && lane == 0) p.dbg[((size_t)(g) * gridDim.x + blockIdx.x) * 16 + (i)] = st_gtime(); } while (0)
+
+template <int MTOK>
+__global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __grid_constant__ ChParams p) {
+  extern __shared__ __align__(1024) char smem_raw[];
+  char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const ChHeader& H = p.h;
+  const int NS = (int)H.slots;
+  const uint32_t bars = smem_u32(smem + H.off_bars);
+  const uint32_t bar_full = bars, bar_empty = bars + 8u * 32u, bar_xready = bars + 8u * 64u, bar_cdone = bars + 8u * 65u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = blockIdx.x, ncta = gridDim.x;
+  const int NG = (int)H.n_groups;
+  const ChGroup* groups = reinterpret_cast<const ChGroup*>(p.plan + H.groups_off);
+  uint32_t* ctr = reinterpret_cast<uint32_t*>(p.ws);
+  float* Pbase = reinterpret_cast<float*>(p.ws + kCounterBytes);
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(reinterpret_cast<uint64_t*>(smem + H.off_bars) + i, 1);
+      mbar_init(reinterpret_cast<uint64_t*>(smem + H.off_bars) + 32 + i, 4);
+    }
+    mbar_init(reinterpret_cast<uint64_t*>(smem + H.off_bars) + 64, 1);
+    mbar_init(reinterpret_cast<uint64_t*>(smem + H.off_bars) + 65, kChWarps);
+    fence_mbar_init();
+  }
+  if (tid < 16) reinterpret_cast<uint32_t*>(smem + H.off_zpad)[tid] = 0u;
+  __syncthreads();
+  pdl_launch_dependents();
+
+  // =========================================== producer ===========================================
+  if (warp == 0) {
+    if (lane != 0) return;
+    const uint32_t ring = smem_u32(smem + H.off_ring), aux = smem_u32(smem + H.off_aux);
+    int slot = 0;
+    uint32_t round = 0;
+    for (int g = 0; g < NG; ++g) {
+      const ChGroup* G = groups + g;
+      const int U = G->U, KC = G->kc, nl = G->n_layers;
+      const int ng = G->ncta;
+      const int a = c < ng ? (int)((long long)c * U / ng) : 0, b = c < ng ? (int)((long long)(c + 1) * U / ng) : 0;
+      if (a >= b) continue;
+      CH_STAMP(g, 8);
+      unsigned long long stall = 0;
+      int tile = a / KC, kk = a - tile * KC, j = 0;
+      while (j + 1 < nl && tile >= G->layer[j + 1].tile0) ++j;
+      const int tx = G->tx_bytes, gps = G->gps, zf = G->zfp16;
+      const int grow_mul = (G->group >= kSlabK) ? 0 : gps;                 // group rows advanced per slab (group < 256)
+      const int gdiv = (G->group >= kSlabK) ? G->group / kSlabK : 1;       // slabs per group row (group >= 256)
+      for (int i = a; i < b; ++i) {
+        if (round > 0) {
+          if (p.dbg) {
+            const unsigned long long t0 = st_gtime();
+            mbar_wait_b(bar_empty + 8u * slot, (round - 1) & 1u, p.ws, 0x100u + g);
+            stall += st_gtime() - t0;
+          } else {
+            mbar_wait_b(bar_empty + 8u * slot, (round - 1) & 1u, p.ws, 0x100u + g);
+          }
+        }
+        const ChLayer* L = &G->layer[j];
+        const int tl = tile - L->tile0;
+        const uint32_t fb = bar_full + 8u * slot;
+        mbar_expect_tx_a(fb, (uint32_t)tx);
+        tma_3d(ring + (uint32_t)slot * kSlabBytes, &L->wmap, 0, 2 * tl, 32 * kk, fb);
+        const int grow = grow_mul ? kk * grow_mul : kk / gdiv;
+        tma_2d(aux + (uint32_t)slot * kAuxBytes, &L->smap, kTileN * tl, grow, fb);
+        tma_2d(aux + (uint32_t)slot * kAuxBytes + 512u, &L->zmap, zf ? kTileN * tl : 8 * tl, grow, fb);
+        if (++slot == NS) { slot = 0; ++round; }
+        if (++kk == KC) {
+          kk = 0;
+          ++tile;
+          if (j + 1 < nl && tile >= G->layer[j + 1].tile0) ++j;
+        }
+      }
+      CH_STAMP(g, 9);
+      if (p.dbg) p.dbg[((size_t)g * gridDim.x + blockIdx.x) * 16 + 10] = stall;
+    }
+    return;
+  }
+
+  // ====================================== sync / finalizer warp =====================================
+  if (warp == 1) {
+    pdl_wait();
+    for (int g = 0; g < NG; ++g) {
+      const ChGroup* G = groups + g;
+      mbar_wait_b(bar_cdone, (uint32_t)g & 1u, p.ws, 0x200u + g);          // this CTA's partial sums of group g are stored
+      if (lane == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + kCtrWord) : "memory");
+        const uint32_t target = (uint32_t)(g + 1) * (uint32_t)ncta;
+        unsigned long long t0 = 0;
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(ctr + kCtrWord) < target) {
+          if ((++spins & 1023u) == 0) {
+            const unsigned long long now = st_gtime();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) ch_fail(p.ws, 0x300u + g);
+          }
+        }
+        if (g + 1 < NG) mbar_arrive_n(bar_xready, 1);                      // consumers may read group g's partials
+      }
+      CH_STAMP(g, 6);
+      __syncwarp();
+      // y = fp16(sum of partials + bias) for tiles c, c + ncta, ... of group g (2 columns per lane)
+      const float* P = Pbase + (size_t)G->region * H.region_floats;
+      const uint32_t* tab = reinterpret_cast<const uint32_t*>(p.plan + G->tab_off);
+      for (int tile = c; tile < G->tiles; tile += ncta) {
+        int j = 0;
+        while (j + 1 < G->n_layers && tile >= G->layer[j + 1].tile0) ++j;
+        const ChLayer* L = &G->layer[j];
+        const int col = (tile - L->tile0) * kTileN + 2 * lane;
+        const int cnt = (int)(__ldg(tab + tile) >> 16);
+#pragma unroll
+        for (int m = 0; m < MTOK; ++m) {
+          const float* base = P + (size_t)m * G->ncols + (size_t)tile * kTileN + 2 * lane;
+          float2 a = ldcg2(base);
+          for (int s = 1; s < cnt; ++s) {
+            const float2 b = ldcg2(base + (size_t)s * MTOK * G->ncols);
+            a.x += b.x; a.y += b.y;
+          }
+          if (col < L->N) {
+            if (L->bias) { a.x += __half2float(__ldg(L->bias + col)); a.y += __half2float(__ldg(L->bias + col + 1)); }
+            *reinterpret_cast<__half2*>(L->y + (size_t)m * L->ldy + col) = __floats2half2_rn(a.x, a.y);
+          }
+        }
+      }
+      CH_STAMP(g, 7);
+    }
+    if (lane == 0) {                                                       // the last CTA out re-zeroes the counters
+      __threadfence();
+      const uint32_t old = atomicAdd(ctr + kExitWord, 1u);
+      if (old == (uint32_t)ncta - 1u) {
+        ctr[kCtrWord] = 0u;
+        ctr[kExitWord] = 0u;
+        __threadfence();
+      }
+    }
+    return;
+  }
+
+  // =========================================== consumers ============================================
+  const int w = warp - 2, ctid = tid - 64;
+  const int g8 = lane >> 2, t = lane & 3;
+  pdl_wait();
+  char* xdig = smem + H.off_digits;
+  float2* parts = reinterpret_cast<float2*>(smem + H.off_parts);
+  float* red = reinterpret_cast<float*>(smem + H.off_red);
+  float2* tabw = reinterpret_cast<float2*>(smem + H.off_tab) + w * kTileN;
+  const int MT = (int)H.max_tiles;
+  float* redw = red + (size_t)w * MT * kTileN * MTOK;
+  const uint32_t ring = smem_u32(smem + H.off_ring);
+  const char* auxp = smem + H.off_aux;
+  // weights: sub-step ss of a slab, half h: ring + slot * 8192 + ss * 1024 + off_h
+  const uint32_t offh0 = (uint32_t)((2 * t) * 128 + ((g8 ^ ((2 * t) & 7)) << 4));
+  const uint32_t offh1 = (uint32_t)((2 * t + 1) * 128 + ((g8 ^ ((2 * t + 1) & 7)) << 4));
+  // digits: B column g8 -> token g8 >> 2, digit g8 & 3 (3 = unused -> zero pad)
+  const bool xreal = (g8 & 3) < 3 && (g8 >> 2) < MTOK;
+  const uint32_t xlane = xreal ? smem_u32(xdig) + (uint32_t)(((g8 >> 2) * 3 + (g8 & 3)) * 32 + t * 8) : smem_u32(smem + H.off_zpad);
+  const uint32_t xsub = xreal ? (uint32_t)(96 * MTOK) : 0u;
+  const int mytok = t >> 1;
+  const bool fx_on = mytok < MTOK;
+  const float dscale = (t & 1) ? (1.0f / 128.0f) : 128.0f, zflag = (t & 1) ? 0.f : 1.f;
+
+  uint32_t q0 = 0;                                                         // CTA-local slab sequence number at group start
+  for (int g = 0; g < NG; ++g) {
+    const ChGroup* G = groups + g;
+    const int K = G->K, U = G->U, KC = G->kc, PK = G->pk, PPS = G->pps;
+    const int ng = G->ncta;
+    const int a = c < ng ? (int)((long long)c * U / ng) : 0, b = c < ng ? (int)((long long)(c + 1) * U / ng) : 0;
+    const int nparts = K / PK;
+    if (w == 0) CH_STAMP(g, 0);
+    if (g > 0) mbar_wait_b(bar_xready, (uint32_t)(g - 1) & 1u, p.ws, 0x400u + g);
+    if (w == 0) CH_STAMP(g, 1);
+
+    // ---- x -> three base-128 digits per element, power-of-two scale per part (PK k) -----------------------------
+    {
+      const float* Psrc = Pbase + (size_t)G->src_region * H.region_floats;
+      const int EL = PK >> 5;                                              // elements per lane: 4 (PK = 128) or 2 (PK = 64)
+      for (int pr = w; pr < nparts; pr += kChWarps) {
+        const int k0 = pr * PK + EL * lane;
+#pragma unroll
+        for (int m = 0; m < MTOK; ++m) {
+          float xv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (G->xmode == 1) {
+            if (!G->xperm && EL == 4) {
+              ch_src4(G, p.plan, Psrc, m, MTOK, G->src_pcol0 + k0, xv);
+              if (G->src_bias) {
+                const uint2 bb = __ldg(reinterpret_cast<const uint2*>(G->src_bias + k0));
+                const __half2 b01 = *reinterpret_cast<const __half2*>(&bb.x), b23 = *reinterpret_cast<const __half2*>(&bb.y);
+                xv[0] += __low2float(b01); xv[1] += __high2float(b01); xv[2] += __low2float(b23); xv[3] += __high2float(b23);
+              }
+            } else {
+              for (int e = 0; e < EL; ++e) {
+                const int kx = G->xperm ? __ldg(G->xperm + k0 + e) : k0 + e;
+                xv[e] = ch_src1(G, p.plan, Psrc, m, MTOK, G->src_pcol0 + kx);
+                if (G->src_bias) xv[e] += __half2float(__ldg(G->src_bias + kx));
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xv[e] = __half2float(__float2half_rn(xv[e]));     // y is fp16 (QuantLinear.forward's output)
+          } else {
+            const __half* xr = G->x + (size_t)m * G->ldx;
+            for (int e = 0; e < EL; ++e) {
+              const int kx = G->xperm ? __ldg(G->xperm + k0 + e) : k0 + e;
+              xv[e] = __half2float(__ushort_as_half(ldcg_u16(xr + kx)));
+            }
+          }
+          // non-finite activations poison the part (the fp16 kernels propagate NaN / Inf through their FMAs)
+          uint32_t bad = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) bad |= ((__float_as_uint(xv[e]) & 0x7f800000u) == 0x7f800000u) ? 1u : 0u;
+          float mx = fmaxf(fmaxf(fabsf(xv[0]), fabsf(xv[1])), fmaxf(fabsf(xv[2]), fabsf(xv[3])));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          bad = __any_sync(0xffffffffu, bad);
+          if (bad) { mx = 0.f; xv[0] = xv[1] = xv[2] = xv[3] = 0.f; }
+          const int ex = (int)((__float_as_uint(mx) >> 23) & 0xffu);
+          const int E = (mx > 0.f) ? (19 + 127 - ex) : 0;
+          const float sc = __uint_as_float((uint32_t)(E + 127) << 23), isc = __uint_as_float((uint32_t)(127 - E) << 23);
+          int tsum = 0;
+          uint32_t dig[3] = {0u, 0u, 0u};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int tv = __float2int_rn(xv[e] * sc);                     // |tv| <= 2^20
+            tsum += tv;
+            const int d2 = ((tv + 64) & 127) - 64;
+            const int t1 = (tv - d2) >> 7;
+            const int d1 = ((t1 + 64) & 127) - 64;
+            const int d0 = (t1 - d1) >> 7;
+            dig[0] |= (uint32_t)(d0 & 0xff) << (8 * e);
+            dig[1] |= (uint32_t)(d1 & 0xff) << (8 * e);
+            dig[2] |= (uint32_t)(d2 & 0xff) << (8 * e);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+          if (lane == 0) parts[pr * MTOK + m] = bad ? make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000))
+                                                    : make_float2(isc, (float)tsum * isc);
+          // element e of this lane sits at k' = (EL lane + e) % 32 of 32-k sub-step sub: prow k' / 8, kk = k' % 8;
+          // even kk -> byte kk / 2 of the first word, odd kk -> byte kk / 2 of the second word
+          const int sub = (pr * PK + EL * lane) >> 5, kq = (EL * lane) & 31;
+          char* dbase = xdig + (size_t)sub * (96 * MTOK) + (size_t)(3 * m) * 32 + (kq >> 3) * 8 + ((kq & 7) >> 1);
+          if (EL == 4) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const uint32_t v = dig[d];
+              *reinterpret_cast<uint16_t*>(dbase + d * 32) = (uint16_t)((v & 0xffu) | ((v >> 8) & 0xff00u));             // e = 0, 2
+              *reinterpret_cast<uint16_t*>(dbase + d * 32 + 4) = (uint16_t)(((v >> 8) & 0xffu) | ((v >> 16) & 0xff00u)); // e = 1, 3
+            }
+          } else {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              dbase[d * 32] = (char)(dig[d] & 0xffu);
+              dbase[d * 32 + 4] = (char)((dig[d] >> 8) & 0xffu);
+            }
+          }
+        }
+      }
+    }
+    consumer_bar();
+    if (w == 0) CH_STAMP(g, 2);
+
+    // ---- this warp's units: (slab, part) pairs number u = q * PPS + part, unit u -> warp u % 16 -------------------
+    int acc[2][2][4];
+    float tot[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tot[i][0] = tot[i][1] = 0.f;
+    uint32_t touched = 0;
+    int cur_tl = -1;                                                       // local tile (tile - first tile of this CTA) of `tot`
+    const int tile_first = (a < b) ? a / KC : 0;
+    auto flush = [&]() {
+      if (cur_tl >= 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a0 = tot[q][0] + __shfl_xor_sync(0xffffffffu, tot[q][0], 1);
+          const float a1 = tot[q][1] + __shfl_xor_sync(0xffffffffu, tot[q][1], 1);
+          if (fx_on && !(t & 1)) {
+            const int n = 32 * (q >> 1) + 4 * g8 + 2 * (q & 1);            // MMA row g8 -> column n, row g8 + 8 -> n + 1
+            float* r = redw + ((size_t)cur_tl * kTileN + n) * MTOK + mytok;
+            r[0] = a0;
+            r[MTOK] = a1;
+          }
+          tot[q][0] = tot[q][1] = 0.f;
+        }
+        touched |= 1u << cur_tl;
+      }
+    };
+    if (a < b) {
+      const uint32_t ubase = q0 * (uint32_t)PPS;
+      const uint32_t uend = (q0 + (uint32_t)(b - a)) * (uint32_t)PPS;
+      uint32_t u = ubase + (((uint32_t)w + kChWarps - (ubase & (kChWarps - 1))) & (kChWarps - 1));
+      const int pshift = (PPS == 4) ? 2 : 1;
+      const int steps_sub = PK >> 5;                                       // 32-k sub-steps per part (4 or 2)
+      const int gshift = (G->group >= kSlabK) ? 31 : ((G->group == 128) ? 7 : 6);
+      for (; u < uend; u += kChWarps) {
+        const uint32_t q = u >> pshift;
+        const int pp = (int)(u & (uint32_t)(PPS - 1));
+        const int i = a + (int)(q - q0);
+        const int tile = i / KC, kk = i - tile * KC;
+        const int slot = (int)(q % (uint32_t)NS);
+        const uint32_t par = (q / (uint32_t)NS) & 1u;
+        const int tl = tile - tile_first;
+        if (tl != cur_tl) { flush(); cur_tl = tl; }
+        mbar_wait_b(bar_full + 8u * slot, par, p.ws, 0x500u + g);
+        // (scale, zero) of the part's group for the 64 columns of the tile -> this warp's table
+        {
+          const int gr = (pp * PK) >> gshift;                              // group row inside the slab's aux boxes
+          const char* ax = auxp + (size_t)slot * kAuxBytes;
+          const __half2 s2 = *reinterpret_cast<const __half2*>(ax + (size_t)gr * 128 + 4 * lane);
+          float z0, z1;
+          if (G->zfp16) {
+            const __half2 z2 = *reinterpret_cast<const __half2*>(ax + 512 + (size_t)gr * 128 + 4 * lane);
+            z0 = __low2float(z2); z1 = __high2float(z2);
+          } else {
+            const uint32_t zw = *reinterpret_cast<const uint32_t*>(ax + 512 + (size_t)gr * 32 + (lane >> 2) * 4);
+            const uint32_t zz = zw >> (8 * (lane & 3));
+            z0 = (float)((zz + (uint32_t)G->zero_bias) & 15u);
+            z1 = (float)(((zz >> 4) + (uint32_t)G->zero_bias) & 15u);
+          }
+          __syncwarp();                                                    // previous unit's table reads are done
+          *reinterpret_cast<float4*>(tabw + 2 * lane) = make_float4(__low2float(s2), z0, __high2float(s2), z1);
+          __syncwarp();
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int cp = 0; cp < 2; ++cp) acc[h][cp][0] = acc[h][cp][1] = acc[h][cp][2] = acc[h][cp][3] = 0;
+        const int ss0 = pp * steps_sub;                                    // first sub-step of the part inside the slab
+        const uint32_t wb = ring + (uint32_t)slot * kSlabBytes + (uint32_t)ss0 * 1024u;
+        uint32_t xp = xlane + (uint32_t)(kk * 8 + ss0) * xsub;
+#pragma unroll 2
+        for (int s = 0; s < steps_sub; ++s) {
+          const uint4 wa = lds128_s(wb + (uint32_t)s * 1024u + offh0), wc = lds128_s(wb + (uint32_t)s * 1024u + offh1);
+          const uint2 xb = lds64_s(xp);
+          xp += xsub;
+          imma_acc(acc[0][0], wa.x & NIBM, wa.y & NIBM, (wa.x >> 4) & NIBM, (wa.y >> 4) & NIBM, xb.x, xb.y);
+          imma_acc(acc[0][1], wa.z & NIBM, wa.w & NIBM, (wa.z >> 4) & NIBM, (wa.w >> 4) & NIBM, xb.x, xb.y);
+          imma_acc(acc[1][0], wc.x & NIBM, wc.y & NIBM, (wc.x >> 4) & NIBM, (wc.y >> 4) & NIBM, xb.x, xb.y);
+          imma_acc(acc[1][1], wc.z & NIBM, wc.w & NIBM, (wc.z >> 4) & NIBM, (wc.w >> 4) & NIBM, xb.x, xb.y);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_n(bar_empty + 8u * slot, (uint32_t)(4 / PPS));   // this warp is done with the slot
+        // fix-up: y += s * (2^-E * dscale * (d_a 2^7 + d_b) - zflag * z * sum(x)) for this lane's 8 (column, token) outputs
+        if (fx_on) {
+          const float2 pt = parts[((kk * kSlabK + pp * PK) / PK) * MTOK + mytok];
+          const float xs = pt.x * dscale, sxz = pt.y * zflag;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 e01 = *reinterpret_cast<const float4*>(tabw + 32 * h + 4 * g8);
+            const float4 e23 = *reinterpret_cast<const float4*>(tabw + 32 * h + 4 * g8 + 2);
+            const float v00 = (float)((acc[h][0][0] << 7) + acc[h][0][1]), v01 = (float)((acc[h][0][2] << 7) + acc[h][0][3]);
+            const float v10 = (float)((acc[h][1][0] << 7) + acc[h][1][1]), v11 = (float)((acc[h][1][2] << 7) + acc[h][1][3]);
+            tot[2 * h][0] = fmaf(e01.x, fmaf(v00, xs, -e01.y * sxz), tot[2 * h][0]);
+            tot[2 * h][1] = fmaf(e01.z, fmaf(v01, xs, -e01.w * sxz), tot[2 * h][1]);
+            tot[2 * h + 1][0] = fmaf(e23.x, fmaf(v10, xs, -e23.y * sxz), tot[2 * h + 1][0]);
+            tot[2 * h + 1][1] = fmaf(e23.z, fmaf(v11, xs, -e23.w * sxz), tot[2 * h + 1][1]);
+          }
+        }
+      }
+      flush();
+    }
+    // tiles of this CTA the warp never touched contribute zeros
+    const int ntl = (a < b) ? ((b - 1) / KC - tile_first + 1) : 0;
+    for (int tl = 0; tl < ntl; ++tl)
+      if (!((touched >> tl) & 1u))
+        for (int idx = lane; idx < kTileN * MTOK; idx += 32) redw[(size_t)tl * kTileN * MTOK + idx] = 0.f;
+    consumer_bar();
+    // ---- CTA-level reduction over the 16 warps (fixed order) -> this CTA's slot of the tile's partial sums ------------
+    {
+      float* P = Pbase + (size_t)G->region * H.region_floats;
+      const uint32_t* tab = reinterpret_cast<const uint32_t*>(p.plan + G->tab_off);
+      for (int idx = ctid; idx < ntl * kTileN * MTOK; idx += kChWarps * 32) {
+        float sum = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < kChWarps; ++wq) sum += red[(size_t)wq * MT * kTileN * MTOK + idx];
+        const int tl = idx / (kTileN * MTOK), rem = idx - tl * (kTileN * MTOK);
+        const int n = rem / MTOK, m = rem - n * MTOK;
+        const int tile = tile_first + tl;
+        const int c0 = (int)(__ldg(tab + tile) & 0xffffu);
+        P[((size_t)(c - c0) * MTOK + m) * G->ncols + (size_t)tile * kTileN + n] = sum;
+      }
+    }
+    __syncwarp();
+    if (w == 0) CH_STAMP(g, 5);
+    if (lane == 0) mbar_arrive_n(bar_cdone, 1);
+    q0 += (uint32_t)(b - a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: plan + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn ch_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int g_ch_ctas = 0, g_ch_slots = 0;
+static unsigned long long* g_ch_dbg = nullptr;
+void decode_chain_set_debug(unsigned long long* buf) { g_ch_dbg = buf; }
+void decode_chain_set_option(int which, int value) {
+  if (which == 0) g_ch_ctas = value;
+  else if (which == 1) g_ch_slots = value;
+}
+
+size_t decode_chain_plan_bytes(int n_groups, const int* tiles_per_group) {
+  size_t b = sizeof(ChHeader);
+  b = (b + 63) & ~(size_t)63;
+  b += (size_t)n_groups * sizeof(ChGroup);
+  for (int i = 0; i < n_groups; ++i) b += ((size_t)tiles_per_group[i] * 4 + 63) & ~(size_t)63;
+  return b;
+}
+
+static bool ch_layer_ok(const LayerView& L) {
+  if (L.layout != B200Q_LAYOUT_GPTQ && L.layout != B200Q_LAYOUT_HQQ) return false;
+  if (L.bits != 4 || L.g_idx) return false;
+  if (!(L.group == 64 || L.group == 128 || L.group % kSlabK == 0)) return false;
+  if (L.K % kSlabK != 0 || L.K % L.group != 0 || L.N % 32 != 0) return false;
+  if (((uintptr_t)L.qw & 15) || ((uintptr_t)L.s & 15) || ((uintptr_t)L.qz & 15)) return false;
+  return true;
+}
+
+// groups[i]: n layers sharing x (LinearArgs as in b200q_linear_group).  Returns 0, or a negative b200q status.
+int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int n_groups, int M, void* plan_out, size_t plan_cap,
+                      size_t* plan_bytes, size_t* ws_bytes) {
+  if (n_groups < 1 || M < 1 || M > 2) return B200Q_ERR_SHAPE;
+  EncodeTiledFn enc = ch_encode();
+  if (!enc) return B200Q_ERR_CUDA;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return B200Q_ERR_CUDA;
+  const int ncta = (g_ch_ctas > 0 && g_ch_ctas <= sms) ? g_ch_ctas : sms;
+  std::vector<int> tiles(n_groups);
+  int kmax = 0, pkmin = 128;
+  for (int g = 0; g < n_groups; ++g) {
+    if (n_layers[g] < 1 || n_layers[g] > kMaxGroupLayers) return B200Q_ERR_SHAPE;
+    const LayerView& A = groups[g][0].L;
+    int T = 0;
+    for (int j = 0; j < n_layers[g]; ++j) {
+      const LinearArgs& a = groups[g][j];
+      if (!ch_layer_ok(a.L)) return B200Q_ERR_UNSUPPORTED;
+      if (a.L.K != A.K || a.L.group != A.group || a.L.layout != A.layout || a.L.zero_bias != A.zero_bias || a.L.x_perm != A.x_perm ||
+          a.x != groups[g][0].x || a.ldx != groups[g][0].ldx || a.M != M)
+        return B200Q_ERR_UNSUPPORTED;
+      if (!a.y || a.ldy < a.L.N || ((uintptr_t)a.y & 3) || (a.ldy & 1)) return B200Q_ERR_ALIGNMENT;
+      T += (a.L.N + kTileN - 1) / kTileN;
+    }
+    if (!groups[g][0].x || ((uintptr_t)groups[g][0].x & 1)) return B200Q_ERR_NULL;
+    tiles[g] = T;
+    if (A.K > kmax) kmax = A.K;
+    if (A.group == 64) pkmin = 64;
+  }
+  const size_t need = decode_chain_plan_bytes(n_groups, tiles.data());
+  if (plan_bytes) *plan_bytes = need;
+  if (!plan_out) return B200Q_OK;                                         // size query
+  if (plan_cap < need) return B200Q_ERR_WORKSPACE;
+  char* blob = (char*)plan_out;
+  memset(blob, 0, need);
+  ChHeader* H = (ChHeader*)blob;
+  size_t off = (sizeof(ChHeader) + 63) & ~(size_t)63;
+  H->groups_off = (uint32_t)off;
+  ChGroup* GG = (ChGroup*)(blob + off);
+  off += (size_t)n_groups * sizeof(ChGroup);
+  int max_tiles = 1, smax_all = 1, ncols_all = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    ChGroup& G = GG[g];
+    const LayerView& A = groups[g][0].L;
+    G.n_layers = n_layers[g]; G.K = A.K; G.tiles = tiles[g]; G.kc = A.K / kSlabK; G.U = G.tiles * G.kc; G.group = A.group;
+    G.pk = (A.group == 64) ? 64 : 128; G.pps = kSlabK / G.pk; G.gps = (A.group >= kSlabK) ? 1 : kSlabK / A.group;
+    G.zfp16 = (A.layout == B200Q_LAYOUT_HQQ) ? 1 : 0; G.zero_bias = A.zero_bias;
+    G.tx_bytes = kSlabBytes + 128 * G.gps + (G.zfp16 ? 128 : 32) * G.gps;
+    G.region = g & 1; G.ncols = G.tiles * kTileN;
+    G.ncta = G.U < ncta ? G.U : ncta;
+    G.x = groups[g][0].x; G.ldx = groups[g][0].ldx; G.xperm = A.x_perm; G.xmode = 0;
+    int t0 = 0;
+    for (int j = 0; j < n_layers[g]; ++j) {
+      const LinearArgs& a = groups[g][j];
+      ChLayer& L = G.layer[j];
+      L.bias = a.L.bias; L.y = a.y; L.ldy = a.ldy; L.N = a.L.N; L.tile0 = t0; L.ntiles = (a.L.N + kTileN - 1) / kTileN;
+      t0 += L.ntiles;
+      {
+        cuuint64_t dims[3] = {32, (cuuint64_t)a.L.N / 32, (cuuint64_t)a.L.K / 8};
+        cuuint64_t strides[2] = {128, (cuuint64_t)a.L.N * 4};
+        cuuint32_t box[3] = {32, 2, 32}, es[3] = {1, 1, 1};
+        if (enc(&L.wmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)a.L.qw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return B200Q_ERR_CUDA;
+      }
+      {
+        cuuint64_t dims[2] = {(cuuint64_t)a.L.N, (cuuint64_t)a.L.G};
+        cuuint64_t strides[1] = {(cuuint64_t)a.L.N * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kTileN, (cuuint32_t)G.gps}, es[2] = {1, 1};
+        if (enc(&L.smap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)a.L.s, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+          return B200Q_ERR_CUDA;
+        if (G.zfp16) {
+          if (enc(&L.zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)a.L.qz, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return B200Q_ERR_CUDA;
+        } else {
+          cuuint64_t zd[2] = {(cuuint64_t)a.L.N / 8, (cuuint64_t)a.L.G};
+          cuuint64_t zs[1] = {(cuuint64_t)a.L.N / 2};
+          cuuint32_t zb[2] = {8, (cuuint32_t)G.gps};
+          if (enc(&L.zmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)a.L.qz, zd, zs, zb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return B200Q_ERR_CUDA;
+        }
+      }
+    }
+    // tile -> (first contributing CTA, number of contributing CTAs): CTA c owns slabs [c U / n, (c + 1) U / n)
+    G.tab_off = (uint32_t)off;
+    uint32_t* tab = (uint32_t*)(blob + off);
+    off += ((size_t)G.tiles * 4 + 63) & ~(size_t)63;
+    auto owner = [&](long long i) { return (int)((((i + 1) * G.ncta) + G.U - 1) / G.U - 1); };
+    int smax = 1;
+    for (int tl = 0; tl < G.tiles; ++tl) {
+      const int c0 = owner((long long)tl * G.kc), c1 = owner((long long)(tl + 1) * G.kc - 1);
+      tab[tl] = (uint32_t)c0 | ((uint32_t)(c1 - c0 + 1) << 16);
+      if (c1 - c0 + 1 > smax) smax = c1 - c0 + 1;
+    }
+    G.smax = smax;
+    if (smax > smax_all) smax_all = smax;
+    if (G.ncols > ncols_all) ncols_all = G.ncols;
+    for (int c = 0; c < G.ncta; ++c) {
+      const long long a = (long long)c * G.U / G.ncta, b = (long long)(c + 1) * G.U / G.ncta;
+      if (b > a) { const int nt = (int)((b - 1) / G.kc - a / G.kc + 1); if (nt > max_tiles) max_tiles = nt; }
+    }
+    // x produced by the previous group of the chain?  (x points into one of its outputs, same row stride)
+    if (g > 0) {
+      const ChGroup& S = GG[g - 1];
+      for (int j = 0; j < S.n_layers; ++j) {
+        const ChLayer& L = S.layer[j];
+        const __half* x = groups[g][0].x;
+        const __half* xe = x + (size_t)(M - 1) * groups[g][0].ldx + A.K;
+        const __half* ye = L.y + (size_t)(M - 1) * L.ldy + L.N;
+        const bool overlap = x < ye && L.y < xe;
+        const bool lazy = x >= L.y && x + A.K <= L.y + L.N && groups[g][0].ldx == L.ldy && ((x - L.y) % 4) == 0;
+        if (overlap && !lazy) return B200Q_ERR_UNSUPPORTED;   // y of the previous group is only complete one barrier later
+        if (lazy) {
+          G.xmode = 1; G.src_region = S.region; G.src_smax = S.smax; G.src_ncols = S.ncols;
+          G.src_pcol0 = L.tile0 * kTileN + (int)(x - L.y); G.src_tab_off = S.tab_off;
+          G.src_bias = L.bias ? L.bias + (x - L.y) : nullptr;
+        }
+      }
+    }
+  }
+  if (max_tiles > 30) return B200Q_ERR_UNSUPPORTED;
+  H->magic = kChMagic; H->n_groups = (uint32_t)n_groups; H->M = (uint32_t)M; H->n_cta = (uint32_t)ncta; H->max_tiles = (uint32_t)max_tiles;
+  H->region_floats = (uint32_t)((size_t)smax_all * M * ncols_all);
+  H->ws_bytes = kCounterBytes + 2ull * H->region_floats * sizeof(float);
+  // shared memory
+  uint32_t so = 0;
+  H->off_bars = so; so += 1024;
+  H->off_digits = so; so += (uint32_t)(kmax / 32) * 96u * (uint32_t)M; so = (so + 15u) & ~15u;
+  H->off_parts = so; so += (uint32_t)(kmax / pkmin) * 8u * (uint32_t)M; so = (so + 15u) & ~15u;
+  H->off_red = so; so += (uint32_t)kChWarps * (uint32_t)max_tiles * kTileN * 4u * (uint32_t)M;
+  H->off_tab = so; so += (uint32_t)kChWarps * kTileN * 8u;
+  H->off_zpad = so; so += 64;
+  so = (so + 127u) & ~127u;                                                // TMA destinations: 128-byte aligned
+  const uint32_t fixed = so;
+  const uint32_t budget = 226u * 1024u - 1024u;                            // 1 KB slack for the 1024-byte alignment of the base
+  int slots = (int)((budget - fixed - 1024u) / (kSlabBytes + kAuxBytes));
+  if (g_ch_slots > 0 && g_ch_slots < slots) slots = g_ch_slots;
+  // a slot must always be consumed by the same warps (a waiter may be at most one mbarrier phase ahead): a warp's
+  // consecutive units are 16 / pps = 8 or 4 slabs apart, so the ring holds a multiple of 8 slabs
+  slots = slots >= 16 ? 16 : (slots >= 8 ? 8 : 0);
+  if (slots < 8) return B200Q_ERR_UNSUPPORTED;
+  H->slots = (uint32_t)slots;
+  H->off_aux = so; so += (uint32_t)slots * kAuxBytes;
+  so = (so + 1023u) & ~1023u;
+  H->off_ring = so; so += (uint32_t)slots * kSlabBytes;
+  H->smem_bytes = so + 1024u;
+  H->total_bytes = (uint32_t)need;
+  if (ws_bytes) *ws_bytes = (size_t)H->ws_bytes;
+  return B200Q_OK;
+}
+
+cudaError_t launch_decode_chain(const void* plan_host, const void* plan_dev, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const ChHeader* H = (const ChHeader*)plan_host;
+  if (!H || H->magic != kChMagic || !plan_dev || !ws || ws_bytes < H->ws_bytes) return cudaErrorInvalidValue;
+  static bool attr_done[64][2] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int mi = H->M == 1 ? 0 : 1;
+  if (!attr_done[dev & 63][mi]) {
+    cudaError_t e = mi == 0 ? cudaFuncSetAttribute(decode_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                            : cudaFuncSetAttribute(decode_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63][mi] = true;
+  }
+  ChParams p;
+  p.plan = (const char*)plan_dev; p.ws = (char*)ws; p.h = *H; p.dbg = g_ch_dbg;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(H->n_cta);
+  cfg.blockDim = dim3(kChThreads);
+  cfg.dynamicSmemBytes = H->smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  count_launch();
+  return mi == 0 ? cudaLaunchKernelEx(&cfg, decode_chain_kernel<1>, p) : cudaLaunchKernelEx(&cfg, decode_chain_kernel<2>, p);
+}
+
+}  // namespace b200q

@@ -94,6 +94,13 @@ bool gemv_imma_describe(const LinearArgs* a, int n, int out[6]);
 void gemv_imma_set_option(int which, int value);
 void gemv_imma_set_debug(unsigned long long* buf, size_t cap_entries);
 
+// decode_chain.cu : a recorded run of b200q_linear_group calls as ONE persistent launch (M <= 2, K-packed 4-bit)
+int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int n_groups, int M, void* plan_out, size_t plan_cap,
+                      size_t* plan_bytes, size_t* ws_bytes);
+cudaError_t launch_decode_chain(const void* plan_host, const void* plan_dev, void* ws, size_t ws_bytes, cudaStream_t st);
+void decode_chain_set_option(int which, int value);
+void decode_chain_set_debug(unsigned long long* buf);   // diagnostic: 16 x u64 per (group, CTA)
+
 // gemv_fma.cu : M <= 2 decode path (CUDA-core fp16x2 FMA, register prefetch, cluster split-K)
 bool gemv_fma_supported(const LayerView& L, int M, const __half* x, int64_t ldx);
 cudaError_t launch_gemv_fma(const LinearArgs& a, const PeerOut* peers);

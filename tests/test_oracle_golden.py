@@ -121,3 +121,31 @@ def test_make_layer_roundtrip(layout, bits):
     assert np.array_equal(q, L["q"])
     assert np.array_equal(np.asarray(z), np.asarray(L["z"]))
     assert np.array_equal(s.view(np.uint16), L["s"].view(np.uint16))
+
+
+def test_cpu_baseline_port_pinned_to_reference_forward(golden_dir):
+    """oracle/cpu_baseline.py (bench.py's cpu_baseline / --impl reference arm) against the reference's own
+    QuantLinearGPTQ.forward outputs and unpack() weights stored in gptq.npz (quant_linear_gptq.py:13-52, :136-143)."""
+    import torch
+    from oracle import cpu_baseline as C
+    d = _load(golden_dir, "gptq.npz")
+    pinned = 0
+    for i in _gptq_cases(d):
+        bits, gs, K, N, act = (int(v) for v in d[f"c{i}_meta"])
+        if bits not in (2, 4, 8) or act:                     # the port restates the 2/4/8-bit, g_idx-free branch
+            continue
+        p = f"c{i}_"
+        qw, qz = torch.from_numpy(d[p + "qweight"]), torch.from_numpy(d[p + "qzeros"])
+        sc = torch.from_numpy(d[p + "scales"]).float()
+        W = C.dequantize_blockwise(qw, sc, qz, gs, bits, K)
+        ref_w = d[p + "unpack_w"].T                          # reference unpack(): [N, K] fp32
+        assert np.abs(W.numpy() - ref_w).max() <= 2e-3 * np.abs(ref_w).max(), f"case {i}: weights"
+        x = torch.from_numpy(d[p + "x"]).float()
+        y = C.quant_linear_forward(x, qw, sc, qz, gs, bits, K).numpy() + d[p + "bias"].astype(np.float32)
+        ref = d[p + "y32"]
+        assert np.abs(y - ref).max() <= 1e-3 * np.abs(ref).max(), f"case {i}: forward"
+        # fp16 arithmetic (what the bench times) stays within fp16 accumulation error of the same outputs
+        y16 = C.quant_linear_forward(x.half(), qw, sc.half(), qz, gs, bits, K).float().numpy() + d[p + "bias"].astype(np.float32)
+        assert np.abs(y16 - ref).max() <= 2e-2 * np.abs(ref).max(), f"case {i}: fp16 forward"
+        pinned += 1
+    assert pinned >= 3
