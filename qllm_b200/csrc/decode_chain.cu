@@ -29,14 +29,17 @@
 namespace b200q {
 
 static constexpr int kChWarps = 16;                       // consumer warps
-static constexpr int kChThreads = 32 * (kChWarps + 2);    // + producer warp + sync/finalizer warp
-static constexpr int kSlabK = 256, kTileN = 64, kSlabBytes = 8192, kAuxBytes = 1024;
-static constexpr uint32_t kChMagic = 0xB2C4A117u;
+static constexpr int kChThreads = 32 * (kChWarps + 4);    // + warpgroup 0: producer warp, finalizer warp, two idle warps
+static constexpr int kSlabK = 256, kTileN = 64, kSlabBytes = 8192;
+static constexpr uint32_t kChMagic = 0xB2C4A118u;
 static constexpr uint32_t NIBM = 0x0f0f0f0fu;
 static constexpr int kCtrWord = 512, kExitWord = 513, kErrWord = 514;   // u32 words inside the 4 KB counter region
+static constexpr size_t kChWsHdr = 256;                   // after the counter region: word 0 = launch epoch (never reset)
 
 struct alignas(64) ChLayer {
-  CUtensorMap wmap, smap, zmap;
+  CUtensorMap wmap;
+  const __half* s;
+  const void* qz;
   const __half* bias;
   __half* y;
   int64_t ldy;
@@ -44,22 +47,22 @@ struct alignas(64) ChLayer {
 };
 struct alignas(64) ChGroup {
   ChLayer layer[kMaxGroupLayers];
-  int32_t n_layers, K, tiles, kc, U, group, pk, pps, gps, zfp16, zero_bias, tx_bytes;
+  int32_t n_layers, K, tiles, kc, U, group, pk, pps, zfp16, zero_bias;
   int32_t ncta;                                // CTAs that share this group's slabs: min(grid, U)
-  int32_t region, smax, ncols;                 // this group's partial sums: P[region][smax][M][ncols] fp32
+  int32_t region, smax, ncols;                 // this group's partial sums: P[region][smax][M][ncols] x {fp32, tag}
   int32_t xmode;                               // 0: plain fp16 x; 1: partial sums of the previous group
   const __half* x;
   int64_t ldx;
   const int32_t* xperm;
-  int32_t src_region, src_smax, src_ncols, src_pcol0;
+  int32_t src_smax, src_ncols, src_pcol0, src_region;
   const __half* src_bias;                      // bias of the source columns (already offset), or NULL
   uint32_t src_tab_off, tab_off;               // byte offsets (from the plan base) of u32 [tiles] tables: c0 | cnt << 16
-  int32_t pad_[1];
 };
 struct ChHeader {
   uint32_t magic, n_groups, M, n_cta, slots, max_tiles, smem_bytes, total_bytes;
-  uint32_t off_bars, off_digits, off_parts, off_red, off_tab, off_zpad, off_aux, off_ring;
-  uint32_t groups_off, region_floats, pad_[2];
+  uint32_t off_bars, off_digits, off_parts, off_red, off_tab, off_zpad, off_ring, use_barrier;
+  uint32_t groups_off, pad_;
+  uint64_t region_elems;                       // 8-byte elements per partial-sum region
   uint64_t ws_bytes;
 };
 struct ChParams {
@@ -72,10 +75,6 @@ struct ChParams {
 __device__ __forceinline__ void tma_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
@@ -95,42 +94,37 @@ __device__ __noinline__ void ch_fail(char* ws, uint32_t code) {
   __threadfence_system();
   __trap();
 }
-__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity, char* ws, uint32_t code) {
-  if (mbar_try_a(bar, parity)) return;
+struct ChSpin {
   unsigned long long t0 = 0;
   uint32_t spins = 0;
-  while (!mbar_try_a(bar, parity)) {
-    if ((++spins & 255u) == 0) {
+  __device__ __forceinline__ void tick(char* ws, uint32_t code) {
+    if ((++spins & 1023u) == 0) {
       const unsigned long long now = st_gtime();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000ull) ch_fail(ws, code);
     }
   }
+};
+__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity, char* ws, uint32_t code) {
+  if (mbar_try_a(bar, parity)) return;
+  ChSpin sp;
+  while (!mbar_try_a(bar, parity)) sp.tick(ws, code);
 }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ float4 ldcg4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+// a partial sum travels as one 64-bit word {fp32 bits, tag}: naturally aligned 8-byte accesses are single-copy atomic,
+// so a reader that sees the step's tag sees the value -- no fence, no flag, the load is the hand-off
+__device__ __forceinline__ unsigned long long ld_tagged(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ float2 ldcg2(const float* p) {
-  float2 v;
-  asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float ldcg1(const float* p) {
-  float v;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint32_t ldcg_u32(const void* p) {
-  uint32_t v;
-  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
+__device__ __forceinline__ void st_tagged(unsigned long long* p, float v, uint32_t tag) {
+  const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 __device__ __forceinline__ unsigned short ldcg_u16(const void* p) {
   unsigned short v;
@@ -144,29 +138,41 @@ __device__ __forceinline__ void imma_acc(int (&d)[4], uint32_t a0, uint32_t a1, 
                : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// fp16(sum of the source group's partials + bias) for 4 consecutive source columns (pc % 4 == 0): exactly what the
-// finalizer stores as y, summed in the same (slot) order
-__device__ __forceinline__ void ch_src4(const ChGroup* G, const char* plan, const float* P, int m, int M, int pc, float (&o)[4]) {
-  const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(plan + G->src_tab_off) + (pc >> 6));
-  const int cnt = (int)(e >> 16);
-  const float* base = P + (size_t)m * G->src_ncols + pc;
-  float4 a = ldcg4(base);
-  for (int s = 1; s < cnt; ++s) {
-    const float4 b = ldcg4(base + (size_t)s * M * G->src_ncols);
-    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+// sum over the contributing CTAs' slots (in slot order) of NE consecutive tagged partial sums; spins until every word
+// carries `tag`.  All loads are issued before the first check.
+template <int NE>
+__device__ __forceinline__ void ch_gather(const unsigned long long* base, size_t slot_stride, int cnt, uint32_t tag, float (&o)[NE],
+                                          char* ws, uint32_t code) {
+#pragma unroll
+  for (int e = 0; e < NE; ++e) o[e] = 0.f;
+  for (int s0 = 0; s0 < cnt; s0 += 4) {
+    unsigned long long r[4][NE];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (s0 + i < cnt) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) r[i][e] = ld_tagged(base + (size_t)(s0 + i) * slot_stride + e);
+      }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (s0 + i < cnt) {
+        ChSpin sp;
+        for (;;) {
+          bool ok = true;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) ok = ok && ((uint32_t)(r[i][e] >> 32) == tag);
+          if (ok) break;
+          sp.tick(ws, code);
+#pragma unroll
+          for (int e = 0; e < NE; ++e) r[i][e] = ld_tagged(base + (size_t)(s0 + i) * slot_stride + e);
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) o[e] += __uint_as_float((uint32_t)r[i][e]);
+      }
   }
-  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-}
-__device__ __forceinline__ float ch_src1(const ChGroup* G, const char* plan, const float* P, int m, int M, int pc) {
-  const uint32_t e = __ldg(reinterpret_cast<const uint32_t*>(plan + G->src_tab_off) + (pc >> 6));
-  const int cnt = (int)(e >> 16);
-  const float* base = P + (size_t)m * G->src_ncols + pc;
-  float a = ldcg1(base);
-  for (int s = 1; s < cnt; ++s) a += ldcg1(base + (size_t)s * M * G->src_ncols);
-  return a;
 }
 
-// diagnostic: 16 x u64 per (group, CTA): consumer warp 0 phases 0..5, sync warp 6..7, producer 8..10
+// diagnostic: 16 x u64 per (group, CTA): consumer warp 0 phases 0..5, finalizer warp 6..7, producer 8..10
 #define CH_STAMP(g, i) do { if (p.dbg && lane == 0) p.dbg[((size_t)(g) * gridDim.x + blockIdx.x) * 16 + (i)] = st_gtime(); } while (0)
 
 template <int MTOK>
@@ -177,12 +183,14 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
   const int NS = (int)H.slots;
   const uint32_t bars = smem_u32(smem + H.off_bars);
   const uint32_t bar_full = bars, bar_empty = bars + 8u * 32u, bar_xready = bars + 8u * 64u, bar_cdone = bars + 8u * 65u;
+  volatile int* fin_count = reinterpret_cast<volatile int*>(smem + H.off_bars + 8 * 66);   // steps whose y this CTA has written
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = blockIdx.x, ncta = gridDim.x;
   const int NG = (int)H.n_groups;
+  const bool use_barrier = H.use_barrier != 0;
   const ChGroup* groups = reinterpret_cast<const ChGroup*>(p.plan + H.groups_off);
   uint32_t* ctr = reinterpret_cast<uint32_t*>(p.ws);
-  float* Pbase = reinterpret_cast<float*>(p.ws + kCounterBytes);
+  unsigned long long* Pbase = reinterpret_cast<unsigned long long*>(p.ws + kCounterBytes + kChWsHdr);
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -191,31 +199,36 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
     }
     mbar_init(reinterpret_cast<uint64_t*>(smem + H.off_bars) + 64, 1);
     mbar_init(reinterpret_cast<uint64_t*>(smem + H.off_bars) + 65, kChWarps);
+    *fin_count = 0;
     fence_mbar_init();
   }
   if (tid < 16) reinterpret_cast<uint32_t*>(smem + H.off_zpad)[tid] = 0u;
   __syncthreads();
   pdl_launch_dependents();
 
+  // register budget: the control warpgroup gives registers back, the four consumer warpgroups take them
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == 2 || warp == 3) return;
   // =========================================== producer ===========================================
+  // packed weights are constants: the stream starts before the upstream kernel has finished (no griddepcontrol.wait)
   if (warp == 0) {
     if (lane != 0) return;
-    const uint32_t ring = smem_u32(smem + H.off_ring), aux = smem_u32(smem + H.off_aux);
+    const uint32_t ring = smem_u32(smem + H.off_ring);
     int slot = 0;
     uint32_t round = 0;
     for (int g = 0; g < NG; ++g) {
       const ChGroup* G = groups + g;
-      const int U = G->U, KC = G->kc, nl = G->n_layers;
-      const int ng = G->ncta;
+      const int U = G->U, KC = G->kc, nl = G->n_layers, ng = G->ncta;
       const int a = c < ng ? (int)((long long)c * U / ng) : 0, b = c < ng ? (int)((long long)(c + 1) * U / ng) : 0;
       if (a >= b) continue;
       CH_STAMP(g, 8);
       unsigned long long stall = 0;
       int tile = a / KC, kk = a - tile * KC, j = 0;
       while (j + 1 < nl && tile >= G->layer[j + 1].tile0) ++j;
-      const int tx = G->tx_bytes, gps = G->gps, zf = G->zfp16;
-      const int grow_mul = (G->group >= kSlabK) ? 0 : gps;                 // group rows advanced per slab (group < 256)
-      const int gdiv = (G->group >= kSlabK) ? G->group / kSlabK : 1;       // slabs per group row (group >= 256)
+      int tile0 = G->layer[j].tile0, tile_end = tile0 + G->layer[j].ntiles;
+      const void* wmap = &G->layer[j].wmap;
+      asm volatile("prefetch.tensormap [%0];" ::"l"(wmap) : "memory");
       for (int i = a; i < b; ++i) {
         if (round > 0) {
           if (p.dbg) {
@@ -226,19 +239,18 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
             mbar_wait_b(bar_empty + 8u * slot, (round - 1) & 1u, p.ws, 0x100u + g);
           }
         }
-        const ChLayer* L = &G->layer[j];
-        const int tl = tile - L->tile0;
         const uint32_t fb = bar_full + 8u * slot;
-        mbar_expect_tx_a(fb, (uint32_t)tx);
-        tma_3d(ring + (uint32_t)slot * kSlabBytes, &L->wmap, 0, 2 * tl, 32 * kk, fb);
-        const int grow = grow_mul ? kk * grow_mul : kk / gdiv;
-        tma_2d(aux + (uint32_t)slot * kAuxBytes, &L->smap, kTileN * tl, grow, fb);
-        tma_2d(aux + (uint32_t)slot * kAuxBytes + 512u, &L->zmap, zf ? kTileN * tl : 8 * tl, grow, fb);
+        mbar_expect_tx_a(fb, kSlabBytes);
+        tma_3d(ring + (uint32_t)slot * kSlabBytes, wmap, 0, 2 * (tile - tile0), 32 * kk, fb);
         if (++slot == NS) { slot = 0; ++round; }
         if (++kk == KC) {
           kk = 0;
-          ++tile;
-          if (j + 1 < nl && tile >= G->layer[j + 1].tile0) ++j;
+          if (++tile == tile_end && j + 1 < nl) {
+            ++j;
+            tile0 = tile_end; tile_end = tile0 + G->layer[j].ntiles;
+            wmap = &G->layer[j].wmap;
+            asm volatile("prefetch.tensormap [%0];" ::"l"(wmap) : "memory");
+          }
         }
       }
       CH_STAMP(g, 9);
@@ -247,33 +259,32 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
     return;
   }
 
-  // ====================================== sync / finalizer warp =====================================
-  if (warp == 1) {
-    pdl_wait();
+  // ============================== finalizer warp (and, in barrier mode, the grid barrier) ======================
+  {
+    pdl_wait();                                                            // upstream results (x, y buffers, workspace) are complete
+    const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(p.ws + kCounterBytes);
+    const uint32_t tag0 = epoch * (uint32_t)(NG + 1) + 1u;                 // tag of step g: tag0 + g (never 0)
     for (int g = 0; g < NG; ++g) {
       const ChGroup* G = groups + g;
-      mbar_wait_b(bar_cdone, (uint32_t)g & 1u, p.ws, 0x200u + g);          // this CTA's partial sums of group g are stored
-      if (lane == 0) {
-        __threadfence();
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + kCtrWord) : "memory");
-        const uint32_t target = (uint32_t)(g + 1) * (uint32_t)ncta;
-        unsigned long long t0 = 0;
-        uint32_t spins = 0;
-        while (ld_acquire_gpu(ctr + kCtrWord) < target) {
-          if ((++spins & 1023u) == 0) {
-            const unsigned long long now = st_gtime();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) ch_fail(p.ws, 0x300u + g);
-          }
+      if (use_barrier) {
+        mbar_wait_b(bar_cdone, (uint32_t)g & 1u, p.ws, 0x200u + g);        // this CTA's partial sums of step g are stored
+        if (lane == 0) {
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr + kCtrWord) : "memory");
+          const uint32_t target = (uint32_t)(g + 1) * (uint32_t)ncta;
+          ChSpin sp;
+          while (ld_acquire_gpu(ctr + kCtrWord) < target) sp.tick(p.ws, 0x300u + g);
+          if (g + 1 < NG) mbar_arrive_n(bar_xready, 1);
         }
-        if (g + 1 < NG) mbar_arrive_n(bar_xready, 1);                      // consumers may read group g's partials
+        __syncwarp();
       }
       CH_STAMP(g, 6);
-      __syncwarp();
-      // y = fp16(sum of partials + bias) for tiles c, c + ncta, ... of group g (2 columns per lane)
-      const float* P = Pbase + (size_t)G->region * H.region_floats;
+      // y = fp16(sum of partials + bias) for the tiles whose FIRST slab this CTA owns (2 columns per lane)
+      const int U = G->U, KC = G->kc, ng = G->ncta;
+      const int a = c < ng ? (int)((long long)c * U / ng) : 0, b = c < ng ? (int)((long long)(c + 1) * U / ng) : 0;
+      const unsigned long long* P = Pbase + (size_t)G->region * H.region_elems;
       const uint32_t* tab = reinterpret_cast<const uint32_t*>(p.plan + G->tab_off);
-      for (int tile = c; tile < G->tiles; tile += ncta) {
+      const uint32_t tag = tag0 + (uint32_t)g;
+      for (int tile = (a + KC - 1) / KC; tile * KC < b; ++tile) {
         int j = 0;
         while (j + 1 < G->n_layers && tile >= G->layer[j + 1].tile0) ++j;
         const ChLayer* L = &G->layer[j];
@@ -281,24 +292,23 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
         const int cnt = (int)(__ldg(tab + tile) >> 16);
 #pragma unroll
         for (int m = 0; m < MTOK; ++m) {
-          const float* base = P + (size_t)m * G->ncols + (size_t)tile * kTileN + 2 * lane;
-          float2 a = ldcg2(base);
-          for (int s = 1; s < cnt; ++s) {
-            const float2 b = ldcg2(base + (size_t)s * MTOK * G->ncols);
-            a.x += b.x; a.y += b.y;
-          }
+          float v[2];
+          ch_gather<2>(P + (size_t)m * G->ncols + (size_t)tile * kTileN + 2 * lane, (size_t)MTOK * G->ncols, cnt, tag, v, p.ws, 0x600u + g);
           if (col < L->N) {
-            if (L->bias) { a.x += __half2float(__ldg(L->bias + col)); a.y += __half2float(__ldg(L->bias + col + 1)); }
-            *reinterpret_cast<__half2*>(L->y + (size_t)m * L->ldy + col) = __floats2half2_rn(a.x, a.y);
+            if (L->bias) { v[0] += __half2float(__ldg(L->bias + col)); v[1] += __half2float(__ldg(L->bias + col + 1)); }
+            *reinterpret_cast<__half2*>(L->y + (size_t)m * L->ldy + col) = __floats2half2_rn(v[0], v[1]);
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); *fin_count = g + 1; }
       CH_STAMP(g, 7);
     }
-    if (lane == 0) {                                                       // the last CTA out re-zeroes the counters
+    if (lane == 0) {                                                       // the last CTA out advances the epoch, re-zeroes the counters
       __threadfence();
       const uint32_t old = atomicAdd(ctr + kExitWord, 1u);
       if (old == (uint32_t)ncta - 1u) {
+        *reinterpret_cast<volatile uint32_t*>(p.ws + kCounterBytes) = epoch + 1u;
         ctr[kCtrWord] = 0u;
         ctr[kExitWord] = 0u;
         __threadfence();
@@ -306,11 +316,15 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
     }
     return;
   }
+  }
 
   // =========================================== consumers ============================================
-  const int w = warp - 2, ctid = tid - 64;
-  const int g8 = lane >> 2, t = lane & 3;
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
   pdl_wait();
+  const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(p.ws + kCounterBytes);
+  const uint32_t tag0 = epoch * (uint32_t)(NG + 1) + 1u;
+  const int w = warp - 4, ctid = tid - 128;
+  const int g8 = lane >> 2, t = lane & 3;
   char* xdig = smem + H.off_digits;
   float2* parts = reinterpret_cast<float2*>(smem + H.off_parts);
   float* red = reinterpret_cast<float*>(smem + H.off_red);
@@ -318,7 +332,6 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
   const int MT = (int)H.max_tiles;
   float* redw = red + (size_t)w * MT * kTileN * MTOK;
   const uint32_t ring = smem_u32(smem + H.off_ring);
-  const char* auxp = smem + H.off_aux;
   // weights: sub-step ss of a slab, half h: ring + slot * 8192 + ss * 1024 + off_h
   const uint32_t offh0 = (uint32_t)((2 * t) * 128 + ((g8 ^ ((2 * t) & 7)) << 4));
   const uint32_t offh1 = (uint32_t)((2 * t + 1) * 128 + ((g8 ^ ((2 * t + 1) & 7)) << 4));
@@ -329,50 +342,98 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
   const int mytok = t >> 1;
   const bool fx_on = mytok < MTOK;
   const float dscale = (t & 1) ? (1.0f / 128.0f) : 128.0f, zflag = (t & 1) ? 0.f : 1.f;
+  const int nsmask = NS - 1;                                               // NS is 8 or 16
 
-  uint32_t q0 = 0;                                                         // CTA-local slab sequence number at group start
+  uint32_t q0 = 0;                                                         // CTA-local slab sequence number at step start
   for (int g = 0; g < NG; ++g) {
     const ChGroup* G = groups + g;
-    const int K = G->K, U = G->U, KC = G->kc, PK = G->pk, PPS = G->pps;
-    const int ng = G->ncta;
+    const int K = G->K, U = G->U, KC = G->kc, PK = G->pk, PPS = G->pps, ng = G->ncta;
+    const int zf = G->zfp16, zbias = G->zero_bias, group = G->group, nl = G->n_layers;
     const int a = c < ng ? (int)((long long)c * U / ng) : 0, b = c < ng ? (int)((long long)(c + 1) * U / ng) : 0;
     const int nparts = K / PK;
+    const int pshift = (PPS == 4) ? 2 : 1;
+    const int dslab = kChWarps >> pshift;                                  // slabs between two consecutive units of a warp
     if (w == 0) CH_STAMP(g, 0);
-    if (g > 0) mbar_wait_b(bar_xready, (uint32_t)(g - 1) & 1u, p.ws, 0x400u + g);
+
+    // ---- this warp's first unit; its (scale, zero) words are fetched now, one unit ahead of their use, from then on ----
+    const uint32_t ubase = q0 << pshift, uend = (q0 + (uint32_t)(b - a)) << pshift;
+    uint32_t u = ubase + (((uint32_t)w + kChWarps - (ubase & (kChWarps - 1))) & (kChWarps - 1));
+    int tile = 0, kk = 0, lj = 0, ltile0 = 0, ltile_end = 0, lN = 0;
+    const __half* ls = nullptr;
+    const char* lqz = nullptr;
+    uint32_t pf_s = 0, pf_z = 0;
+    auto load_layer = [&]() {
+      while (lj + 1 < nl && tile >= G->layer[lj + 1].tile0) ++lj;
+      const ChLayer* L = &G->layer[lj];
+      ltile0 = L->tile0; ltile_end = ltile0 + L->ntiles; lN = L->N; ls = L->s; lqz = reinterpret_cast<const char*>(L->qz);
+    };
+    auto prefetch_sz = [&](int tile_, int kk_, int pp_) {                  // scale / zero words of columns 2 lane, 2 lane + 1 of the unit
+      const int col = (tile_ - ltile0) * kTileN + 2 * lane;
+      const int grow = (kk_ * kSlabK + pp_ * PK) / group;
+      pf_s = 0; pf_z = 0;
+      if (col < lN) {
+        pf_s = __ldg(reinterpret_cast<const uint32_t*>(ls + (size_t)grow * lN + col));
+        pf_z = zf ? __ldg(reinterpret_cast<const uint32_t*>(lqz + ((size_t)grow * lN + col) * 2))
+                  : __ldg(reinterpret_cast<const uint32_t*>(lqz + ((size_t)grow * (lN >> 3) + (col >> 3)) * 4));
+      }
+    };
+    if (u < uend) {
+      const int i0 = a + (int)((u >> pshift) - q0);
+      tile = i0 / KC; kk = i0 - tile * KC;
+      load_layer();
+      prefetch_sz(tile, kk, (int)(u & (uint32_t)(PPS - 1)));
+    }
+
+    if (use_barrier && g > 0) mbar_wait_b(bar_xready, (uint32_t)(g - 1) & 1u, p.ws, 0x400u + g);
     if (w == 0) CH_STAMP(g, 1);
 
     // ---- x -> three base-128 digits per element, power-of-two scale per part (PK k) -----------------------------
     {
-      const float* Psrc = Pbase + (size_t)G->src_region * H.region_floats;
+      const unsigned long long* Psrc = Pbase + (size_t)G->src_region * H.region_elems;
+      const uint32_t* stab = reinterpret_cast<const uint32_t*>(p.plan + G->src_tab_off);
+      const uint32_t xtag = tag0 + (uint32_t)(g - 1);
       const int EL = PK >> 5;                                              // elements per lane: 4 (PK = 128) or 2 (PK = 64)
+      const int xmode = G->xmode;
+      const int* xperm = G->xperm;
+      const __half* sbias = G->src_bias;
       for (int pr = w; pr < nparts; pr += kChWarps) {
         const int k0 = pr * PK + EL * lane;
 #pragma unroll
         for (int m = 0; m < MTOK; ++m) {
           float xv[4] = {0.f, 0.f, 0.f, 0.f};
-          if (G->xmode == 1) {
-            if (!G->xperm && EL == 4) {
-              ch_src4(G, p.plan, Psrc, m, MTOK, G->src_pcol0 + k0, xv);
-              if (G->src_bias) {
-                const uint2 bb = __ldg(reinterpret_cast<const uint2*>(G->src_bias + k0));
+          if (xmode == 1) {
+            if (!xperm && EL == 4) {
+              const int pc = G->src_pcol0 + k0;
+              const int cnt = (int)(__ldg(stab + (pc >> 6)) >> 16);
+              ch_gather<4>(Psrc + (size_t)m * G->src_ncols + pc, (size_t)MTOK * G->src_ncols, cnt, xtag, xv, p.ws, 0x700u + g);
+              if (sbias) {
+                const uint2 bb = __ldg(reinterpret_cast<const uint2*>(sbias + k0));
                 const __half2 b01 = *reinterpret_cast<const __half2*>(&bb.x), b23 = *reinterpret_cast<const __half2*>(&bb.y);
                 xv[0] += __low2float(b01); xv[1] += __high2float(b01); xv[2] += __low2float(b23); xv[3] += __high2float(b23);
               }
             } else {
-              for (int e = 0; e < EL; ++e) {
-                const int kx = G->xperm ? __ldg(G->xperm + k0 + e) : k0 + e;
-                xv[e] = ch_src1(G, p.plan, Psrc, m, MTOK, G->src_pcol0 + kx);
-                if (G->src_bias) xv[e] += __half2float(__ldg(G->src_bias + kx));
-              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < EL) {
+                  const int kx = xperm ? __ldg(xperm + k0 + e) : k0 + e;
+                  const int pc = G->src_pcol0 + kx;
+                  const int cnt = (int)(__ldg(stab + (pc >> 6)) >> 16);
+                  float v1[1];
+                  ch_gather<1>(Psrc + (size_t)m * G->src_ncols + pc, (size_t)MTOK * G->src_ncols, cnt, xtag, v1, p.ws, 0x700u + g);
+                  xv[e] = v1[0];
+                  if (sbias) xv[e] += __half2float(__ldg(sbias + kx));
+                }
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) xv[e] = __half2float(__float2half_rn(xv[e]));     // y is fp16 (QuantLinear.forward's output)
           } else {
             const __half* xr = G->x + (size_t)m * G->ldx;
-            for (int e = 0; e < EL; ++e) {
-              const int kx = G->xperm ? __ldg(G->xperm + k0 + e) : k0 + e;
-              xv[e] = __half2float(__ushort_as_half(ldcg_u16(xr + kx)));
-            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < EL) {
+                const int kx = xperm ? __ldg(xperm + k0 + e) : k0 + e;
+                xv[e] = __half2float(__ushort_as_half(ldcg_u16(xr + kx)));
+              }
           }
           // non-finite activations poison the part (the fp16 kernels propagate NaN / Inf through their FMAs)
           uint32_t bad = 0;
@@ -428,7 +489,7 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
     consumer_bar();
     if (w == 0) CH_STAMP(g, 2);
 
-    // ---- this warp's units: (slab, part) pairs number u = q * PPS + part, unit u -> warp u % 16 -------------------
+    // ---- this warp's units: (slab, part) pairs numbered u = q * PPS + part, unit u -> warp u % 16 ------------------
     int acc[2][2][4];
     float tot[4][2];
 #pragma unroll
@@ -453,49 +514,48 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
         touched |= 1u << cur_tl;
       }
     };
-    if (a < b) {
-      const uint32_t ubase = q0 * (uint32_t)PPS;
-      const uint32_t uend = (q0 + (uint32_t)(b - a)) * (uint32_t)PPS;
-      uint32_t u = ubase + (((uint32_t)w + kChWarps - (ubase & (kChWarps - 1))) & (kChWarps - 1));
-      const int pshift = (PPS == 4) ? 2 : 1;
+    if (u < uend) {
       const int steps_sub = PK >> 5;                                       // 32-k sub-steps per part (4 or 2)
-      const int gshift = (G->group >= kSlabK) ? 31 : ((G->group == 128) ? 7 : 6);
+      int slot = (int)((u >> pshift) & (uint32_t)nsmask);
+      uint32_t par = ((u >> pshift) / (uint32_t)NS) & 1u;
+      const int pp = (int)(u & (uint32_t)(PPS - 1));                       // the part index of a warp's units never changes (16 % PPS == 0)
+      const int ss0 = pp * steps_sub;
       for (; u < uend; u += kChWarps) {
-        const uint32_t q = u >> pshift;
-        const int pp = (int)(u & (uint32_t)(PPS - 1));
-        const int i = a + (int)(q - q0);
-        const int tile = i / KC, kk = i - tile * KC;
-        const int slot = (int)(q % (uint32_t)NS);
-        const uint32_t par = (q / (uint32_t)NS) & 1u;
         const int tl = tile - tile_first;
         if (tl != cur_tl) { flush(); cur_tl = tl; }
-        mbar_wait_b(bar_full + 8u * slot, par, p.ws, 0x500u + g);
-        // (scale, zero) of the part's group for the 64 columns of the tile -> this warp's table
+        // (scale, zero) of the part's group for the 64 columns of the tile -> this warp's table (words fetched one unit ago)
         {
-          const int gr = (pp * PK) >> gshift;                              // group row inside the slab's aux boxes
-          const char* ax = auxp + (size_t)slot * kAuxBytes;
-          const __half2 s2 = *reinterpret_cast<const __half2*>(ax + (size_t)gr * 128 + 4 * lane);
+          const __half2 s2 = *reinterpret_cast<const __half2*>(&pf_s);
           float z0, z1;
-          if (G->zfp16) {
-            const __half2 z2 = *reinterpret_cast<const __half2*>(ax + 512 + (size_t)gr * 128 + 4 * lane);
+          if (zf) {
+            const __half2 z2 = *reinterpret_cast<const __half2*>(&pf_z);
             z0 = __low2float(z2); z1 = __high2float(z2);
           } else {
-            const uint32_t zw = *reinterpret_cast<const uint32_t*>(ax + 512 + (size_t)gr * 32 + (lane >> 2) * 4);
-            const uint32_t zz = zw >> (8 * (lane & 3));
-            z0 = (float)((zz + (uint32_t)G->zero_bias) & 15u);
-            z1 = (float)(((zz >> 4) + (uint32_t)G->zero_bias) & 15u);
+            const uint32_t zz = pf_z >> (8 * (lane & 3));
+            z0 = (float)((zz + (uint32_t)zbias) & 15u);
+            z1 = (float)(((zz >> 4) + (uint32_t)zbias) & 15u);
           }
           __syncwarp();                                                    // previous unit's table reads are done
           *reinterpret_cast<float4*>(tabw + 2 * lane) = make_float4(__low2float(s2), z0, __high2float(s2), z1);
-          __syncwarp();
         }
+        const int kk_cur = kk;
+        // next unit of this warp: advance (tile, kk), fetch its scale / zero words now
+        {
+          kk += dslab;
+          while (kk >= KC) { kk -= KC; ++tile; }
+          if (u + kChWarps < uend) {
+            if (tile >= ltile_end) load_layer();
+            prefetch_sz(tile, kk, pp);
+          }
+        }
+        mbar_wait_b(bar_full + 8u * slot, par, p.ws, 0x500u + g);
+        __syncwarp();
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
           for (int cp = 0; cp < 2; ++cp) acc[h][cp][0] = acc[h][cp][1] = acc[h][cp][2] = acc[h][cp][3] = 0;
-        const int ss0 = pp * steps_sub;                                    // first sub-step of the part inside the slab
         const uint32_t wb = ring + (uint32_t)slot * kSlabBytes + (uint32_t)ss0 * 1024u;
-        uint32_t xp = xlane + (uint32_t)(kk * 8 + ss0) * xsub;
+        uint32_t xp = xlane + (uint32_t)(kk_cur * 8 + ss0) * xsub;
 #pragma unroll 2
         for (int s = 0; s < steps_sub; ++s) {
           const uint4 wa = lds128_s(wb + (uint32_t)s * 1024u + offh0), wc = lds128_s(wb + (uint32_t)s * 1024u + offh1);
@@ -507,10 +567,10 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
           imma_acc(acc[1][1], wc.z & NIBM, wc.w & NIBM, (wc.z >> 4) & NIBM, (wc.w >> 4) & NIBM, xb.x, xb.y);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive_n(bar_empty + 8u * slot, (uint32_t)(4 / PPS));   // this warp is done with the slot
+        if (lane == 0) mbar_arrive_n(bar_empty + 8u * slot, (uint32_t)(4 >> (pshift - 1)) >> 1);   // 4 / PPS: this warp is done with the slot
         // fix-up: y += s * (2^-E * dscale * (d_a 2^7 + d_b) - zflag * z * sum(x)) for this lane's 8 (column, token) outputs
         if (fx_on) {
-          const float2 pt = parts[((kk * kSlabK + pp * PK) / PK) * MTOK + mytok];
+          const float2 pt = parts[(kk_cur * PPS + pp) * MTOK + mytok];
           const float xs = pt.x * dscale, sxz = pt.y * zflag;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -524,6 +584,8 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
             tot[2 * h + 1][1] = fmaf(e23.z, fmaf(v11, xs, -e23.w * sxz), tot[2 * h + 1][1]);
           }
         }
+        slot += dslab;
+        if (slot >= NS) { slot -= NS; par ^= 1u; }
       }
       flush();
     }
@@ -532,25 +594,35 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
     for (int tl = 0; tl < ntl; ++tl)
       if (!((touched >> tl) & 1u))
         for (int idx = lane; idx < kTileN * MTOK; idx += 32) redw[(size_t)tl * kTileN * MTOK + idx] = 0.f;
+    if (w == 0) CH_STAMP(g, 3);
     consumer_bar();
+    if (w == 0) CH_STAMP(g, 4);
+    // the partial sums of step g - 2 live where step g's go: this CTA's finalizer must have read what it needed of them
+    if (!use_barrier && g >= 2) {
+      ChSpin sp;
+      while (*fin_count < g - 1) sp.tick(p.ws, 0x800u + g);
+    }
     // ---- CTA-level reduction over the 16 warps (fixed order) -> this CTA's slot of the tile's partial sums ------------
     {
-      float* P = Pbase + (size_t)G->region * H.region_floats;
+      unsigned long long* P = Pbase + (size_t)G->region * H.region_elems;
       const uint32_t* tab = reinterpret_cast<const uint32_t*>(p.plan + G->tab_off);
+      const uint32_t tag = tag0 + (uint32_t)g;
       for (int idx = ctid; idx < ntl * kTileN * MTOK; idx += kChWarps * 32) {
         float sum = 0.f;
 #pragma unroll
         for (int wq = 0; wq < kChWarps; ++wq) sum += red[(size_t)wq * MT * kTileN * MTOK + idx];
         const int tl = idx / (kTileN * MTOK), rem = idx - tl * (kTileN * MTOK);
         const int n = rem / MTOK, m = rem - n * MTOK;
-        const int tile = tile_first + tl;
-        const int c0 = (int)(__ldg(tab + tile) & 0xffffu);
-        P[((size_t)(c - c0) * MTOK + m) * G->ncols + (size_t)tile * kTileN + n] = sum;
+        const int tile_o = tile_first + tl;
+        const int c0 = (int)(__ldg(tab + tile_o) & 0xffffu);
+        st_tagged(P + ((size_t)(c - c0) * MTOK + m) * G->ncols + (size_t)tile_o * kTileN + n, sum, tag);
       }
     }
-    __syncwarp();
     if (w == 0) CH_STAMP(g, 5);
-    if (lane == 0) mbar_arrive_n(bar_cdone, 1);
+    if (use_barrier) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_n(bar_cdone, 1);
+    }
     q0 += (uint32_t)(b - a);
   }
 }
@@ -572,12 +644,13 @@ static EncodeTiledFn ch_encode() {
   return fn;
 }
 
-static int g_ch_ctas = 0, g_ch_slots = 0;
+static int g_ch_ctas = 0, g_ch_slots = 0, g_ch_barrier = 0;
 static unsigned long long* g_ch_dbg = nullptr;
 void decode_chain_set_debug(unsigned long long* buf) { g_ch_dbg = buf; }
 void decode_chain_set_option(int which, int value) {
   if (which == 0) g_ch_ctas = value;
   else if (which == 1) g_ch_slots = value;
+  else if (which == 2) g_ch_barrier = value;
 }
 
 size_t decode_chain_plan_bytes(int n_groups, const int* tiles_per_group) {
@@ -638,21 +711,22 @@ int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int 
   ChGroup* GG = (ChGroup*)(blob + off);
   off += (size_t)n_groups * sizeof(ChGroup);
   int max_tiles = 1, smax_all = 1, ncols_all = 0;
+  bool small_group = false;
   for (int g = 0; g < n_groups; ++g) {
     ChGroup& G = GG[g];
     const LayerView& A = groups[g][0].L;
     G.n_layers = n_layers[g]; G.K = A.K; G.tiles = tiles[g]; G.kc = A.K / kSlabK; G.U = G.tiles * G.kc; G.group = A.group;
-    G.pk = (A.group == 64) ? 64 : 128; G.pps = kSlabK / G.pk; G.gps = (A.group >= kSlabK) ? 1 : kSlabK / A.group;
+    G.pk = (A.group == 64) ? 64 : 128; G.pps = kSlabK / G.pk;
     G.zfp16 = (A.layout == B200Q_LAYOUT_HQQ) ? 1 : 0; G.zero_bias = A.zero_bias;
-    G.tx_bytes = kSlabBytes + 128 * G.gps + (G.zfp16 ? 128 : 32) * G.gps;
     G.region = g & 1; G.ncols = G.tiles * kTileN;
     G.ncta = G.U < ncta ? G.U : ncta;
+    if (G.U < ncta) small_group = true;               // idle CTAs: the tag hand-off alone does not order their finalizers
     G.x = groups[g][0].x; G.ldx = groups[g][0].ldx; G.xperm = A.x_perm; G.xmode = 0;
     int t0 = 0;
     for (int j = 0; j < n_layers[g]; ++j) {
       const LinearArgs& a = groups[g][j];
       ChLayer& L = G.layer[j];
-      L.bias = a.L.bias; L.y = a.y; L.ldy = a.ldy; L.N = a.L.N; L.tile0 = t0; L.ntiles = (a.L.N + kTileN - 1) / kTileN;
+      L.s = a.L.s; L.qz = a.L.qz; L.bias = a.L.bias; L.y = a.y; L.ldy = a.ldy; L.N = a.L.N; L.tile0 = t0; L.ntiles = (a.L.N + kTileN - 1) / kTileN;
       t0 += L.ntiles;
       {
         cuuint64_t dims[3] = {32, (cuuint64_t)a.L.N / 32, (cuuint64_t)a.L.K / 8};
@@ -661,26 +735,6 @@ int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int 
         if (enc(&L.wmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)a.L.qw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
           return B200Q_ERR_CUDA;
-      }
-      {
-        cuuint64_t dims[2] = {(cuuint64_t)a.L.N, (cuuint64_t)a.L.G};
-        cuuint64_t strides[1] = {(cuuint64_t)a.L.N * 2};
-        cuuint32_t box[2] = {(cuuint32_t)kTileN, (cuuint32_t)G.gps}, es[2] = {1, 1};
-        if (enc(&L.smap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)a.L.s, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-          return B200Q_ERR_CUDA;
-        if (G.zfp16) {
-          if (enc(&L.zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)a.L.qz, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return B200Q_ERR_CUDA;
-        } else {
-          cuuint64_t zd[2] = {(cuuint64_t)a.L.N / 8, (cuuint64_t)a.L.G};
-          cuuint64_t zs[1] = {(cuuint64_t)a.L.N / 2};
-          cuuint32_t zb[2] = {8, (cuuint32_t)G.gps};
-          if (enc(&L.zmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)a.L.qz, zd, zs, zb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return B200Q_ERR_CUDA;
-        }
       }
     }
     // tile -> (first contributing CTA, number of contributing CTAs): CTA c owns slabs [c U / n, (c + 1) U / n)
@@ -722,8 +776,9 @@ int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int 
   }
   if (max_tiles > 30) return B200Q_ERR_UNSUPPORTED;
   H->magic = kChMagic; H->n_groups = (uint32_t)n_groups; H->M = (uint32_t)M; H->n_cta = (uint32_t)ncta; H->max_tiles = (uint32_t)max_tiles;
-  H->region_floats = (uint32_t)((size_t)smax_all * M * ncols_all);
-  H->ws_bytes = kCounterBytes + 2ull * H->region_floats * sizeof(float);
+  H->region_elems = (uint64_t)smax_all * M * ncols_all;
+  H->ws_bytes = kCounterBytes + kChWsHdr + 2ull * H->region_elems * 8ull;
+  H->use_barrier = (g_ch_barrier || small_group) ? 1u : 0u;
   // shared memory
   uint32_t so = 0;
   H->off_bars = so; so += 1024;
@@ -732,18 +787,16 @@ int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int 
   H->off_red = so; so += (uint32_t)kChWarps * (uint32_t)max_tiles * kTileN * 4u * (uint32_t)M;
   H->off_tab = so; so += (uint32_t)kChWarps * kTileN * 8u;
   H->off_zpad = so; so += 64;
-  so = (so + 127u) & ~127u;                                                // TMA destinations: 128-byte aligned
+  so = (so + 1023u) & ~1023u;
   const uint32_t fixed = so;
   const uint32_t budget = 226u * 1024u - 1024u;                            // 1 KB slack for the 1024-byte alignment of the base
-  int slots = (int)((budget - fixed - 1024u) / (kSlabBytes + kAuxBytes));
+  int slots = (int)((budget - fixed) / kSlabBytes);
   if (g_ch_slots > 0 && g_ch_slots < slots) slots = g_ch_slots;
   // a slot must always be consumed by the same warps (a waiter may be at most one mbarrier phase ahead): a warp's
-  // consecutive units are 16 / pps = 8 or 4 slabs apart, so the ring holds a multiple of 8 slabs
+  // consecutive units are 16 / pps = 8 or 4 slabs apart, so the ring holds 8 or 16 slabs
   slots = slots >= 16 ? 16 : (slots >= 8 ? 8 : 0);
   if (slots < 8) return B200Q_ERR_UNSUPPORTED;
   H->slots = (uint32_t)slots;
-  H->off_aux = so; so += (uint32_t)slots * kAuxBytes;
-  so = (so + 1023u) & ~1023u;
   H->off_ring = so; so += (uint32_t)slots * kSlabBytes;
   H->smem_bytes = so + 1024u;
   H->total_bytes = (uint32_t)need;
