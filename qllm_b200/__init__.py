@@ -12,6 +12,12 @@ from .loader import from_quantized, load_quant_config, save_quantized  # noqa: F
 
 __version__ = "0.1.0"
 
+# tuning / diagnostic switches for A/B runs: B200Q_OPTS="chain_window=6,chain_slots=8" (b200q_debug_set_option names)
+import os as _os
+for _kv in filter(None, _os.environ.get("B200Q_OPTS", "").split(",")):
+    _k, _, _v = _kv.partition("=")
+    check(lib.b200q_debug_set_option(_k.strip().encode(), float(_v)), "B200Q_OPTS " + _kv)
+
 
 def patch_qllm():
     """Route an installed `qllm` through this engine: replaces the one dispatch function the reference

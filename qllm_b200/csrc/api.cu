@@ -599,6 +599,7 @@ int b200q_debug_set_option(const char* name, double value) {
   else if (n == "chain_ctas") decode_chain_set_option(0, (int)value);
   else if (n == "chain_slots") decode_chain_set_option(1, (int)value);
   else if (n == "chain_barrier") decode_chain_set_option(2, (int)value);
+  else if (n == "chain_window") decode_chain_set_option(3, (int)value);
   else return B200Q_ERR_UNSUPPORTED;
   return B200Q_OK;
 }

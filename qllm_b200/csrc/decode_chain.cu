@@ -58,10 +58,27 @@ struct alignas(64) ChGroup {
   const __half* src_bias;                      // bias of the source columns (already offset), or NULL
   uint32_t src_tab_off, tab_off;               // byte offsets (from the plan base) of u32 [tiles] tables: c0 | cnt << 16
 };
+// the scalars of a step the consumers and the finalizer need, copied into shared memory at kernel start (a global load
+// costs ~1 us under the weight stream; the step descriptors are on every step's critical path)
+struct alignas(16) ChGS {
+  const __half* s[kMaxGroupLayers];
+  const void* qz[kMaxGroupLayers];
+  const __half* bias[kMaxGroupLayers];
+  __half* y[kMaxGroupLayers];
+  int64_t ldy[kMaxGroupLayers];
+  const __half* x;
+  const int32_t* xperm;
+  const __half* src_bias;
+  int64_t ldx;
+  int32_t N[kMaxGroupLayers], tile0[kMaxGroupLayers];
+  int32_t n_layers, K, tiles, kc, U, group, pk, pps, zfp16, zero_bias, ncta, region, smax, ncols, xmode;
+  int32_t src_smax, src_ncols, src_pcol0, src_region, tab_off, gshift, pad_[1];
+};
+static_assert(sizeof(ChGS) % 16 == 0, "ChGS is copied as uint4");
 struct ChHeader {
   uint32_t magic, n_groups, M, n_cta, slots, max_tiles, smem_bytes, total_bytes;
   uint32_t off_bars, off_digits, off_parts, off_red, off_tab, off_zpad, off_ring, use_barrier;
-  uint32_t groups_off, pad_;
+  uint32_t groups_off, gs_off, off_gs, n_cached, window, pad_;
   uint64_t region_elems;                       // 8-byte elements per partial-sum region
   uint64_t ws_bytes;
 };
@@ -172,8 +189,18 @@ __device__ __forceinline__ void ch_gather(const unsigned long long* base, size_t
   }
 }
 
-// diagnostic: 16 x u64 per (group, CTA): consumer warp 0 phases 0..5, finalizer warp 6..7, producer 8..10
+// diagnostic: 16 x u64 per (step, CTA): consumer warp 0 phases 0..5, finalizer warp 6..7, producer 8..10, consumer warp 0
+// cycle counters 11..13 (waiting for weights, units, unit loop)
 #define CH_STAMP(g, i) do { if (p.dbg && lane == 0) p.dbg[((size_t)(g) * gridDim.x + blockIdx.x) * 16 + (i)] = st_gtime(); } while (0)
+
+#define CH_PROLOGUE()                                                                                                   \
+  /* step scalars -> shared memory (finalizer warp + consumers copy, then meet on named barrier 2) */                  \
+  for (int i = (warp == 1) ? lane : tid - 96; i < ncached * (int)(sizeof(ChGS) / 16); i += kChWarps * 32 + 32)        \
+    reinterpret_cast<uint4*>(smem + H.off_gs)[i] = __ldg(reinterpret_cast<const uint4*>(gs_global) + i);               \
+  pdl_wait(); /* upstream results (x, y buffers, workspace) are complete */                                            \
+  const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(p.ws + kCounterBytes);                            \
+  const uint32_t tag0 = epoch * (uint32_t)(NG + 1) + 1u; /* tag of step g: tag0 + g (never 0) */                       \
+  asm volatile("bar.sync 2, %0;" ::"n"(kChWarps * 32 + 32) : "memory");
 
 template <int MTOK>
 __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __grid_constant__ ChParams p) {
@@ -189,6 +216,9 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
   const int NG = (int)H.n_groups;
   const bool use_barrier = H.use_barrier != 0;
   const ChGroup* groups = reinterpret_cast<const ChGroup*>(p.plan + H.groups_off);
+  const ChGS* gs_global = reinterpret_cast<const ChGS*>(p.plan + H.gs_off);
+  const ChGS* gs_cache = reinterpret_cast<const ChGS*>(smem + H.off_gs);
+  const int ncached = (int)H.n_cached;
   uint32_t* ctr = reinterpret_cast<uint32_t*>(p.ws);
   unsigned long long* Pbase = reinterpret_cast<unsigned long long*>(p.ws + kCounterBytes + kChWsHdr);
 
@@ -208,64 +238,63 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
 
   // register budget: the control warpgroup gives registers back, the four consumer warpgroups take them
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp == 2 || warp == 3) return;
-  // =========================================== producer ===========================================
-  // packed weights are constants: the stream starts before the upstream kernel has finished (no griddepcontrol.wait)
-  if (warp == 0) {
-    if (lane != 0) return;
-    const uint32_t ring = smem_u32(smem + H.off_ring);
-    int slot = 0;
-    uint32_t round = 0;
-    for (int g = 0; g < NG; ++g) {
-      const ChGroup* G = groups + g;
-      const int U = G->U, KC = G->kc, nl = G->n_layers, ng = G->ncta;
-      const int a = c < ng ? (int)((long long)c * U / ng) : 0, b = c < ng ? (int)((long long)(c + 1) * U / ng) : 0;
-      if (a >= b) continue;
-      CH_STAMP(g, 8);
-      unsigned long long stall = 0;
-      int tile = a / KC, kk = a - tile * KC, j = 0;
-      while (j + 1 < nl && tile >= G->layer[j + 1].tile0) ++j;
-      int tile0 = G->layer[j].tile0, tile_end = tile0 + G->layer[j].ntiles;
-      const void* wmap = &G->layer[j].wmap;
-      asm volatile("prefetch.tensormap [%0];" ::"l"(wmap) : "memory");
-      for (int i = a; i < b; ++i) {
-        if (round > 0) {
-          if (p.dbg) {
-            const unsigned long long t0 = st_gtime();
-            mbar_wait_b(bar_empty + 8u * slot, (round - 1) & 1u, p.ws, 0x100u + g);
-            stall += st_gtime() - t0;
-          } else {
-            mbar_wait_b(bar_empty + 8u * slot, (round - 1) & 1u, p.ws, 0x100u + g);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 2 || warp == 3) return;
+    // =========================================== producer ===========================================
+    // packed weights are constants: the stream starts before the upstream kernel has finished (no griddepcontrol.wait).
+    // At most `window` slabs are in flight per SM: more only lengthens every queue between the SM and HBM (a demand
+    // load behind 128 KB of bulk reads waits ~3 us) without adding bandwidth; landed slabs may fill the whole ring.
+    if (warp == 0) {
+      if (lane != 0) return;
+      const uint32_t ring = smem_u32(smem + H.off_ring);
+      const int W = (int)H.window;
+      int slot = 0, wslot = 0, issued = 0;
+      uint32_t round = 0, wround = 0;
+      for (int g = 0; g < NG; ++g) {
+        const ChGroup* G = groups + g;
+        const int U = G->U, KC = G->kc, nl = G->n_layers, ng = G->ncta;
+        const int a = c < ng ? (int)((long long)c * U / ng) : 0, b = c < ng ? (int)((long long)(c + 1) * U / ng) : 0;
+        if (a >= b) continue;
+        CH_STAMP(g, 8);
+        unsigned long long stall = 0;
+        int tile = a / KC, kk = a - tile * KC, j = 0;
+        while (j + 1 < nl && tile >= G->layer[j + 1].tile0) ++j;
+        int tile0 = G->layer[j].tile0, tile_end = tile0 + G->layer[j].ntiles;
+        const void* wmap = &G->layer[j].wmap;
+        asm volatile("prefetch.tensormap [%0];" ::"l"(wmap) : "memory");
+        for (int i = a; i < b; ++i) {
+          const unsigned long long t0 = p.dbg ? st_gtime() : 0ull;
+          if (round > 0) mbar_wait_b(bar_empty + 8u * slot, (round - 1) & 1u, p.ws, 0x100u + g);
+          if (issued >= W) {                                               // the slab issued W slabs ago has landed
+            mbar_wait_b(bar_full + 8u * wslot, wround & 1u, p.ws, 0x180u + g);
+            if (++wslot == NS) { wslot = 0; ++wround; }
+          }
+          if (p.dbg) stall += st_gtime() - t0;
+          const uint32_t fb = bar_full + 8u * slot;
+          mbar_expect_tx_a(fb, kSlabBytes);
+          tma_3d(ring + (uint32_t)slot * kSlabBytes, wmap, 0, 2 * (tile - tile0), 32 * kk, fb);
+          ++issued;
+          if (++slot == NS) { slot = 0; ++round; }
+          if (++kk == KC) {
+            kk = 0;
+            if (++tile == tile_end && j + 1 < nl) {
+              ++j;
+              tile0 = tile_end; tile_end = tile0 + G->layer[j].ntiles;
+              wmap = &G->layer[j].wmap;
+              asm volatile("prefetch.tensormap [%0];" ::"l"(wmap) : "memory");
+            }
           }
         }
-        const uint32_t fb = bar_full + 8u * slot;
-        mbar_expect_tx_a(fb, kSlabBytes);
-        tma_3d(ring + (uint32_t)slot * kSlabBytes, wmap, 0, 2 * (tile - tile0), 32 * kk, fb);
-        if (++slot == NS) { slot = 0; ++round; }
-        if (++kk == KC) {
-          kk = 0;
-          if (++tile == tile_end && j + 1 < nl) {
-            ++j;
-            tile0 = tile_end; tile_end = tile0 + G->layer[j].ntiles;
-            wmap = &G->layer[j].wmap;
-            asm volatile("prefetch.tensormap [%0];" ::"l"(wmap) : "memory");
-          }
-        }
+        CH_STAMP(g, 9);
+        if (p.dbg) p.dbg[((size_t)g * gridDim.x + blockIdx.x) * 16 + 10] = stall;
       }
-      CH_STAMP(g, 9);
-      if (p.dbg) p.dbg[((size_t)g * gridDim.x + blockIdx.x) * 16 + 10] = stall;
+      return;
     }
-    return;
-  }
-
   // ============================== finalizer warp (and, in barrier mode, the grid barrier) ======================
   {
-    pdl_wait();                                                            // upstream results (x, y buffers, workspace) are complete
-    const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(p.ws + kCounterBytes);
-    const uint32_t tag0 = epoch * (uint32_t)(NG + 1) + 1u;                 // tag of step g: tag0 + g (never 0)
+    CH_PROLOGUE();
     for (int g = 0; g < NG; ++g) {
-      const ChGroup* G = groups + g;
+      const ChGS* G = g < ncached ? gs_cache + g : gs_global + g;
       if (use_barrier) {
         mbar_wait_b(bar_cdone, (uint32_t)g & 1u, p.ws, 0x200u + g);        // this CTA's partial sums of step g are stored
         if (lane == 0) {
@@ -279,24 +308,22 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
       }
       CH_STAMP(g, 6);
       // y = fp16(sum of partials + bias) for the tiles whose FIRST slab this CTA owns (2 columns per lane)
-      const int U = G->U, KC = G->kc, ng = G->ncta;
+      const int U = G->U, KC = G->kc, ng = G->ncta, smax = G->smax, ncols = G->ncols, nl = G->n_layers;
       const int a = c < ng ? (int)((long long)c * U / ng) : 0, b = c < ng ? (int)((long long)(c + 1) * U / ng) : 0;
       const unsigned long long* P = Pbase + (size_t)G->region * H.region_elems;
-      const uint32_t* tab = reinterpret_cast<const uint32_t*>(p.plan + G->tab_off);
       const uint32_t tag = tag0 + (uint32_t)g;
       for (int tile = (a + KC - 1) / KC; tile * KC < b; ++tile) {
         int j = 0;
-        while (j + 1 < G->n_layers && tile >= G->layer[j + 1].tile0) ++j;
-        const ChLayer* L = &G->layer[j];
-        const int col = (tile - L->tile0) * kTileN + 2 * lane;
-        const int cnt = (int)(__ldg(tab + tile) >> 16);
+        while (j + 1 < nl && tile >= G->tile0[j + 1]) ++j;
+        const int col = (tile - G->tile0[j]) * kTileN + 2 * lane;
 #pragma unroll
         for (int m = 0; m < MTOK; ++m) {
           float v[2];
-          ch_gather<2>(P + (size_t)m * G->ncols + (size_t)tile * kTileN + 2 * lane, (size_t)MTOK * G->ncols, cnt, tag, v, p.ws, 0x600u + g);
-          if (col < L->N) {
-            if (L->bias) { v[0] += __half2float(__ldg(L->bias + col)); v[1] += __half2float(__ldg(L->bias + col + 1)); }
-            *reinterpret_cast<__half2*>(L->y + (size_t)m * L->ldy + col) = __floats2half2_rn(v[0], v[1]);
+          ch_gather<2>(P + (size_t)m * ncols + (size_t)tile * kTileN + 2 * lane, (size_t)MTOK * ncols, smax, tag, v, p.ws, 0x600u + g);
+          if (col < G->N[j]) {
+            const __half* bias = G->bias[j];
+            if (bias) { v[0] += __half2float(__ldg(bias + col)); v[1] += __half2float(__ldg(bias + col + 1)); }
+            *reinterpret_cast<__half2*>(G->y[j] + (size_t)m * G->ldy[j] + col) = __floats2half2_rn(v[0], v[1]);
           }
         }
       }
@@ -320,9 +347,7 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
 
   // =========================================== consumers ============================================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-  pdl_wait();
-  const uint32_t epoch = *reinterpret_cast<const volatile uint32_t*>(p.ws + kCounterBytes);
-  const uint32_t tag0 = epoch * (uint32_t)(NG + 1) + 1u;
+  CH_PROLOGUE();
   const int w = warp - 4, ctid = tid - 128;
   const int g8 = lane >> 2, t = lane & 3;
   char* xdig = smem + H.off_digits;
@@ -346,14 +371,20 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
 
   uint32_t q0 = 0;                                                         // CTA-local slab sequence number at step start
   for (int g = 0; g < NG; ++g) {
-    const ChGroup* G = groups + g;
+    const ChGS* G = g < ncached ? gs_cache + g : gs_global + g;
     const int K = G->K, U = G->U, KC = G->kc, PK = G->pk, PPS = G->pps, ng = G->ncta;
-    const int zf = G->zfp16, zbias = G->zero_bias, group = G->group, nl = G->n_layers;
+    const int zf = G->zfp16, zbias = G->zero_bias, gshift = G->gshift, nl = G->n_layers;
     const int a = c < ng ? (int)((long long)c * U / ng) : 0, b = c < ng ? (int)((long long)(c + 1) * U / ng) : 0;
     const int nparts = K / PK;
     const int pshift = (PPS == 4) ? 2 : 1;
     const int dslab = kChWarps >> pshift;                                  // slabs between two consecutive units of a warp
+    const int tile_first = (a < b) ? a / KC : 0;
+    const int ntl = (a < b) ? ((b - 1) / KC - tile_first + 1) : 0;
     if (w == 0) CH_STAMP(g, 0);
+    // table entry (first contributor, contributors) of the tile this thread will store a partial sum of
+    uint32_t my_tab = 0;
+    if (ctid < ntl * kTileN * MTOK)
+      my_tab = __ldg(reinterpret_cast<const uint32_t*>(p.plan + G->tab_off) + tile_first + ctid / (kTileN * MTOK));
 
     // ---- this warp's first unit; its (scale, zero) words are fetched now, one unit ahead of their use, from then on ----
     const uint32_t ubase = q0 << pshift, uend = (q0 + (uint32_t)(b - a)) << pshift;
@@ -363,13 +394,14 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
     const char* lqz = nullptr;
     uint32_t pf_s = 0, pf_z = 0;
     auto load_layer = [&]() {
-      while (lj + 1 < nl && tile >= G->layer[lj + 1].tile0) ++lj;
-      const ChLayer* L = &G->layer[lj];
-      ltile0 = L->tile0; ltile_end = ltile0 + L->ntiles; lN = L->N; ls = L->s; lqz = reinterpret_cast<const char*>(L->qz);
+      while (lj + 1 < nl && tile >= G->tile0[lj + 1]) ++lj;
+      ltile0 = G->tile0[lj]; ltile_end = (lj + 1 < nl) ? G->tile0[lj + 1] : G->tiles; lN = G->N[lj];
+      ls = G->s[lj]; lqz = reinterpret_cast<const char*>(G->qz[lj]);
     };
     auto prefetch_sz = [&](int tile_, int kk_, int pp_) {                  // scale / zero words of columns 2 lane, 2 lane + 1 of the unit
       const int col = (tile_ - ltile0) * kTileN + 2 * lane;
-      const int grow = (kk_ * kSlabK + pp_ * PK) / group;
+      const int k = kk_ * kSlabK + pp_ * PK;
+      const int grow = gshift >= 0 ? (k >> gshift) : k / G->group;
       pf_s = 0; pf_z = 0;
       if (col < lN) {
         pf_s = __ldg(reinterpret_cast<const uint32_t*>(ls + (size_t)grow * lN + col));
@@ -390,10 +422,9 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
     // ---- x -> three base-128 digits per element, power-of-two scale per part (PK k) -----------------------------
     {
       const unsigned long long* Psrc = Pbase + (size_t)G->src_region * H.region_elems;
-      const uint32_t* stab = reinterpret_cast<const uint32_t*>(p.plan + G->src_tab_off);
       const uint32_t xtag = tag0 + (uint32_t)(g - 1);
       const int EL = PK >> 5;                                              // elements per lane: 4 (PK = 128) or 2 (PK = 64)
-      const int xmode = G->xmode;
+      const int xmode = G->xmode, ssmax = G->src_smax, sncols = G->src_ncols, spc0 = G->src_pcol0;
       const int* xperm = G->xperm;
       const __half* sbias = G->src_bias;
       for (int pr = w; pr < nparts; pr += kChWarps) {
@@ -403,9 +434,7 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
           float xv[4] = {0.f, 0.f, 0.f, 0.f};
           if (xmode == 1) {
             if (!xperm && EL == 4) {
-              const int pc = G->src_pcol0 + k0;
-              const int cnt = (int)(__ldg(stab + (pc >> 6)) >> 16);
-              ch_gather<4>(Psrc + (size_t)m * G->src_ncols + pc, (size_t)MTOK * G->src_ncols, cnt, xtag, xv, p.ws, 0x700u + g);
+              ch_gather<4>(Psrc + (size_t)m * sncols + spc0 + k0, (size_t)MTOK * sncols, ssmax, xtag, xv, p.ws, 0x700u + g);
               if (sbias) {
                 const uint2 bb = __ldg(reinterpret_cast<const uint2*>(sbias + k0));
                 const __half2 b01 = *reinterpret_cast<const __half2*>(&bb.x), b23 = *reinterpret_cast<const __half2*>(&bb.y);
@@ -416,10 +445,8 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
               for (int e = 0; e < 4; ++e)
                 if (e < EL) {
                   const int kx = xperm ? __ldg(xperm + k0 + e) : k0 + e;
-                  const int pc = G->src_pcol0 + kx;
-                  const int cnt = (int)(__ldg(stab + (pc >> 6)) >> 16);
                   float v1[1];
-                  ch_gather<1>(Psrc + (size_t)m * G->src_ncols + pc, (size_t)MTOK * G->src_ncols, cnt, xtag, v1, p.ws, 0x700u + g);
+                  ch_gather<1>(Psrc + (size_t)m * sncols + spc0 + kx, (size_t)MTOK * sncols, ssmax, xtag, v1, p.ws, 0x700u + g);
                   xv[e] = v1[0];
                   if (sbias) xv[e] += __half2float(__ldg(sbias + kx));
                 }
@@ -496,7 +523,8 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
     for (int i = 0; i < 4; ++i) tot[i][0] = tot[i][1] = 0.f;
     uint32_t touched = 0;
     int cur_tl = -1;                                                       // local tile (tile - first tile of this CTA) of `tot`
-    const int tile_first = (a < b) ? a / KC : 0;
+    long long cyc_wait = 0, cyc_loop = 0;
+    int n_units = 0;
     auto flush = [&]() {
       if (cur_tl >= 0) {
 #pragma unroll
@@ -515,6 +543,7 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
       }
     };
     if (u < uend) {
+      const long long tl0 = p.dbg ? clock64() : 0;
       const int steps_sub = PK >> 5;                                       // 32-k sub-steps per part (4 or 2)
       int slot = (int)((u >> pshift) & (uint32_t)nsmask);
       uint32_t par = ((u >> pshift) / (uint32_t)NS) & 1u;
@@ -548,7 +577,14 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
             prefetch_sz(tile, kk, pp);
           }
         }
-        mbar_wait_b(bar_full + 8u * slot, par, p.ws, 0x500u + g);
+        if (p.dbg) {
+          const long long tw = clock64();
+          mbar_wait_b(bar_full + 8u * slot, par, p.ws, 0x500u + g);
+          cyc_wait += clock64() - tw;
+          ++n_units;
+        } else {
+          mbar_wait_b(bar_full + 8u * slot, par, p.ws, 0x500u + g);
+        }
         __syncwarp();
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -588,9 +624,9 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
         if (slot >= NS) { slot -= NS; par ^= 1u; }
       }
       flush();
+      if (p.dbg) cyc_loop = clock64() - tl0;
     }
     // tiles of this CTA the warp never touched contribute zeros
-    const int ntl = (a < b) ? ((b - 1) / KC - tile_first + 1) : 0;
     for (int tl = 0; tl < ntl; ++tl)
       if (!((touched >> tl) & 1u))
         for (int idx = lane; idx < kTileN * MTOK; idx += 32) redw[(size_t)tl * kTileN * MTOK + idx] = 0.f;
@@ -602,11 +638,12 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
       ChSpin sp;
       while (*fin_count < g - 1) sp.tick(p.ws, 0x800u + g);
     }
-    // ---- CTA-level reduction over the 16 warps (fixed order) -> this CTA's slot of the tile's partial sums ------------
+    // ---- CTA-level reduction over the 16 warps (fixed order) -> this CTA's slot of the tile's partial sums; the LAST
+    //      contributor of a tile also fills the tile's unused slots with tagged zeros, so readers never need the table ----
     {
       unsigned long long* P = Pbase + (size_t)G->region * H.region_elems;
-      const uint32_t* tab = reinterpret_cast<const uint32_t*>(p.plan + G->tab_off);
       const uint32_t tag = tag0 + (uint32_t)g;
+      const int smax = G->smax, ncols = G->ncols;
       for (int idx = ctid; idx < ntl * kTileN * MTOK; idx += kChWarps * 32) {
         float sum = 0.f;
 #pragma unroll
@@ -614,11 +651,21 @@ __global__ void __launch_bounds__(kChThreads, 1) decode_chain_kernel(const __gri
         const int tl = idx / (kTileN * MTOK), rem = idx - tl * (kTileN * MTOK);
         const int n = rem / MTOK, m = rem - n * MTOK;
         const int tile_o = tile_first + tl;
-        const int c0 = (int)(__ldg(tab + tile_o) & 0xffffu);
-        st_tagged(P + ((size_t)(c - c0) * MTOK + m) * G->ncols + (size_t)tile_o * kTileN + n, sum, tag);
+        const uint32_t e = (idx == ctid) ? my_tab : __ldg(reinterpret_cast<const uint32_t*>(p.plan + G->tab_off) + tile_o);
+        const int c0 = (int)(e & 0xffffu), cnt = (int)(e >> 16);
+        unsigned long long* dst = P + (size_t)m * ncols + (size_t)tile_o * kTileN + n;
+        st_tagged(dst + (size_t)(c - c0) * MTOK * ncols, sum, tag);
+        if (c == c0 + cnt - 1)
+          for (int sl = cnt; sl < smax; ++sl) st_tagged(dst + (size_t)sl * MTOK * ncols, 0.f, tag);
       }
     }
-    if (w == 0) CH_STAMP(g, 5);
+    if (w == 0) {
+      CH_STAMP(g, 5);
+      if (p.dbg && lane == 0) {
+        unsigned long long* d = p.dbg + ((size_t)g * gridDim.x + blockIdx.x) * 16;
+        d[11] = (unsigned long long)cyc_wait; d[12] = (unsigned long long)n_units; d[13] = (unsigned long long)cyc_loop;
+      }
+    }
     if (use_barrier) {
       __syncwarp();
       if (lane == 0) mbar_arrive_n(bar_cdone, 1);
@@ -644,19 +691,21 @@ static EncodeTiledFn ch_encode() {
   return fn;
 }
 
-static int g_ch_ctas = 0, g_ch_slots = 0, g_ch_barrier = 0;
+static int g_ch_ctas = 0, g_ch_slots = 0, g_ch_barrier = 0, g_ch_window = 0;
 static unsigned long long* g_ch_dbg = nullptr;
 void decode_chain_set_debug(unsigned long long* buf) { g_ch_dbg = buf; }
 void decode_chain_set_option(int which, int value) {
   if (which == 0) g_ch_ctas = value;
   else if (which == 1) g_ch_slots = value;
   else if (which == 2) g_ch_barrier = value;
+  else if (which == 3) g_ch_window = value;
 }
 
 size_t decode_chain_plan_bytes(int n_groups, const int* tiles_per_group) {
   size_t b = sizeof(ChHeader);
   b = (b + 63) & ~(size_t)63;
   b += (size_t)n_groups * sizeof(ChGroup);
+  b += ((size_t)n_groups * sizeof(ChGS) + 63) & ~(size_t)63;
   for (int i = 0; i < n_groups; ++i) b += ((size_t)tiles_per_group[i] * 4 + 63) & ~(size_t)63;
   return b;
 }
@@ -710,6 +759,9 @@ int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int 
   H->groups_off = (uint32_t)off;
   ChGroup* GG = (ChGroup*)(blob + off);
   off += (size_t)n_groups * sizeof(ChGroup);
+  H->gs_off = (uint32_t)off;
+  ChGS* GS = (ChGS*)(blob + off);
+  off += ((size_t)n_groups * sizeof(ChGS) + 63) & ~(size_t)63;
   int max_tiles = 1, smax_all = 1, ncols_all = 0;
   bool small_group = false;
   for (int g = 0; g < n_groups; ++g) {
@@ -719,8 +771,9 @@ int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int 
     G.pk = (A.group == 64) ? 64 : 128; G.pps = kSlabK / G.pk;
     G.zfp16 = (A.layout == B200Q_LAYOUT_HQQ) ? 1 : 0; G.zero_bias = A.zero_bias;
     G.region = g & 1; G.ncols = G.tiles * kTileN;
-    G.ncta = G.U < ncta ? G.U : ncta;
-    if (G.U < ncta) small_group = true;               // idle CTAs: the tag hand-off alone does not order their finalizers
+    // every CTA gets >= kc / 3 slabs (a tile then has <= 4 contributors: readers sum `smax` slots unconditionally)
+    G.ncta = 3 * G.tiles < ncta ? 3 * G.tiles : ncta;
+    if (G.ncta < ncta) small_group = true;            // idle CTAs: the tag hand-off alone does not order their finalizers
     G.x = groups[g][0].x; G.ldx = groups[g][0].ldx; G.xperm = A.x_perm; G.xmode = 0;
     int t0 = 0;
     for (int j = 0; j < n_layers[g]; ++j) {
@@ -775,6 +828,22 @@ int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int 
     }
   }
   if (max_tiles > 30) return B200Q_ERR_UNSUPPORTED;
+  for (int g = 0; g < n_groups; ++g) {
+    const ChGroup& G = GG[g];
+    ChGS& S = GS[g];
+    for (int j = 0; j < G.n_layers; ++j) {
+      const ChLayer& L = G.layer[j];
+      S.s[j] = L.s; S.qz[j] = L.qz; S.bias[j] = L.bias; S.y[j] = L.y; S.ldy[j] = L.ldy; S.N[j] = L.N; S.tile0[j] = L.tile0;
+    }
+    S.x = G.x; S.xperm = G.xperm; S.src_bias = G.src_bias; S.ldx = G.ldx;
+    S.n_layers = G.n_layers; S.K = G.K; S.tiles = G.tiles; S.kc = G.kc; S.U = G.U; S.group = G.group; S.pk = G.pk; S.pps = G.pps;
+    S.zfp16 = G.zfp16; S.zero_bias = G.zero_bias; S.ncta = G.ncta; S.region = G.region; S.smax = G.smax; S.ncols = G.ncols;
+    S.xmode = G.xmode; S.src_smax = G.src_smax; S.src_ncols = G.src_ncols; S.src_pcol0 = G.src_pcol0; S.src_region = G.src_region;
+    S.tab_off = (int32_t)G.tab_off;
+    S.gshift = -1;
+    for (int sh = 0; sh < 31; ++sh)
+      if ((1 << sh) == G.group) S.gshift = sh;
+  }
   H->magic = kChMagic; H->n_groups = (uint32_t)n_groups; H->M = (uint32_t)M; H->n_cta = (uint32_t)ncta; H->max_tiles = (uint32_t)max_tiles;
   H->region_elems = (uint64_t)smax_all * M * ncols_all;
   H->ws_bytes = kCounterBytes + kChWsHdr + 2ull * H->region_elems * 8ull;
@@ -798,6 +867,13 @@ int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int 
   if (slots < 8) return B200Q_ERR_UNSUPPORTED;
   H->slots = (uint32_t)slots;
   H->off_ring = so; so += (uint32_t)slots * kSlabBytes;
+  H->off_gs = so;
+  int ncached = (int)((budget - so) / sizeof(ChGS));
+  if (ncached > n_groups) ncached = n_groups;
+  if (ncached < 0) ncached = 0;
+  H->n_cached = (uint32_t)ncached;
+  so += (uint32_t)(ncached * sizeof(ChGS));
+  H->window = (uint32_t)((g_ch_window > 0 && g_ch_window <= slots) ? g_ch_window : (slots < 8 ? slots : 8));
   H->smem_bytes = so + 1024u;
   H->total_bytes = (uint32_t)need;
   if (ws_bytes) *ws_bytes = (size_t)H->ws_bytes;

@@ -26,7 +26,7 @@ def main(blocks=6, reps=3):
     qllm_b200.lib.b200q_debug_set_chain_timeline(None)
     t = buf.cpu().numpy().reshape(n_steps, sms, 16).astype(np.float64)
     t0 = t[0, :, 0][t[0, :, 0] > 0].min()
-    names = ["start", "x_ready", "digits", "own_units", "all_units", "stored", "barrier", "y_written", "prod_first", "prod_last"]
+    names = ["start", "x_ready", "digits", "own_units", "all_units", "stored", "fin_start", "y_written", "prod_first", "prod_last"]
     kinds = ["qkv", "o", "gate|up", "down"]
     for g in range(n_steps):
         row = f"{g:3d} {kinds[g % 4]:8s}"
@@ -39,6 +39,8 @@ def main(blocks=6, reps=3):
             row += f" {nm}[{v.min():7.2f},{np.median(v):7.2f},{v.max():7.2f}]"
         st = t[g, :, 10] / 1e3
         row += f" stall_us[med {np.median(st):5.2f} max {st.max():5.2f}]"
+        nu = np.maximum(t[g, :, 12], 1)
+        row += f" w0: units {np.median(t[g, :, 12]):.0f} wait_cyc/unit {np.median(t[g, :, 11] / nu):.0f} loop_cyc/unit {np.median(t[g, :, 13] / nu):.0f}"
         print(row)
     total = (t[n_steps - 1, :, 7].max() - t0) / 1e3
     print(f"total {total:.2f} us for {blocks} blocks = {total / blocks:.2f} us / block")
