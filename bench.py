@@ -500,7 +500,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200q", choices=["b200q", "reference"])
-    ap.add_argument("--chain", type=int, default=32,
+    ap.add_argument("--chain", type=int, default=0,
                     help="decoder blocks per decode-chain launch (b200q_chain_run); 0 = one launch per sibling group (b200q_linear_group)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prefill", action="store_true")
