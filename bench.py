@@ -9,7 +9,7 @@ going through the C ABI exactly as QuantLinear.forward does: siblings that share
 b200q_linear_group launch (the host shim's fuse_siblings), the others as b200q_linear -- 128 launches, 224 layers.
 A "step" = one token through all 224 layers.  3.4 GB of distinct packed weights: far larger than L2.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200q|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200q|reference] [--config decode7b|prefill7b|act13b|mixtral]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1: column-sharded)
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
@@ -30,6 +30,25 @@ HIDDEN, INTER, BLOCKS, GROUP, BITS = 4096, 11008, 32, 128, 4
 METRIC = "llama2_7b_int4_g128_quantlinear_decode_tokens_per_s"
 SHAPES = [("q", HIDDEN, HIDDEN), ("k", HIDDEN, HIDDEN), ("v", HIDDEN, HIDDEN), ("o", HIDDEN, HIDDEN),
           ("gate", HIDDEN, INTER), ("up", HIDDEN, INTER), ("down", INTER, HIDDEN)]
+LAYOUT, WORKLOAD = "GEMM", None
+
+# BASELINE.json configs: [1] = decode7b (the configuration the metric is quoted on, default), [2] = prefill7b,
+# [3] = act13b, [4] = mixtral.  configs[0] (CPU plumbing) is the reference arm.
+CONFIGS = {
+    "decode7b": dict(hidden=4096, inter=11008, blocks=32, layout="GEMM", metric=METRIC),
+    "prefill7b": dict(hidden=4096, inter=11008, blocks=32, layout="GPTQ", metric="llama2_7b_int4_g128_gptq_quantlinear_prefill_m512_tflops"),
+    "act13b": dict(hidden=5120, inter=13824, blocks=40, layout="GPTQ_ACT",
+                   metric="llama2_13b_int4_g128_gptq_actorder_quantlinear_decode_tokens_per_s"),
+    "mixtral": dict(hidden=4096, inter=14336, blocks=1, layout="HQQ", metric="mixtral_8x7b_expert_ffn_hqq_decode_expert_tokens_per_s"),
+}
+
+
+def select_config(name):
+    global HIDDEN, INTER, BLOCKS, METRIC, SHAPES, LAYOUT
+    c = CONFIGS[name]
+    HIDDEN, INTER, BLOCKS, METRIC, LAYOUT = c["hidden"], c["inter"], c["blocks"], c["metric"], c["layout"]
+    SHAPES = [("q", HIDDEN, HIDDEN), ("k", HIDDEN, HIDDEN), ("v", HIDDEN, HIDDEN), ("o", HIDDEN, HIDDEN),
+              ("gate", HIDDEN, INTER), ("up", HIDDEN, INTER), ("down", INTER, HIDDEN)]
 
 
 def peaks():
@@ -95,38 +114,49 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """Reference arm: the reference's own CPU implementation of the path (torch dequant + matmul,
-    restated in oracle/cpu_baseline.py because /root/reference does not travel), all host threads,
-    each step a bounded sample (one decoder block = 7 QuantLinears) extrapolated to 32 blocks."""
+    restated in oracle/cpu_baseline.py because /root/reference does not travel; pinned to the reference's
+    own forward outputs by tests/test_oracle_golden.py), on ALL host threads (torchrun exports OMP_NUM_THREADS=1).
+    A timed step is the whole token: the 7 QuantLinears of a decoder block x 32 blocks (the blocks reuse one
+    block's packed buffers -- CPU time does not depend on the values); warm-up steps run one block each."""
     if rank != 0:
         return
     import torch
     from oracle import cpu_baseline as C
+    torch.set_num_threads(os.cpu_count() or 1)
     steps, warm = max(1, args.steps), max(1, args.warmup)
     layers = C.make_block(HIDDEN, INTER, GROUP, BITS, torch.float16)
     h = torch.randn(1, HIDDEN).to(torch.float16)
 
-    def block():
+    def block(x):
         fw = lambda i, x: C.quant_linear_forward(x, layers[i][2], layers[i][3], layers[i][4], GROUP, BITS, layers[i][0])
-        q, k, v = fw(0, h), fw(1, h), fw(2, h)
+        q, k, v = fw(0, x), fw(1, x), fw(2, x)
         o = fw(3, v)
         gt, up = fw(4, o), fw(5, o)
         return fw(6, gt)
 
     for _ in range(warm):
-        block()
+        block(h)
+    # bound the run: whole tokens while they fit ~150 s, else fewer blocks per step (reported)
+    t0 = time.perf_counter()
+    block(h)
+    t_block = time.perf_counter() - t0
+    blocks_per_step = BLOCKS if t_block * BLOCKS * steps <= 150.0 else max(1, int(150.0 / (t_block * steps)))
     t0 = time.perf_counter()
     for _ in range(steps):
-        block()
+        x = h
+        for _ in range(blocks_per_step):
+            x = block(x)
     dt = (time.perf_counter() - t0) / steps
-    tok_s = 1.0 / (dt * BLOCKS)
+    tok_s = blocks_per_step / (dt * BLOCKS)
     cores = torch.get_num_threads()
-    sample = f"1 of {BLOCKS} decoder blocks (7 QuantLinears, M=1, fp16) per step, x{BLOCKS} extrapolated"
+    sample = (f"{blocks_per_step} of {BLOCKS} decoder blocks ({7 * blocks_per_step} QuantLinears, M=1, fp16) timed per step"
+              + ("" if blocks_per_step == BLOCKS else f", x{BLOCKS / blocks_per_step:.2f} extrapolated"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": dt * BLOCKS * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": "Llama-2-7B int4 g128 QuantLinear decode, M=1 (reference torch-CPU dequant+matmul, GPTQ layout)",
-                   "layers": 7 * BLOCKS},
+                   "layers": 7 * BLOCKS, "blocks_timed_per_step": blocks_per_step, "extrapolated": blocks_per_step != BLOCKS},
         "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -159,6 +189,9 @@ def build_model(dev, rank, world, layout="GEMM"):
                 l = qllm_b200.QuantLinearGPTQ(BITS, GROUP, K, n, False, dtype=torch.float16)
                 l.qweight, l.qzeros = ri(K * BITS // 32, n), ri(G, n * BITS // 32)
                 l.g_idx = l.g_idx.to(dev)
+                if layout == "GPTQ_ACT":                  # desc_act checkpoint: every group's rows scattered over K (same map on every rank)
+                    gp = torch.Generator(device=dev).manual_seed(99 + K)
+                    l.g_idx = l.g_idx[torch.randperm(K, device=dev, generator=gp)].contiguous()
             l.scales = ((torch.rand(G, n, device=dev, generator=g) * 0.4 + 0.8) / (6.5 * K ** 0.5)).to(torch.float16)
             l = l.to(dev)
             l.col0, l.full_n = c0, N
@@ -347,11 +380,11 @@ def run_b200q(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     P = peaks()
     steps, warm = max(1, args.steps), max(3, args.warmup)
-    blocks = build_model(dev, rank, world, "GEMM")
+    blocks = build_model(dev, rank, world, LAYOUT)
     M = 1
     fused_err = None
     step = None
-    if world > 1 and os.environ.get("B200Q_BENCH_NCCL") is None:
+    if world > 1 and os.environ.get("B200Q_BENCH_NCCL") is None and LAYOUT != "GPTQ_ACT":   # x_perm layers cannot read tagged activations yet
         try:
             step = FusedShardedStep(blocks, dev, M, rank, world)
         except Exception as e:                            # symmetric memory unavailable: NCCL all-gather per layer
@@ -389,11 +422,15 @@ def run_b200q(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(warm):
-        graph.replay()
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
+        t_w = time.perf_counter()
+        for _ in range(warm):
+            graph.replay()
+        barrier()
+        while time.perf_counter() - t_w < 0.35:      # nvidia-smi's first sample takes ~0.2 s: keep the GPU under the same load until it reports
+            graph.replay()
+        barrier()
         e0.record()
         for _ in range(steps):
             graph.replay()
@@ -426,7 +463,7 @@ def run_b200q(args, rank, world, local_rank):
 
     if rank != 0:
         return
-    total_bytes = BLOCKS * sum(alg_bytes(K, N, M) for _, K, N in SHAPES)
+    total_bytes = BLOCKS * sum(alg_bytes(K, N, M) + (K * 4 if LAYOUT == "GPTQ_ACT" else 0) for _, K, N in SHAPES)
     n_layers = BLOCKS * len(SHAPES)
     achieved = total_bytes * world / world / (ms_per_step * 1e-3) / 1e9      # whole-job algorithmic GB/s
     roofline = {"bound": "hbm", "achieved": achieved / world, "peak": P["hbm_gbs"], "unit": "GB/s",
@@ -442,7 +479,8 @@ def run_b200q(args, rank, world, local_rank):
         "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": "Llama-2-7B int4 g128 AWQ pack_mode=GEMM, batch=1 decode: the 224 QuantLinear layers of one token "
+        "config": {"workload": ("Llama-2-7B int4 g128 AWQ pack_mode=GEMM" if LAYOUT == "GEMM" else "Llama-2-13B int4 g128 GPTQ act_order (g_idx gather)")
+                               + f", batch=1 decode: the {n_layers} QuantLinear layers of one token "
                                "in LlamaDecoderLayer dependency order (q|k|v -> o -> gate|up -> down)",
                    "launches_per_step": int(launches_per_step), "chain_blocks_per_launch": chain_span, "sibling_groups": bool(step.fuse and world == 1),
                    "M": M, "layers": n_layers, "parallelism": (f"column-shard x{world}, all-gather + hand-off fused into the decode kernels (NVLink peer stores, "
@@ -458,10 +496,11 @@ def run_b200q(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu:
         from oracle import cpu_baseline as C
-        t_block = C.time_block(M=1, repeats=3)
+        torch.set_num_threads(os.cpu_count() or 1)
+        t_block = C.time_block(M=1, repeats=3, hidden=HIDDEN, inter=INTER)
         result["cpu_baseline"] = {"value": 1.0 / (t_block * BLOCKS), "unit": "tokens/s", "cores": torch.get_num_threads(),
                                   "kind": "port", "sample": f"1 of {BLOCKS} decoder blocks (7 QuantLinears, M=1, fp16 torch-CPU dequant+matmul), best of 3, x{BLOCKS}"}
-    if world == 1 and not args.no_prefill:
+    if world == 1 and not args.no_prefill and args.config == "decode7b":
         try:
             result["prefill"] = prefill_tflops(dev, P)
         except Exception as e:                       # the decode metric stands on its own
@@ -494,6 +533,201 @@ def prefill_tflops(dev, P, M=512, iters=20):
             "frac_of_bf16_peak": tf / P["bf16_tflops"], "peak": P["bf16_tflops"], "kernel": "gemm_tc_gptq4_kernel (tcgen05)"}
 
 
+def _timed(fn, steps, warm, barrier):
+    """W warm-up + K timed replays of fn() on the current stream, CUDA events; returns ms per step."""
+    import torch
+    for _ in range(warm):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def run_prefill(args, rank, world, local_rank):
+    """configs[2]: Llama-2-7B GPTQ int4 g128, 512 rows per QuantLinear call (the graded prefill tile), the 224 layers of
+    the model chained as in LlamaDecoderLayer, one CUDA graph; single GPU (N > 1: independent replicas, weak scaling)."""
+    import torch
+    import torch.distributed as dist
+    import qllm_b200
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    P = peaks()
+    steps, warm, M = max(1, args.steps), max(3, args.warmup), args.m if args.m > 0 else 512
+    blocks = build_model(dev, 0, 1, "GPTQ")
+    h = torch.zeros(M, HIDDEN, dtype=torch.float16, device=dev)
+    h0 = torch.randn(M, HIDDEN, generator=torch.Generator().manual_seed(7)).to(torch.float16).pin_memory()
+    y_pinned = torch.empty(M, HIDDEN, dtype=torch.float16).pin_memory()
+    h.copy_(h0)
+
+    def forward():
+        x = h
+        for b in blocks:
+            q, k, v = b["q"](x), b["k"](x), b["v"](x)
+            o = b["o"](v)
+            gt, up = b["gate"](o), b["up"](o)
+            x = b["down"](gt)
+        return x
+
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        out = forward()
+    s.synchronize()
+    n0 = qllm_b200.lib.b200q_launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        out = forward()
+    launches = qllm_b200.lib.b200q_launch_count() - n0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with ClockSampler(local_rank) as clk:
+        ms = _timed(graph.replay, steps, warm, barrier)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            h.copy_(h0, non_blocking=True)
+            graph.replay()
+            y_pinned.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / steps
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = t.tolist()
+    if rank != 0:
+        return
+    flops = 2.0 * M * BLOCKS * sum(K * N for _, K, N in SHAPES)
+    tf = flops / (ms * 1e-3) / 1e12
+    peak = P.get("bf16_tflops_sustained", P["bf16_tflops"])
+    print(json.dumps({
+        "metric": METRIC, "value": tf * world, "unit": "TFLOP/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"Llama-2-7B int4 g128 GPTQ, prefill tile M={M} rows per QuantLinear call: the 224 layers of the model "
+                               "(q,k,v -> o -> gate,up -> down), one CUDA graph", "M": M, "layers": BLOCKS * len(SHAPES),
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
+                   "l2_policy": "inputs (3.4 GB packed weights) larger than L2", "cuda_graph": True,
+                   "outputs_finite": bool(torch.isfinite(out.float()).all().item())},
+        "clocks": clk.summary(),
+        "e2e": {"value": flops / e2e_s / 1e12 * world, "unit": "TFLOP/s", "h2d_bytes_per_step": M * HIDDEN * 2, "d2h_bytes_per_step": M * HIDDEN * 2},
+        "gpu_launches": int(launches * steps),
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                     "peak_source": P["source"] + " (sustained: the kernel is timed inside a long step)",
+                     "kernel": "gemm_tc_gptq_kernel (tcgen05.mma kind::f16, W dequantised into TMEM, X by TMA)",
+                     "flops_per_launch": flops / launches, "us_per_launch": ms * 1e3 / launches, "frac_of_burst_peak": tf / P["bf16_tflops"]},
+    }), flush=True)
+
+
+def run_mixtral(args, rank, world, local_rank):
+    """configs[4]: Mixtral-8x7B expert FFN (w1, w3: 4096 -> 14336; w2: 14336 -> 4096), HQQ layouts.  Headline: 4-bit g64, one
+    token per expert (M = 1): (token, expert) FFN evaluations per second over the 8 experts of one layer; experts are
+    split across the ranks (expert parallel, no collective inside the path).  `sweep`: the other (bits, group, M)."""
+    import torch
+    import torch.distributed as dist
+    import qllm_b200
+    from tools.microbench import rand_layer
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    P = peaks()
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    experts = [e for e in range(8) if e % world == rank]
+
+    def build(bits, gs):
+        return [dict(w1=rand_layer("HQQ", bits, gs, HIDDEN, INTER, dev, 10 * e + 1), w3=rand_layer("HQQ", bits, gs, HIDDEN, INTER, dev, 10 * e + 2),
+                     w2=rand_layer("HQQ", bits, gs, INTER, HIDDEN, dev, 10 * e + 3)) for e in experts]
+
+    def make_graph(ex, M):
+        x = torch.randn(M, HIDDEN, dtype=torch.float16, device=dev)
+
+        def fwd():
+            outs = []
+            for e in ex:
+                a, b = qllm_b200.linear_group([e["w1"], e["w3"]], x) if M <= 8 else (e["w1"](x), e["w3"](x))
+                outs.append(e["w2"](a))                                       # silu(a) * b is outside the QuantLinear path
+            return outs
+
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fwd()
+        s.synchronize()
+        n0 = qllm_b200.lib.b200q_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            outs = fwd()
+        return g, x, outs, qllm_b200.lib.b200q_launch_count() - n0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def bytes_per_expert(bits, gs, M):
+        tot = 0
+        for K, N in ((HIDDEN, INTER), (HIDDEN, INTER), (INTER, HIDDEN)):
+            G = K // gs
+            tot += K * N * bits // 8 + G * N * 2 + G * N * 2 + M * K * 2 + M * N * 2
+        return tot
+
+    ex = build(4, 64)
+    g, x, outs, launches = make_graph(ex, 1)
+    x_pinned = torch.randn(1, HIDDEN).to(torch.float16).pin_memory()
+    y_pinned = torch.empty(1, HIDDEN, dtype=torch.float16).pin_memory()
+    with ClockSampler(local_rank) as clk:
+        ms = _timed(g.replay, steps, warm, barrier)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            x.copy_(x_pinned, non_blocking=True)
+            g.replay()
+            y_pinned.copy_(outs[-1], non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / steps
+    sweep = []
+    if world == 1 and not args.no_sweep:
+        for bits, gs in ((4, 64), (2, 64), (3, 64), (8, 128)):
+            if (bits, gs) != (4, 64):
+                del ex
+                torch.cuda.empty_cache()
+                ex = build(bits, gs)
+            for M in (1, 16, 512):
+                g2, _, _, _ = make_graph(ex, M)
+                t = _timed(g2.replay, max(5, steps // 4), 3, barrier)
+                b = bytes_per_expert(bits, gs, M) * len(ex)
+                fl = 2.0 * M * 3 * HIDDEN * INTER * len(ex)
+                sweep.append({"bits": bits, "group": gs, "M": M, "ms": round(t, 4), "GBps": round(b / t / 1e6, 1),
+                              "hbm_frac": round(b / t / 1e6 / P["hbm_gbs"], 3), "TFLOPs": round(fl / t / 1e9, 1)})
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = t.tolist()
+    if rank != 0:
+        return
+    b = bytes_per_expert(4, 64, 1) * len(ex)
+    print(json.dumps({
+        "metric": METRIC, "value": 8 / (ms * 1e-3), "unit": "expert-tokens/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "Mixtral-8x7B expert FFN QuantLinears (w1|w3 4096->14336, w2 14336->4096), HQQ 4-bit g64, M=1 per expert, "
+                               "the 8 experts of one layer", "experts_per_rank": len(ex), "parallelism": "single GPU" if world == 1 else f"expert parallel x{world} (no collective)",
+                   "l2_policy": "inputs (8 x 99 MB packed weights) larger than L2", "cuda_graph": True},
+        "clocks": clk.summary(),
+        "e2e": {"value": 8 / e2e_s, "unit": "expert-tokens/s", "h2d_bytes_per_step": HIDDEN * 2, "d2h_bytes_per_step": HIDDEN * 2},
+        "gpu_launches": int(launches * steps),
+        "roofline": {"bound": "hbm", "achieved": b / ms / 1e6, "peak": P["hbm_gbs"], "unit": "GB/s", "frac": b / ms / 1e6 / P["hbm_gbs"],
+                     "traffic": None, "peak_source": P["source"], "kernel": "gemv_imma_kernel (HQQ fp16 zeros)", "per_gpu": True,
+                     "bytes_per_launch": b / launches, "us_per_launch": ms * 1e3 / launches},
+        "sweep": sweep,
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -502,12 +736,18 @@ def main():
     ap.add_argument("--impl", default="b200q", choices=["b200q", "reference"])
     ap.add_argument("--chain", type=int, default=0,
                     help="decoder blocks per decode-chain launch (b200q_chain_run); 0 = one launch per sibling group (b200q_linear_group)")
+    ap.add_argument("--config", default="decode7b", choices=sorted(CONFIGS),
+                    help="BASELINE.json workload: decode7b = configs[1] (default, the configuration the metric is quoted on), "
+                         "prefill7b = configs[2], act13b = configs[3], mixtral = configs[4]")
+    ap.add_argument("--m", type=int, default=0, help="prefill7b: rows per QuantLinear call (default 512)")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prefill", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    select_config(args.config)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -517,7 +757,12 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_b200q(args, rank, world, local_rank)
+        if args.config == "prefill7b":
+            run_prefill(args, rank, world, local_rank)
+        elif args.config == "mixtral":
+            run_mixtral(args, rank, world, local_rank)
+        else:
+            run_b200q(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -232,12 +232,26 @@ int b200q_unpack(const b200q_layer* layer, int32_t* q_out, int32_t* z_out, b200q
 /*
  * One-time exact integer re-layout of a 4-bit AWQ-GEMM or Marlin layer into the K-packed GPTQ layout
  * (qweight i32 [K/8, N], qzeros i32 [G, N/8] holding z with bias 0, scales fp16 [G, N] natural order).
- * Used by the host shim to give the tcgen05 GEMM a K-packed copy of layouts whose native GEMM producer is
- * not written yet; the decode kernels always read the checkpoint bytes in place.  Device restatement of
+ * The host shim re-lays an AWQ-GEMM / Marlin layer out ONCE (first forward), releases the checkpoint-format buffers and
+ * runs every kernel on the K-packed copy (zero extra weight memory; b200q_repack_from_gptq4 restores the checkpoint
+ * format for state_dict()).  GPTQ / HQQ checkpoints are consumed in place.  Device restatement of
  * the unpack -> pack round trip of repack_to_new_mode (qllm/auto_model_quantization.py:115-147) without
  * the fp16 dequant/requant in the middle.
  */
 int b200q_repack_gptq4(const b200q_layer* layer, void* qweight_out, void* qzeros_out, void* scales_out, b200q_stream_t stream);
+
+/*
+ * The inverse of b200q_repack_gptq4 (exact): a K-packed 4-bit layer (layout GPTQ, g_idx == NULL) -> the buffers of
+ * target_layout = B200Q_LAYOUT_AWQ_GEMM (qweight [K, N/8], qzeros [G, N/8], scales [G, N]) or B200Q_LAYOUT_MARLIN
+ * (qweight [K/16, 2N], scales [G, N] in Marlin's permuted order; qzeros_out ignored -- the caller guarantees z == 8),
+ * bit-identical to what WQLinear_GEMM.pack / QuantLinearMarlin.pack produce from the same integers
+ * (quant_linear_awq.py:95-140, quant_linear_marlin.py:95-137).  Together with b200q_repack_gptq4 this is the integer
+ * core of `--pack_mode` conversion (repack_to_new_mode, qllm/auto_model_quantization.py:115-147) without the fp16
+ * dequantise / re-quantise round trip, and it lets the host shim keep ONE packed copy of an AWQ / Marlin layer in HBM
+ * (the K-packed one the kernels read) while state_dict() still returns the checkpoint's own format.
+ */
+int b200q_repack_from_gptq4(const b200q_layer* layer, int32_t target_layout, void* qweight_out, void* qzeros_out, void* scales_out,
+                            b200q_stream_t stream);
 
 /*
  * Act-order (desc_act) checkpoints: qweight_out[K*b/32, N] = the layer's packed rows re-ordered so that packed row j

@@ -37,7 +37,7 @@ EXPORTS = ["b200q_linear", "b200q_linear_group", "b200q_gemv", "b200q_gemm", "b2
            "b200q_workspace_bytes", "b200q_gemv_max_m", "b200q_select_kernel", "b200q_launch_count",
            "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4", "b200q_debug_decode_plan", "b200q_debug_set_option", "b200q_linear_group_sharded", "b200q_sharded_posts",
            "b200q_peer_epoch_advance", "b200q_peer_wait", "b200q_peer_untag", "b200q_repack_actorder",
-           "b200q_chain_plan_bytes", "b200q_chain_plan", "b200q_chain_run", "b200q_debug_set_chain_timeline"]
+           "b200q_repack_from_gptq4", "b200q_chain_plan_bytes", "b200q_chain_plan", "b200q_chain_run", "b200q_debug_set_chain_timeline"]
 
 
 def _load():
@@ -91,6 +91,8 @@ def _load():
     lib.b200q_repack_actorder.restype = ctypes.c_int
     lib.b200q_repack_gptq4.argtypes = [LP, P, P, P, P]
     lib.b200q_repack_gptq4.restype = ctypes.c_int
+    lib.b200q_repack_from_gptq4.argtypes = [LP, ctypes.c_int32, P, P, P, P]
+    lib.b200q_repack_from_gptq4.restype = ctypes.c_int
     lib.b200q_workspace_bytes.argtypes = [LP, I64]
     lib.b200q_workspace_bytes.restype = SZ
     lib.b200q_gemv_max_m.restype = ctypes.c_int

@@ -529,6 +529,24 @@ int b200q_repack_gptq4(const b200q_layer* layer, void* qweight_out, void* qzeros
                                          (cudaStream_t)stream));
 }
 
+int b200q_repack_from_gptq4(const b200q_layer* layer, int32_t target_layout, void* qweight_out, void* qzeros_out, void* scales_out,
+                            b200q_stream_t stream) {
+  const int v = validate(layer);
+  if (v != B200Q_OK) return v;
+  if (!qweight_out || !scales_out) return B200Q_ERR_NULL;
+  if (layer->layout != B200Q_LAYOUT_GPTQ || layer->bits != 4 || layer->g_idx || layer->x_perm || layer->K % 8 != 0) return B200Q_ERR_UNSUPPORTED;
+  if (target_layout == B200Q_LAYOUT_AWQ_GEMM) {
+    if (!qzeros_out) return B200Q_ERR_NULL;
+  } else if (target_layout == B200Q_LAYOUT_MARLIN) {
+    if (layer->K % 16 != 0 || layer->N % 64 != 0) return B200Q_ERR_SHAPE;          // tile permutation granularity
+    if (layer->group_size != 128 && layer->group_size != layer->K) return B200Q_ERR_UNSUPPORTED;   // quant_linear_marlin.py:78-80
+  } else {
+    return B200Q_ERR_UNSUPPORTED;
+  }
+  return cuda_status(launch_repack_from_gptq4(make_view(layer), target_layout, (uint32_t*)qweight_out, (uint32_t*)qzeros_out,
+                                              (__half*)scales_out, (cudaStream_t)stream));
+}
+
 size_t b200q_workspace_bytes(const b200q_layer* layer, int64_t M) {
   if (validate(layer) != B200Q_OK || M < 1) return 0;
   gemv_variant();

@@ -22,6 +22,8 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include <mutex>
+
 #include "kernels.h"
 
 namespace b200q {
@@ -530,11 +532,45 @@ static EncodeTiledFn get_encode() {
 
 static unsigned long long* g_tc_dbg = nullptr;
 void gemm_tc_set_debug(unsigned long long* buf) { g_tc_dbg = buf; }
-static int* g_err_flag = nullptr;      // device int, lazily allocated (diagnostic only)
-int gemm_tc_last_error() {
-  int v = 0;
-  if (g_err_flag) cudaMemcpy(&v, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost);
-  return v;
+// bring-up aid (B200Q_BOUNDED_WAITS builds only): a CALLER-provided device int that receives the code of a wait that
+// gave up.  The library itself never allocates (b200q.h): without a flag the kernels run with err == nullptr.
+static int* g_err_flag = nullptr;
+void gemm_tc_set_error_flag(int* device_flag) { g_err_flag = device_flag; }
+
+// TMA descriptors are a pure function of (base pointer, shape, strides, box, swizzle): encoded once, then served from a
+// small direct-mapped cache (cuTensorMapEncodeTiled costs ~1-2 us of host time per call, twice per GEMM launch).
+struct TmapKey {
+  const void* base;
+  uint64_t d0, d1, stride;
+  uint32_t b0, b1, dtype, swizzle;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1 && dtype == o.dtype && swizzle == o.swizzle;
+  }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool valid; };
+static constexpr int kTmapSlots = 2048;
+static TmapSlot g_tmaps[kTmapSlots];
+static std::mutex g_tmap_mu;
+static bool cached_tmap_2d(EncodeTiledFn enc, CUtensorMap* out, CUtensorMapDataType dtype, const void* base, uint64_t d0, uint64_t d1,
+                           uint64_t stride_bytes, uint32_t b0, uint32_t b1, CUtensorMapSwizzle swz) {
+  const TmapKey key{base, d0, d1, stride_bytes, b0, b1, (uint32_t)dtype, (uint32_t)swz};
+  uint64_t h = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
+  h ^= (d0 * 0xC2B2AE3D27D4EB4Full) ^ (d1 * 0x165667B19E3779F9ull) ^ (stride_bytes << 7) ^ ((uint64_t)b0 << 40) ^ ((uint64_t)b1 << 20) ^ swz;
+  TmapSlot& sl = g_tmaps[(h >> 17) % kTmapSlots];
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (sl.valid && sl.key == key) { *out = sl.map; return true; }
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+  cuuint64_t strides[1] = {(cuuint64_t)stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)b0, (cuuint32_t)b1};
+  cuuint32_t es[2] = {1, 1};
+  if (enc(out, dtype, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  sl.key = key; sl.map = *out; sl.valid = true;
+  return true;
 }
 
 static int g_tc_pdl = 1;                  // B200Q_GEMM_PDL=0 / option "gemm_pdl": plain stream-ordered launches
@@ -577,28 +613,12 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return cudaErrorNotSupported;
   CUtensorMap xmap, wmap;
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)L.K, (cuuint64_t)a.M};
-    cuuint64_t strides[1] = {(cuuint64_t)a.ldx * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)TT};
-    cuuint32_t es[2] = {1, 1};
-    if (enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)a.x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return cudaErrorInvalidValue;
-  }
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)L.N, (cuuint64_t)(L.K * BITS / 32)};
-    cuuint64_t strides[1] = {(cuuint64_t)L.N * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kBN, (cuuint32_t)(kBK * BITS / 32)};
-    cuuint32_t es[2] = {1, 1};
-    if (enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)L.qw, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return cudaErrorInvalidValue;
-  }
-  if (!g_err_flag) {
-    if (cudaMalloc(&g_err_flag, sizeof(int)) != cudaSuccess) return cudaErrorMemoryAllocation;
-    cudaMemset(g_err_flag, 0, sizeof(int));
-  }
+  if (!cached_tmap_2d(enc, &xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.x, (uint64_t)L.K, (uint64_t)a.M, (uint64_t)a.ldx * 2, (uint32_t)kBK,
+                      (uint32_t)TT, CU_TENSOR_MAP_SWIZZLE_128B))
+    return cudaErrorInvalidValue;
+  if (!cached_tmap_2d(enc, &wmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, L.qw, (uint64_t)L.N, (uint64_t)(L.K * BITS / 32), (uint64_t)L.N * 4,
+                      (uint32_t)kBN, (uint32_t)(kBK * BITS / 32), CU_TENSOR_MAP_SWIZZLE_NONE))
+    return cudaErrorInvalidValue;
   TcParams p;
   p.L = L; p.M = a.M;
   if (peers) p.out = *peers; else { p.out.n = 1; p.out.y[0] = a.y; }

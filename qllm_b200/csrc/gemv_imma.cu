@@ -8,7 +8,8 @@
 //   * a packed word (8 consecutive k of one column) becomes two MMA operand registers with three ALU ops:
 //     (w & 0x0f0f0f0f) = the even k as four u8, ((w >> 4) & 0x0f0f0f0f) = the odd k -- no magic numbers, no pairing;
 //   * the activations are split ONCE per launch into three balanced base-128 digits of a 21-bit fixed-point value
-//     (power-of-two scale per <= 128-k part, so nothing is lost against fp16's 11 bits); the three digits ride in three
+//     (power-of-two scale per <= 128-k part: block fixed point, an element below 2^-9 of its part's maximum keeps fewer
+//     than fp16's 11 bits -- an absolute error below 2^-21 of that maximum); the three digits ride in three
 //     of the eight B columns of the same mma.sync.m16n8k32.s32.u8.s8 (SASS IMMA.16832.U8.S8, 512 weights per
 //     instruction), whose int32 accumulation is exact; a second token uses columns 4..6;
 //   * per part: y += s * (2^-E * (d0 2^14 + d1 2^7 + d2) - z * sum(x)), fp32 -- the same algebra as the fp16 kernels.
@@ -185,6 +186,13 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
           const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
           xv[0] = __low2float(h01); xv[1] = __high2float(h01); xv[2] = __low2float(h23); xv[3] = __high2float(h23);
         }
+        // a NaN / Inf activation poisons its part (fmaxf drops NaN and the fixed-point conversion would turn Inf into
+        // finite garbage; the reference's fp16 FMA chains propagate both): every output of the layer becomes NaN
+        uint32_t bad = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bad |= ((__float_as_uint(xv[e]) & 0x7f800000u) == 0x7f800000u) ? 1u : 0u;
+        bad = __any_sync(0xffffffffu, bad);
+        if (bad) xv[0] = xv[1] = xv[2] = xv[3] = 0.f;
         float mx = fmaxf(fmaxf(fabsf(xv[0]), fabsf(xv[1])), fmaxf(fabsf(xv[2]), fabsf(xv[3])));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -208,7 +216,8 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
-        if (lane == 0) part[pi * MTOK + m] = make_float2(isc, (float)tsum * isc);
+        if (lane == 0) part[pi * MTOK + m] = bad ? make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000))
+                                                 : make_float2(isc, (float)tsum * isc);
         if (4 * lane < len) {
           // element e of this lane: k' = 4 (lane % 8) + e inside its sub-step -> word t' = (lane % 8) / 2, kk = 4 (lane & 1) + e:
           // even kk -> byte kk / 2 of the first half, odd kk -> byte kk / 2 of the second half

@@ -56,6 +56,7 @@ cudaError_t launch_dequant(const LayerView& L, __half* w_out, cudaStream_t st);
 cudaError_t launch_repack_actorder(const LayerView& L, const int* perm, uint32_t* qw_out, cudaStream_t st);
 cudaError_t launch_gather_x(const __half* x, int64_t ldx, const int* perm, __half* out, int M, int K, cudaStream_t st);
 cudaError_t launch_repack_gptq4(const LayerView& L, uint32_t* qw_out, uint32_t* qz_out, __half* s_out, cudaStream_t st);
+cudaError_t launch_repack_from_gptq4(const LayerView& L, int target, uint32_t* qw_out, uint32_t* qz_out, __half* s_out, cudaStream_t st);
 
 // gemv_generic.cu : any layout / bits / group / g_idx, M <= 16, CUDA cores
 size_t gemv_generic_workspace(const LayerView& L, int M);
@@ -117,5 +118,6 @@ void gemm_tc_set_tt256_min_m(int m);
 void gemm_tc_set_pdl(int on);
 void gemm_tc_set_splitk(int on);
 void gemm_tc_set_debug(unsigned long long* buf);
+void gemm_tc_set_error_flag(int* device_flag);   // bring-up builds (B200Q_BOUNDED_WAITS) only
 
 }  // namespace b200q

@@ -73,6 +73,48 @@ cudaError_t launch_repack_gptq4(const LayerView& L, uint32_t* qw_out, uint32_t* 
   return cudaGetLastError();
 }
 
+// The inverse re-layout (exact): K-packed GPTQ words -> AWQ-GEMM (target 1) or Marlin (target 2) buffers, i.e. what
+// WQLinear_GEMM.pack / QuantLinearMarlin.pack would have produced from the same integers (quant_linear_awq.py:95-140,
+// quant_linear_marlin.py:95-137).  One thread per element; nibbles are OR-ed into zero-initialised outputs.
+__global__ void __launch_bounds__(256) repack_from_gptq4_kernel(LayerView L, int target, uint32_t* __restrict__ qw_out,
+                                                                uint32_t* __restrict__ qz_out, __half* __restrict__ s_out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (size_t)L.K * L.N) {
+    const int k = (int)(idx / L.N), n = (int)(idx % L.N);
+    const uint32_t q = load_q(L, k, n) & 0xFu;
+    if (target == B200Q_LAYOUT_AWQ_GEMM) {
+      atomicOr(qw_out + (size_t)k * (L.N >> 3) + (n >> 3), q << (4 * awq_nibble_of_col(n & 7)));
+    } else {
+      size_t word; int nib;
+      marlin_locate(k, n, L.N, word, nib);
+      atomicOr(qw_out + word, q << (4 * nib));
+    }
+  }
+  if (idx < (size_t)L.G * L.N) {
+    const int g = (int)(idx / L.N), n = (int)(idx % L.N);
+    if (target == B200Q_LAYOUT_AWQ_GEMM) {
+      atomicOr(qz_out + (size_t)g * (L.N >> 3) + (n >> 3), ((uint32_t)load_z(L, g, n) & 0xFu) << (4 * awq_nibble_of_col(n & 7)));
+      s_out[idx] = L.s[idx];
+    } else {
+      s_out[(size_t)g * L.N + marlin_scale_index(n, L.group == L.K)] = L.s[idx];
+    }
+  }
+}
+
+cudaError_t launch_repack_from_gptq4(const LayerView& L, int target, uint32_t* qw_out, uint32_t* qz_out, __half* s_out, cudaStream_t st) {
+  const size_t words = (size_t)(L.K >> 3) * L.N;                          // same word count in all three 4-bit layouts
+  cudaError_t e = cudaMemsetAsync(qw_out, 0, words * 4, st);
+  if (e != cudaSuccess) return e;
+  if (target == B200Q_LAYOUT_AWQ_GEMM) {
+    e = cudaMemsetAsync(qz_out, 0, (size_t)L.G * (L.N >> 3) * 4, st);
+    if (e != cudaSuccess) return e;
+  }
+  const size_t total = (size_t)L.K * L.N;
+  repack_from_gptq4_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, target, qw_out, qz_out, s_out);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // Act-order re-layout: packed row-block kw of the output holds original rows perm[P kw .. P kw + P - 1] (P = 32 / bits).
 __global__ void __launch_bounds__(256) repack_actorder_kernel(LayerView L, const int* __restrict__ perm, uint32_t* __restrict__ qw_out) {
   const int P = 32 / L.bits;

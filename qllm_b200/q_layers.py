@@ -32,6 +32,10 @@ DECODE_RELAYOUT = os.environ.get("B200Q_DECODE_RELAYOUT", "1") != "0"
 # Act-order (desc_act) GPTQ layers run on their exact row-permuted re-layout with activations gathered through the
 # permutation (b200q_repack_actorder + b200q_layer.x_perm); B200Q_ACTORDER_RELAYOUT=0 keeps them on the generic kernel.
 ACTORDER_RELAYOUT = os.environ.get("B200Q_ACTORDER_RELAYOUT", "1") != "0"
+# AWQ-GEMM / Marlin layers run on ONE packed copy: the exact K-packed re-layout built at first use, after which the
+# checkpoint-format buffers are released (state_dict() restores them through b200q_repack_from_gptq4).
+# B200Q_KEEP_NATIVE=1 keeps both copies resident (+0.5 B/weight) and lets 3 <= M <= 8 read the checkpoint bytes.
+KEEP_NATIVE = os.environ.get("B200Q_KEEP_NATIVE", "0") == "1"
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
@@ -77,8 +81,10 @@ class _B200QuantLinearBase(nn.Module):
     def _descriptor(self):
         if self.act_order is None:
             self.act_order = self._detect_act_order()
+        if getattr(self, "_consolidated", False):
+            return self._shadow_desc                      # the only packed copy left: the K-packed re-layout (same q, z, s)
         qw, qz, sc, gi, bias = self._tensors()
-        key = tuple(0 if t is None else t.data_ptr() for t in (qw, qz, sc, gi, bias))
+        key = self._buffer_key()
         if self._desc is None or key != self._desc_key:
             if not qw.is_cuda:
                 raise RuntimeError("qllm_b200 QuantLinear.forward needs CUDA buffers (no CPU fallback)")
@@ -104,8 +110,13 @@ class _B200QuantLinearBase(nn.Module):
             d.g_idx = gi.data_ptr() if gi is not None else None
             d.bias = self._bias16.data_ptr() if self._bias16 is not None else None
             self._desc = d
-            self._desc_key = tuple(0 if t is None else t.data_ptr() for t in self._tensors())
+            self._desc_key = self._buffer_key()
         return self._desc
+
+    def _buffer_key(self):
+        """Identity AND version of every buffer: an in-place update (load_state_dict without assign=True, .copy_())
+        keeps data_ptr() but bumps _version, and must invalidate the descriptor and every derived re-layout."""
+        return tuple((0, 0) if t is None else (t.data_ptr(), t._version) for t in self._tensors())
 
     # -- act-order: groups made contiguous once, activations gathered at run time ------------------
     def _fast_descriptor(self):
@@ -138,11 +149,15 @@ class _B200QuantLinearBase(nn.Module):
 
     # -- K-packed shadow for the tensor-core GEMM (AWQ / Marlin until their native producers exist) --
     def _gemm_descriptor(self):
-        """b200q_layer the tcgen05 GEMM can take.  GPTQ/HQQ: the checkpoint buffers themselves.  AWQ/Marlin:
-        a one-time exact integer re-layout (b200q_repack_gptq4) kept beside the native buffers."""
-        desc = self._descriptor()
+        """b200q_layer for the kernels that need K-packed words (tcgen05 GEMM, integer-path decode, decode chain).
+        GPTQ/HQQ: the checkpoint buffers themselves.  AWQ/Marlin: a one-time exact integer re-layout
+        (b200q_repack_gptq4); unless B200Q_KEEP_NATIVE=1 the checkpoint-format buffers are then released, so the
+        layer holds ONE packed copy (state_dict() restores the checkpoint format through b200q_repack_from_gptq4)."""
         if self._layout not in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN):
             return self._fast_descriptor()
+        if getattr(self, "_consolidated", False):
+            return self._shadow_desc
+        desc = self._descriptor()
         key = self._desc_key
         if getattr(self, "_shadow_key", None) != key:
             dev = self.qweight.device
@@ -157,12 +172,63 @@ class _B200QuantLinearBase(nn.Module):
             d.layout, d.bits, d.group_size, d.K, d.N, d.zero_bias = LAYOUT_GPTQ, 4, self.groupsize, K, N, 0
             d.qweight, d.qzeros, d.scales, d.g_idx, d.bias = qw.data_ptr(), qz.data_ptr(), sc.data_ptr(), None, desc.bias
             self._shadow, self._shadow_desc, self._shadow_key = (qw, qz, sc), d, key
+            if not KEEP_NATIVE:
+                self._release_native()
         return self._shadow_desc
+
+    # -- one packed copy: release / restore the checkpoint-format buffers --------------------------------
+    def _release_native(self):
+        self._native_meta = {n: (tuple(getattr(self, n).shape), getattr(self, n).dtype) for n in ("qweight", "qzeros", "scales")
+                             if isinstance(getattr(self, n, None), torch.Tensor)}
+        dev = self.qweight.device
+        for n, (_, dt) in self._native_meta.items():
+            setattr(self, n, torch.empty(0, dtype=dt, device=dev))
+        self._consolidated = True
+        self._desc = None
+
+    def _native_tensors(self):
+        """Checkpoint-format (qweight, qzeros, scales) rebuilt from the K-packed copy (exact)."""
+        qw, qz, sc = self._shadow
+        dev = qw.device
+        meta = self._native_meta
+        out_qw = torch.empty(meta["qweight"][0], dtype=torch.int32, device=dev)
+        out_qz = torch.empty(meta["qzeros"][0], dtype=torch.int32, device=dev) if "qzeros" in meta else None
+        out_sc = torch.empty(meta["scales"][0], dtype=torch.float16, device=dev)
+        check(lib.b200q_repack_from_gptq4(ctypes.byref(self._shadow_desc), self._layout, out_qw.data_ptr(),
+                                          None if out_qz is None else out_qz.data_ptr(), out_sc.data_ptr(),
+                                          torch.cuda.current_stream(dev).cuda_stream), "b200q_repack_from_gptq4")
+        return out_qw, out_qz, out_sc.to(meta["scales"][1])
+
+    def _restore_native(self):
+        if getattr(self, "_consolidated", False):
+            qw, qz, sc = self._native_tensors()
+            self.qweight, self.scales = qw, sc
+            if qz is not None:
+                self.qzeros = qz
+            self._consolidated = False
+            self._shadow = self._shadow_desc = self._shadow_key = None
+            self._desc = None
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        if getattr(self, "_consolidated", False):
+            qw, qz, sc = self._native_tensors()
+            super()._save_to_state_dict(destination, prefix, keep_vars)
+            destination[prefix + "qweight"], destination[prefix + "scales"] = qw, sc
+            if qz is not None:
+                destination[prefix + "qzeros"] = qz
+            return
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        self._restore_native()                      # buffers regain their checkpoint shapes before they are overwritten
+        self._desc = None
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def _decode_descriptor(self, M):
         """Descriptor the decode kernels should read at batch M: the checkpoint buffers, or -- AWQ-GEMM / Marlin at
         M <= 2 -- the one-time exact K-packed re-layout that the integer-tensor-path kernel consumes."""
-        if DECODE_RELAYOUT and M <= 2 and self._layout in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN):
+        if self._layout in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN) and ((DECODE_RELAYOUT and M <= 2) or not KEEP_NATIVE
+                                                                 or getattr(self, "_consolidated", False)):
             return self._gemm_descriptor()
         return self._fast_descriptor()
 
@@ -174,7 +240,7 @@ class _B200QuantLinearBase(nn.Module):
         return super().__call__(x)
 
     def forward(self, x):
-        desc = self._fast_descriptor()
+        desc = self._decode_descriptor(8) if self._layout in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN) else self._fast_descriptor()
         out_shape = x.shape[:-1] + (self.outfeatures,)
         x2 = x.reshape(-1, x.shape[-1])
         if x2.dtype != torch.float16:
@@ -358,11 +424,15 @@ class WQLinear_GEMM(_B200QuantLinearBase):
         self._desc = None
 
     def unpack(self):
-        q = codec.awq_unpack_qweight(self.qweight)
-        z = codec.awq_unpack_qzeros(self.qzeros)
+        if getattr(self, "_consolidated", False):
+            qw, qz, sc = self._native_tensors()
+        else:
+            qw, qz, sc = self.qweight, self.qzeros, self.scales
+        q = codec.awq_unpack_qweight(qw)
+        z = codec.awq_unpack_qzeros(qz)
         gi = self._default_g_idx().long().to(q.device)
-        w = ((q.float() - z.float()[gi]) * self.scales.float()[gi]).to(torch.float16)
-        return w.t().contiguous().cpu(), self.scales.cpu(), z.cpu()
+        w = ((q.float() - z.float()[gi]) * sc.float()[gi]).to(torch.float16)
+        return w.t().contiguous().cpu(), sc.cpu(), z.cpu()
 
 
 class QuantLinearMarlin(_B200QuantLinearBase):
@@ -407,7 +477,11 @@ class QuantLinearMarlin(_B200QuantLinearBase):
 
     def unpack(self):
         """The reference raises NotImplementedError here (quant_linear_marlin.py:139-140)."""
-        q, s = codec.marlin_unpack(self.qweight, self.scales, self.group_size, self.infeatures)
+        if getattr(self, "_consolidated", False):
+            qw, _, sc = self._native_tensors()
+        else:
+            qw, sc = self.qweight, self.scales
+        q, s = codec.marlin_unpack(qw, sc, self.group_size, self.infeatures)
         gi = self._default_g_idx().long().to(q.device)
         w = ((q.float() - 8.0) * s.float()[gi]).to(torch.float16)
         return w.t().contiguous().cpu(), s.cpu(), torch.full_like(s, 8, dtype=torch.int32).cpu()
@@ -425,7 +499,7 @@ def linear_group(layers, x):
         x2 = x2.contiguous()
     M = x2.shape[0]
     if M == 0 or M > lib.b200q_gemv_max_m() or any(l.infeatures != K for l in layers):
-        return [l(x) for l in layers]
+        return [_B200QuantLinearBase.forward(l, x) for l in layers]      # not l(x): that would re-enter the sibling group
     n = len(layers)
     ys = [torch.empty((M, l.outfeatures), dtype=torch.float16, device=x.device) for l in layers]
     LP = ctypes.POINTER(Layer)
@@ -458,7 +532,8 @@ class _SiblingGroup:
         key = (id(x), x._version, x.data_ptr(), tuple(x.shape))
         if self.key == key and id(layer) in self.parked:
             return self.parked.pop(id(layer))
-        if layer is not self.layers[0] or x.reshape(-1, x.shape[-1]).shape[0] > lib.b200q_gemv_max_m() or not x.is_cuda:
+        rows = x.reshape(-1, x.shape[-1]).shape[0]
+        if layer is not self.layers[0] or rows == 0 or rows > lib.b200q_gemv_max_m() or not x.is_cuda:
             return _B200QuantLinearBase.forward(layer, x)
         outs = linear_group(self.layers, x)
         self.key = key
@@ -482,7 +557,7 @@ def fuse_siblings(model, sibling_sets=SIBLING_SETS):
                 continue
             a = subs[0]
             if any(type(m) is not type(a) or m.bits != a.bits or m.groupsize != a.groupsize or m.infeatures != a.infeatures
-                   or getattr(m, "act_order", None) for m in subs):
+                   or m._detect_act_order() for m in subs):      # act_order itself is only filled in by the first forward
                 continue
             grp = _SiblingGroup(subs)
             for m in subs:

@@ -39,8 +39,9 @@ def test_awq_gemm_forward_cuda(M, gs, K, N):
     L = O.make_layer("GEMM", 4, gs, K, N, seed=K + N + M)
     layer = layer_from_dict(L)
     x = torch.randn(M, K, dtype=torch.float16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(M))
+    ref = awq.gemm_forward_cuda(x, layer.qweight, layer.scales, layer.qzeros, 8)     # quant_linear_awq.py:144-145 (before the
+    torch.cuda.synchronize()                                                          # first forward releases the AWQ-format buffers)
     y = layer(x)
-    ref = awq.gemm_forward_cuda(x, layer.qweight, layer.scales, layer.qzeros, 8)     # quant_linear_awq.py:144-145
     torch.cuda.synchronize()
     assert _rel(y, ref) < TOL
 
