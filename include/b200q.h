@@ -50,7 +50,14 @@ typedef enum b200q_layout {
   B200Q_LAYOUT_GPTQ = 0,     /* QuantLinearGPTQ   quant_linear_gptq.py:92-143  qweight i32 [K*b/32, N], qzeros i32 [G, N*b/32] */
   B200Q_LAYOUT_AWQ_GEMM = 1, /* WQLinear_GEMM     quant_linear_awq.py:38-153   qweight i32 [K, N/8],   qzeros i32 [G, N/8], nibble order 0,2,4,6,1,3,5,7 */
   B200Q_LAYOUT_MARLIN = 2,   /* QuantLinearMarlin quant_linear_marlin.py:60-146 qweight i32 [K/16, 2N], scales permuted, z == 8 */
-  B200Q_LAYOUT_HQQ = 3       /* QuantLinearHQQ    quant_linear_hqq.py:48-80    qweight as GPTQ, qzeros fp16 [G, N] */
+  B200Q_LAYOUT_HQQ = 3,      /* QuantLinearHQQ    quant_linear_hqq.py:48-80    qweight as GPTQ, qzeros fp16 [G, N] */
+  B200Q_LAYOUT_ORT = 5,      /* QuantLinearORT    quant_linear_onnxruntime.py:85-174 (com.microsoft::MatMulNBits blobs, 4-bit): qweight u8
+                                [N, G, group/2] (byte b of block (n, g) = q[g group + 2b] | q[.. + 1] << 4), qzeros u8 [N, ceil(G/2)]
+                                (byte j = z[2j] | z[2j+1] << 4), scales fp16 [N, G]; g_idx allowed (groups of scales / zeros only) */
+  B200Q_LAYOUT_AWQ_GEMV = 4  /* WQLinear_GEMV     quant_linear_awq.py:156-265  qweight i32 [N, K/8] (nibble i = k 8w+i), qzeros i32 [N, ZW]
+                                (nibble i of word c = group 8c+i), scales fp16 [N, 8 ZW], ZW = calculate_zeros_width (:15-27);
+                                kernels: gemv_cuda.cu:60-186, gemmv2 gemm_cuda_gen.cu:683-1094.  Unpack / dequant / the generic
+                                kernel read it in place; the fast kernels run on its exact K-packed re-layout (b200q_repack_gptq4) */
 } b200q_layout;
 
 /*
@@ -65,8 +72,8 @@ typedef struct b200q_layer {
   int32_t N;           /* out_features held by this rank (column shard width when sharded) */
   int32_t zero_bias;   /* added to unpacked integer zeros then masked: the reference's
                           COMPATIBLE_WITH_AUTOGPTQ env / add_zero_bias arg (ort_ops.cc:63). 0 or 1. */
-  const void* qweight; /* int32, shape per layout */
-  const void* qzeros;  /* int32 packed (GPTQ, AWQ_GEMM) | fp16 [G,N] (HQQ) | NULL (MARLIN) */
+  const void* qweight; /* int32 (uint8 blobs for ORT), shape per layout */
+  const void* qzeros;  /* int32 packed (GPTQ, AWQ_GEMM, AWQ_GEMV) | fp16 [G,N] (HQQ) | NULL (MARLIN) */
   const void* scales;  /* fp16 [G,N] (MARLIN: in the reference's permuted order) */
   const int32_t* g_idx;/* int32 [K] act-order group map, or NULL for k / group_size (GPTQ only) */
   const void* bias;    /* fp16 [N] or NULL */
@@ -230,7 +237,7 @@ int b200q_dequant(const b200q_layer* layer, void* w_out, b200q_stream_t stream);
 int b200q_unpack(const b200q_layer* layer, int32_t* q_out, int32_t* z_out, b200q_stream_t stream);
 
 /*
- * One-time exact integer re-layout of a 4-bit AWQ-GEMM or Marlin layer into the K-packed GPTQ layout
+ * One-time exact integer re-layout of a 4-bit AWQ-GEMM, AWQ-GEMV or Marlin layer into the K-packed GPTQ layout
  * (qweight i32 [K/8, N], qzeros i32 [G, N/8] holding z with bias 0, scales fp16 [G, N] natural order).
  * The host shim re-lays an AWQ-GEMM / Marlin layer out ONCE (first forward), releases the checkpoint-format buffers and
  * runs every kernel on the K-packed copy (zero extra weight memory; b200q_repack_from_gptq4 restores the checkpoint
@@ -242,7 +249,8 @@ int b200q_repack_gptq4(const b200q_layer* layer, void* qweight_out, void* qzeros
 
 /*
  * The inverse of b200q_repack_gptq4 (exact): a K-packed 4-bit layer (layout GPTQ, g_idx == NULL) -> the buffers of
- * target_layout = B200Q_LAYOUT_AWQ_GEMM (qweight [K, N/8], qzeros [G, N/8], scales [G, N]) or B200Q_LAYOUT_MARLIN
+ * target_layout = B200Q_LAYOUT_AWQ_GEMM (qweight [K, N/8], qzeros [G, N/8], scales [G, N]), B200Q_LAYOUT_AWQ_GEMV
+ * (qweight [N, K/8], qzeros [N, ZW], scales [N, 8 ZW], padding zero), B200Q_LAYOUT_ORT (MatMulNBits blobs) or B200Q_LAYOUT_MARLIN
  * (qweight [K/16, 2N], scales [G, N] in Marlin's permuted order; qzeros_out ignored -- the caller guarantees z == 8),
  * bit-identical to what WQLinear_GEMM.pack / QuantLinearMarlin.pack produce from the same integers
  * (quant_linear_awq.py:95-140, quant_linear_marlin.py:95-137).  Together with b200q_repack_gptq4 this is the integer

@@ -257,6 +257,63 @@ def matmul_ref(x: np.ndarray, W: np.ndarray, bias: np.ndarray | None = None, acc
 
 
 # --------------------------------------------------------------------------------------
+# AWQ GEMV layout (WQLinear_GEMV, quant_linear_awq.py:156-265; kernels gemv_cuda.cu:60-186)
+# --------------------------------------------------------------------------------------
+def awq_gemv_zeros_width(K: int, group_size: int) -> int:
+    """calculate_zeros_width, quant_linear_awq.py:15-27."""
+    mult = 1 if group_size >= 128 else {64: 2, 32: 4}[group_size]
+    base = (K // group_size + 7) // 8
+    return (base + mult - 1) // mult * mult
+
+
+def awq_gemv_pack(q: np.ndarray, z: np.ndarray, s: np.ndarray, group_size: int):
+    """q [K,N], z [G,N], s [G,N] -> qweight [N, K/8] (word w of row n: nibble i = q[8w+i, n], order_map 0..7,
+    quant_linear_awq.py:224-232), qzeros [N, ZW] (nibble i of word c = z[8c+i, n], :242-253), scales [N, 8 ZW] (:204-210)."""
+    K, N = q.shape
+    G = z.shape[0]
+    zw = awq_gemv_zeros_width(K, group_size)
+    qweight = np.ascontiguousarray(pack_rows(q, 4).T)
+    zp = np.zeros((zw * 8, N), dtype=np.int32)
+    zp[:G] = z
+    qzeros = np.ascontiguousarray(pack_rows(zp, 4).T)
+    sp = np.zeros((N, zw * 8), dtype=np.float16)
+    sp[:, :G] = np.asarray(s).T
+    return qweight, qzeros, sp
+
+
+def awq_gemv_unpack(qweight: np.ndarray, qzeros: np.ndarray, scales: np.ndarray, K: int, group_size: int):
+    G = K // group_size
+    q = unpack_rows(np.ascontiguousarray(np.asarray(qweight).T), 4, K)
+    z = unpack_rows(np.ascontiguousarray(np.asarray(qzeros).T), 4, qzeros.shape[1] * 8)[:G]
+    return q, np.ascontiguousarray(z), np.ascontiguousarray(np.asarray(scales)[:, :G].T)
+
+
+# --------------------------------------------------------------------------------------
+# ORT MatMulNBits blobs (QuantLinearORT.pack_on_device, quant_linear_onnxruntime.py:112-150; dequantize_blockwise_4bits :48-82)
+# --------------------------------------------------------------------------------------
+def ort_pack(q: np.ndarray, z: np.ndarray, s: np.ndarray, group_size: int):
+    """q [K,N], z [G,N], s [G,N] -> qweight u8 [N, G, group/2] (low nibble = even k), qzeros u8 [N * ceil(G/2)], scales [N * G]."""
+    K, N = q.shape
+    G = z.shape[0]
+    qt = q.T.astype(np.uint8)
+    qweight = np.ascontiguousarray((qt[:, 0::2] | (qt[:, 1::2] << 4)).reshape(N, G, group_size // 2))
+    zt = z.T.astype(np.uint8)
+    if G & 1:
+        zt = np.pad(zt, ((0, 0), (0, 1)))
+    qzeros = np.ascontiguousarray((zt[:, 0::2] | (zt[:, 1::2] << 4)).reshape(-1))
+    return qweight, qzeros, np.ascontiguousarray(np.asarray(s).T).reshape(-1)
+
+
+def ort_unpack(qweight: np.ndarray, qzeros: np.ndarray, scales: np.ndarray, K: int, N: int, group_size: int):
+    G = K // group_size
+    b = np.asarray(qweight).reshape(N, K // 2).astype(np.int32)
+    q = np.stack((b & 0xF, (b >> 4) & 0xF), axis=2).reshape(N, K).T
+    zb = np.asarray(qzeros).reshape(N, (G + 1) // 2).astype(np.int32)
+    z = np.stack((zb & 0xF, (zb >> 4) & 0xF), axis=2).reshape(N, -1)[:, :G].T
+    return np.ascontiguousarray(q), np.ascontiguousarray(z), np.ascontiguousarray(np.asarray(scales).reshape(N, G).T)
+
+
+# --------------------------------------------------------------------------------------
 # One-call forward per pack mode, from the *packed* buffers (what a checkpoint holds)
 # --------------------------------------------------------------------------------------
 def unpack_layer(layout: str, bits: int, group_size: int, K: int, N: int, qweight, qzeros, scales,
@@ -273,6 +330,14 @@ def unpack_layer(layout: str, bits: int, group_size: int, K: int, N: int, qweigh
     if layout in ("GEMM", "AWQ"):
         assert bits == 4
         return awq_unpack_qweight(qweight), awq_unpack_qzeros(qzeros), np.asarray(scales), gi
+    if layout == "GEMV":
+        assert bits == 4
+        q, z, s = awq_gemv_unpack(qweight, qzeros, scales, K, gs)
+        return q, z, s, gi
+    if layout == "ORT":
+        assert bits == 4
+        q, z, s = ort_unpack(qweight, qzeros, scales, K, N, gs)
+        return q, z, s, gi
     if layout == "MARLIN":
         assert bits == 4
         q, s = marlin_unpack(qweight, scales, gs, K)
@@ -311,6 +376,14 @@ def make_layer(layout: str, bits: int, group_size: int, K: int, N: int, seed: in
     elif layout in ("GEMM", "AWQ"):
         z = rng.integers(0, 1 << bits, size=(G, N), dtype=np.int32)
         out.update(qweight=awq_pack_qweight(q), qzeros=awq_pack_qzeros(z), scales=s, z=z)
+    elif layout == "ORT":
+        z = rng.integers(0, 1 << bits, size=(G, N), dtype=np.int32)
+        qw, qz, sp = ort_pack(q, z, s, gs)
+        out.update(qweight=qw, qzeros=qz, scales=sp, z=z)
+    elif layout == "GEMV":
+        z = rng.integers(0, 1 << bits, size=(G, N), dtype=np.int32)
+        qw, qz, sp = awq_gemv_pack(q, z, s, gs)
+        out.update(qweight=qw, qzeros=qz, scales=sp, z=z)
     elif layout == "HQQ":
         z = rng.integers(0, 1 << bits, size=(G, N)).astype(np.float16)
         if float_zeros:

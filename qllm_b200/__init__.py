@@ -4,10 +4,11 @@ Importing this package loads libb200q.so (hand-written sm_100a CUDA behind a C A
 if the library has not been built the import raises: there is no CPU or PyTorch fallback.
 """
 from ._lib import lib, check, Layer  # noqa: F401  (raises ImportError when the .so is missing)
-from .q_layers import (QuantLinearGPTQ, QuantLinearHQQ, QuantLinearMarlin, WQLinear_GEMM,  # noqa: F401
+from .q_layers import (QuantLinearGPTQ, QuantLinearHQQ, QuantLinearMarlin, QuantLinearORT, WQLinear_GEMM, WQLinear_GEMV,  # noqa: F401
                        fuse_siblings, linear_group, make_mixbits_quant_linear, select_quant_linear)
 
 from .chain import DecodeChain  # noqa: F401,E402
+from .repack import convert_layer, repack_to_new_mode  # noqa: F401,E402
 from .loader import from_quantized, load_quant_config, save_quantized  # noqa: F401,E402  (qllm --load for this engine)
 
 __version__ = "0.1.0"

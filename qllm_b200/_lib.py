@@ -6,7 +6,7 @@ import os
 from ._build import LIB
 
 B200Q_OK = 0
-LAYOUT_GPTQ, LAYOUT_AWQ_GEMM, LAYOUT_MARLIN, LAYOUT_HQQ = 0, 1, 2, 3
+LAYOUT_GPTQ, LAYOUT_AWQ_GEMM, LAYOUT_MARLIN, LAYOUT_HQQ, LAYOUT_AWQ_GEMV, LAYOUT_ORT = 0, 1, 2, 3, 4, 5
 KERNEL_GEMV, KERNEL_GEMM, KERNEL_GENERIC = 1, 2, 3
 PEER_Y_TAGGED, PEER_X_TAGGED = 1, 2
 

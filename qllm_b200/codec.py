@@ -81,6 +81,69 @@ awq_pack_qzeros = _awq_pack
 awq_unpack_qzeros = _awq_unpack
 
 
+# ---- AWQ GEMV layout (WQLinear_GEMV, quant_linear_awq.py:156-265) ------------------------------
+def awq_gemv_zeros_width(in_features: int, group_size: int, pack_num: int = 8) -> int:
+    """calculate_zeros_width (quant_linear_awq.py:15-27)."""
+    if group_size >= 128:
+        mult = 1
+    elif group_size == 64:
+        mult = 2
+    elif group_size == 32:
+        mult = 4
+    else:
+        raise NotImplementedError(group_size)
+    base = (in_features // group_size + pack_num - 1) // pack_num
+    return (base + mult - 1) // mult * mult
+
+
+def awq_gemv_pack(q: torch.Tensor, z: torch.Tensor, scales: torch.Tensor, group_size: int):
+    """q int [K,N], z int [G,N], scales [G,N] -> qweight i32 [N, K/8] (nibble i = k 8w+i), qzeros i32 [N, ZW]
+    (nibble i of word c = group 8c+i), scales [N, 8 ZW] (zero padded)."""
+    K, N = q.shape
+    G = z.shape[0]
+    zw = awq_gemv_zeros_width(K, group_size)
+    qweight = pack_rows(q, 4).t().contiguous()
+    zp = torch.zeros((zw * 8, N), dtype=torch.int32, device=z.device)
+    zp[:G] = z.to(torch.int32)
+    qzeros = pack_rows(zp, 4).t().contiguous()
+    sp = torch.zeros((N, zw * 8), dtype=scales.dtype, device=scales.device)
+    sp[:, :G] = scales.t()
+    return qweight, qzeros, sp
+
+
+def awq_gemv_unpack(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, K: int, group_size: int):
+    """-> (q int32 [K,N], z int32 [G,N], scales [G,N])."""
+    G = K // group_size
+    q = unpack_rows(qweight.t().contiguous(), 4, K)
+    z = unpack_rows(qzeros.t().contiguous(), 4, qzeros.shape[1] * 8)[:G]
+    return q, z.contiguous(), scales[:, :G].t().contiguous()
+
+
+# ---- ORT MatMulNBits blobs (QuantLinearORT, quant_linear_onnxruntime.py:85-174), 4-bit ----------
+def ort_pack(q: torch.Tensor, z: torch.Tensor, scales: torch.Tensor, group_size: int):
+    """q int [K,N], z int [G,N], scales [G,N] -> qweight u8 [N, G, group/2], qzeros u8 [N * ceil(G/2)], scales [N * G]
+    (pack_on_device, quant_linear_onnxruntime.py:112-150)."""
+    K, N = q.shape
+    G = z.shape[0]
+    qt = q.t().to(torch.uint8)                                   # [N, K]
+    qweight = (qt[:, 0::2] | (qt[:, 1::2] << 4)).reshape(N, G, group_size // 2).contiguous()
+    zt = z.t().to(torch.uint8)                                   # [N, G]
+    if G & 1:
+        zt = torch.nn.functional.pad(zt, (0, 1))
+    qzeros = (zt[:, 0::2] | (zt[:, 1::2] << 4)).reshape(-1).contiguous()
+    return qweight, qzeros, scales.t().contiguous().reshape(-1)
+
+
+def ort_unpack(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, K: int, N: int, group_size: int):
+    """-> (q int32 [K,N], z int32 [G,N], scales [G,N])."""
+    G = K // group_size
+    b = qweight.reshape(N, K // 2).to(torch.int32)
+    q = torch.stack((b & 0xF, (b >> 4) & 0xF), dim=2).reshape(N, K).t().contiguous()
+    zb = qzeros.reshape(N, (G + 1) // 2).to(torch.int32)
+    z = torch.stack((zb & 0xF, (zb >> 4) & 0xF), dim=2).reshape(N, -1)[:, :G].t().contiguous()
+    return q, z, scales.reshape(N, G).t().contiguous()
+
+
 # ---- Marlin -----------------------------------------------------------------------------------
 def _marlin_perms():
     perm = []

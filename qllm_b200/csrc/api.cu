@@ -66,6 +66,15 @@ static int validate(const b200q_layer* L) {
       if (L->bits != 4) return B200Q_ERR_UNSUPPORTED;       // quant_linear_awq.py:42-43
       if (L->g_idx) return B200Q_ERR_UNSUPPORTED;           // quant_linear_awq.py:96-103
       break;
+    case B200Q_LAYOUT_ORT:
+      if (L->bits != 4) return B200Q_ERR_UNSUPPORTED;               // quant_linear_onnxruntime.py:114 (pack), :46 (forward)
+      if (L->K % L->group_size != 0 || L->group_size % 2 != 0) return B200Q_ERR_SHAPE;
+      break;
+    case B200Q_LAYOUT_AWQ_GEMV:
+      if (L->bits != 4 || L->g_idx) return B200Q_ERR_UNSUPPORTED;   // quant_linear_awq.py:161-162
+      if (L->K % 8 != 0) return B200Q_ERR_SHAPE;
+      if (L->group_size < 128 && L->group_size != 64 && L->group_size != 32) return B200Q_ERR_UNSUPPORTED;   // calculate_zeros_width :15-27
+      break;
     case B200Q_LAYOUT_MARLIN:
       if (L->bits != 4 || L->g_idx) return B200Q_ERR_UNSUPPORTED;   // quant_linear_marlin.py:96-99
       if (L->K % 16 != 0 || L->N % 64 != 0) return B200Q_ERR_SHAPE; // tile permutation granularity
@@ -535,8 +544,10 @@ int b200q_repack_from_gptq4(const b200q_layer* layer, int32_t target_layout, voi
   if (v != B200Q_OK) return v;
   if (!qweight_out || !scales_out) return B200Q_ERR_NULL;
   if (layer->layout != B200Q_LAYOUT_GPTQ || layer->bits != 4 || layer->g_idx || layer->x_perm || layer->K % 8 != 0) return B200Q_ERR_UNSUPPORTED;
-  if (target_layout == B200Q_LAYOUT_AWQ_GEMM) {
+  if (target_layout == B200Q_LAYOUT_AWQ_GEMM || target_layout == B200Q_LAYOUT_AWQ_GEMV || target_layout == B200Q_LAYOUT_ORT) {
     if (!qzeros_out) return B200Q_ERR_NULL;
+    if (target_layout == B200Q_LAYOUT_AWQ_GEMV && layer->group_size < 128 && layer->group_size != 64 && layer->group_size != 32)
+      return B200Q_ERR_UNSUPPORTED;
   } else if (target_layout == B200Q_LAYOUT_MARLIN) {
     if (layer->K % 16 != 0 || layer->N % 64 != 0) return B200Q_ERR_SHAPE;          // tile permutation granularity
     if (layer->group_size != 128 && layer->group_size != layer->K) return B200Q_ERR_UNSUPPORTED;   // quant_linear_marlin.py:78-80

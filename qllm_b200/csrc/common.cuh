@@ -12,6 +12,7 @@ namespace b200q {
 
 struct LayerView {
   int layout, bits, group, K, N, G, zero_bias;
+  int zw;                            // AWQ-GEMV: words per qzeros row (calculate_zeros_width, quant_linear_awq.py:15-27)
   const uint32_t* __restrict__ qw;
   const void* __restrict__ qz;       // uint32 packed | half [G,N] (HQQ) | nullptr (Marlin)
   const __half* __restrict__ s;
@@ -26,6 +27,8 @@ __host__ inline LayerView make_view(const b200q_layer* L) {
   v.G = (L->K + L->group_size - 1) / L->group_size; v.zero_bias = L->zero_bias;
   v.qw = (const uint32_t*)L->qweight; v.qz = L->qzeros; v.s = (const __half*)L->scales;
   v.g_idx = L->g_idx; v.bias = (const __half*)L->bias; v.x_perm = L->x_perm;
+  const int mult = L->group_size >= 128 ? 1 : (L->group_size == 64 ? 2 : 4);
+  v.zw = ((((v.G + 7) / 8) + mult - 1) / mult) * mult;
   return v;
 }
 
@@ -71,6 +74,12 @@ __device__ __forceinline__ uint32_t load_q(const LayerView& L, int k, int n) {
       const uint32_t w = __ldg(L.qw + (size_t)k * (L.N >> 3) + (n >> 3));
       return (w >> (4 * awq_nibble_of_col(n & 7))) & 0xFu;
     }
+    case B200Q_LAYOUT_AWQ_GEMV:
+      return (__ldg(L.qw + (size_t)n * (L.K >> 3) + (k >> 3)) >> (4 * (k & 7))) & 0xFu;
+    case B200Q_LAYOUT_ORT: {   // blobs [N, K / group, group / 2] bytes == [N, K / 2] bytes (K % group == 0): byte k / 2, nibble k & 1
+      const uint8_t b = __ldg(reinterpret_cast<const uint8_t*>(L.qw) + (size_t)n * (L.K >> 1) + (k >> 1));
+      return (uint32_t)(b >> (4 * (k & 1))) & 0xFu;
+    }
     default: {  // MARLIN
       size_t word; int nib;
       marlin_locate(k, n, L.N, word, nib);
@@ -93,6 +102,12 @@ __device__ __forceinline__ float load_z(const LayerView& L, int g, int n) {
       const uint32_t w = __ldg((const uint32_t*)L.qz + (size_t)g * (L.N >> 3) + (n >> 3));
       return (float)((w >> (4 * awq_nibble_of_col(n & 7))) & 0xFu);
     }
+    case B200Q_LAYOUT_AWQ_GEMV:
+      return (float)((__ldg((const uint32_t*)L.qz + (size_t)n * L.zw + (g >> 3)) >> (4 * (g & 7))) & 0xFu);
+    case B200Q_LAYOUT_ORT: {
+      const uint8_t b = __ldg(reinterpret_cast<const uint8_t*>(L.qz) + (size_t)n * ((L.G + 1) >> 1) + (g >> 1));
+      return (float)((b >> (4 * (g & 1))) & 0xFu);
+    }
     default:
       return 8.0f;
   }
@@ -101,6 +116,8 @@ __device__ __forceinline__ float load_z(const LayerView& L, int g, int n) {
 __device__ __forceinline__ float load_s(const LayerView& L, int g, int n) {
   if (L.layout == B200Q_LAYOUT_MARLIN)
     return __half2float(__ldg(L.s + (size_t)g * L.N + marlin_scale_index(n, L.group == L.K)));
+  if (L.layout == B200Q_LAYOUT_AWQ_GEMV) return __half2float(__ldg(L.s + (size_t)n * (8 * L.zw) + g));
+  if (L.layout == B200Q_LAYOUT_ORT) return __half2float(__ldg(L.s + (size_t)n * L.G + g));
   return __half2float(__ldg(L.s + (size_t)g * L.N + n));
 }
 

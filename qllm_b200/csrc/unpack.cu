@@ -84,6 +84,10 @@ __global__ void __launch_bounds__(256) repack_from_gptq4_kernel(LayerView L, int
     const uint32_t q = load_q(L, k, n) & 0xFu;
     if (target == B200Q_LAYOUT_AWQ_GEMM) {
       atomicOr(qw_out + (size_t)k * (L.N >> 3) + (n >> 3), q << (4 * awq_nibble_of_col(n & 7)));
+    } else if (target == B200Q_LAYOUT_AWQ_GEMV) {
+      atomicOr(qw_out + (size_t)n * (L.K >> 3) + (k >> 3), q << (4 * (k & 7)));
+    } else if (target == B200Q_LAYOUT_ORT) {                              // byte n K/2 + k/2 -> word (little endian), nibble k & 7
+      atomicOr(qw_out + (size_t)n * (L.K >> 3) + (k >> 3), q << (4 * (k & 7)));
     } else {
       size_t word; int nib;
       marlin_locate(k, n, L.N, word, nib);
@@ -95,6 +99,13 @@ __global__ void __launch_bounds__(256) repack_from_gptq4_kernel(LayerView L, int
     if (target == B200Q_LAYOUT_AWQ_GEMM) {
       atomicOr(qz_out + (size_t)g * (L.N >> 3) + (n >> 3), ((uint32_t)load_z(L, g, n) & 0xFu) << (4 * awq_nibble_of_col(n & 7)));
       s_out[idx] = L.s[idx];
+    } else if (target == B200Q_LAYOUT_AWQ_GEMV) {
+      atomicOr(qz_out + (size_t)n * L.zw + (g >> 3), ((uint32_t)load_z(L, g, n) & 0xFu) << (4 * (g & 7)));
+      s_out[(size_t)n * (8 * L.zw) + g] = L.s[idx];
+    } else if (target == B200Q_LAYOUT_ORT) {                              // nibble index n * 2 ceil(G/2) + g of a byte stream
+      const size_t nib = (size_t)n * (2 * ((L.G + 1) >> 1)) + g;
+      atomicOr(qz_out + (nib >> 3), ((uint32_t)load_z(L, g, n) & 0xFu) << (4 * (nib & 7)));
+      s_out[(size_t)n * L.G + g] = L.s[idx];
     } else {
       s_out[(size_t)g * L.N + marlin_scale_index(n, L.group == L.K)] = L.s[idx];
     }
@@ -107,6 +118,14 @@ cudaError_t launch_repack_from_gptq4(const LayerView& L, int target, uint32_t* q
   if (e != cudaSuccess) return e;
   if (target == B200Q_LAYOUT_AWQ_GEMM) {
     e = cudaMemsetAsync(qz_out, 0, (size_t)L.G * (L.N >> 3) * 4, st);
+    if (e != cudaSuccess) return e;
+  } else if (target == B200Q_LAYOUT_ORT) {                                // N ceil(G/2) bytes, rounded up to whole words
+    e = cudaMemsetAsync(qz_out, 0, (((size_t)L.N * ((L.G + 1) >> 1)) + 3) / 4 * 4, st);
+    if (e != cudaSuccess) return e;
+  } else if (target == B200Q_LAYOUT_AWQ_GEMV) {                           // rows are padded to ZW words / 8 ZW scales
+    e = cudaMemsetAsync(qz_out, 0, (size_t)L.N * L.zw * 4, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(s_out, 0, (size_t)L.N * L.zw * 8 * 2, st);
     if (e != cudaSuccess) return e;
   }
   const size_t total = (size_t)L.K * L.N;

@@ -158,6 +158,8 @@ def from_quantized(path: str, device="cuda", dtype=torch.float16, fuse: bool = T
                 m.handle_qzeros_for_autogptq()
     model.quant_config, model.quant_config_by_layer, model.unexpected_keys = qc, qc.by_op, unexpected
     model.eval()
+    if dtype is not None:                              # assign=True keeps the checkpoint's dtypes (an fp32 checkpoint would stay fp32)
+        model = model.to(dtype)
     if device is not None and str(device) != "cpu":
         model = model.to(device)
     if fuse:

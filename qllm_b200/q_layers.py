@@ -22,7 +22,9 @@ import torch
 import torch.nn as nn
 
 from . import codec
-from ._lib import (LAYOUT_AWQ_GEMM, LAYOUT_GPTQ, LAYOUT_HQQ, LAYOUT_MARLIN, Layer, check, lib)
+from ._lib import (LAYOUT_AWQ_GEMM, LAYOUT_AWQ_GEMV, LAYOUT_GPTQ, LAYOUT_HQQ, LAYOUT_MARLIN, LAYOUT_ORT, Layer, check, lib)
+
+_RELAYOUT = (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN, LAYOUT_AWQ_GEMV, LAYOUT_ORT)      # layouts that run on their exact K-packed re-layout
 
 _workspaces = {}
 
@@ -73,7 +75,7 @@ class _B200QuantLinearBase(nn.Module):
 
     def _detect_act_order(self):
         g = getattr(self, "g_idx", None)
-        if self._layout != LAYOUT_GPTQ or not isinstance(g, torch.Tensor):
+        if self._layout not in (LAYOUT_GPTQ, LAYOUT_ORT) or not isinstance(g, torch.Tensor):
             return False
         trivial = torch.arange(self.infeatures, device=g.device, dtype=torch.int64) // self.groupsize
         return bool((g.to(torch.int64) != trivial).any().item())
@@ -153,7 +155,7 @@ class _B200QuantLinearBase(nn.Module):
         GPTQ/HQQ: the checkpoint buffers themselves.  AWQ/Marlin: a one-time exact integer re-layout
         (b200q_repack_gptq4); unless B200Q_KEEP_NATIVE=1 the checkpoint-format buffers are then released, so the
         layer holds ONE packed copy (state_dict() restores the checkpoint format through b200q_repack_from_gptq4)."""
-        if self._layout not in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN):
+        if self._layout not in _RELAYOUT or (self._layout == LAYOUT_ORT and self.act_order):
             return self._fast_descriptor()
         if getattr(self, "_consolidated", False):
             return self._shadow_desc
@@ -191,13 +193,20 @@ class _B200QuantLinearBase(nn.Module):
         qw, qz, sc = self._shadow
         dev = qw.device
         meta = self._native_meta
-        out_qw = torch.empty(meta["qweight"][0], dtype=torch.int32, device=dev)
-        out_qz = torch.empty(meta["qzeros"][0], dtype=torch.int32, device=dev) if "qzeros" in meta else None
+
+        def alloc(name):                                  # outputs are OR-ed / memset in whole 32-bit words
+            shape, dt = meta[name]
+            nbytes = int(torch.tensor(shape).prod().item()) * torch.empty(0, dtype=dt).element_size()
+            return torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=dev), shape, dt, nbytes
+
+        bq, sq, dq, nq = alloc("qweight")
+        bz = alloc("qzeros") if "qzeros" in meta else None
         out_sc = torch.empty(meta["scales"][0], dtype=torch.float16, device=dev)
-        check(lib.b200q_repack_from_gptq4(ctypes.byref(self._shadow_desc), self._layout, out_qw.data_ptr(),
-                                          None if out_qz is None else out_qz.data_ptr(), out_sc.data_ptr(),
+        check(lib.b200q_repack_from_gptq4(ctypes.byref(self._shadow_desc), self._layout, bq.data_ptr(),
+                                          None if bz is None else bz[0].data_ptr(), out_sc.data_ptr(),
                                           torch.cuda.current_stream(dev).cuda_stream), "b200q_repack_from_gptq4")
-        return out_qw, out_qz, out_sc.to(meta["scales"][1])
+        view = lambda b, shape, dt, n: b.view(torch.uint8)[:n].view(dt).reshape(shape)
+        return view(bq, sq, dq, nq), (None if bz is None else view(*bz)), out_sc.to(meta["scales"][1])
 
     def _restore_native(self):
         if getattr(self, "_consolidated", False):
@@ -213,7 +222,7 @@ class _B200QuantLinearBase(nn.Module):
         if getattr(self, "_consolidated", False):
             qw, qz, sc = self._native_tensors()
             super()._save_to_state_dict(destination, prefix, keep_vars)
-            destination[prefix + "qweight"], destination[prefix + "scales"] = qw, sc
+            destination[prefix + "qweight"], destination[prefix + "scales"] = qw.contiguous(), sc
             if qz is not None:
                 destination[prefix + "qzeros"] = qz
             return
@@ -227,7 +236,7 @@ class _B200QuantLinearBase(nn.Module):
     def _decode_descriptor(self, M):
         """Descriptor the decode kernels should read at batch M: the checkpoint buffers, or -- AWQ-GEMM / Marlin at
         M <= 2 -- the one-time exact K-packed re-layout that the integer-tensor-path kernel consumes."""
-        if self._layout in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN) and ((DECODE_RELAYOUT and M <= 2) or not KEEP_NATIVE
+        if self._layout in _RELAYOUT and ((DECODE_RELAYOUT and M <= 2) or not KEEP_NATIVE or self._layout in (LAYOUT_AWQ_GEMV, LAYOUT_ORT)
                                                                  or getattr(self, "_consolidated", False)):
             return self._gemm_descriptor()
         return self._fast_descriptor()
@@ -240,7 +249,7 @@ class _B200QuantLinearBase(nn.Module):
         return super().__call__(x)
 
     def forward(self, x):
-        desc = self._decode_descriptor(8) if self._layout in (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN) else self._fast_descriptor()
+        desc = self._decode_descriptor(8) if self._layout in _RELAYOUT else self._fast_descriptor()
         out_shape = x.shape[:-1] + (self.outfeatures,)
         x2 = x.reshape(-1, x.shape[-1])
         if x2.dtype != torch.float16:
@@ -435,6 +444,101 @@ class WQLinear_GEMM(_B200QuantLinearBase):
         return w.t().contiguous().cpu(), sc.cpu(), z.cpu()
 
 
+class WQLinear_GEMV(_B200QuantLinearBase):
+    """pack_mode=GEMV (AWQ): qweight i32 [N, K/8], qzeros i32 [N, ZW], scales [N, 8 ZW] (quant_linear_awq.py:156-265).
+    The reference's dispatch never selects it (utils/modelutils.py:52-67) but its kernels are built and exported
+    (gemv_forward_cuda / gemmv2_forward_cuda, pybind_awq.cpp:17-18), so checkpoints in this layout exist."""
+    _layout = LAYOUT_AWQ_GEMV
+
+    def __init__(self, w_bit, group_size, in_features, out_features, bias, dtype=None):
+        super().__init__()
+        if w_bit not in [4]:
+            raise NotImplementedError("Only 4-bit are supported for now.")
+        self._init_common(w_bit, group_size, in_features, out_features, dtype)
+        self.in_features, self.out_features = in_features, out_features
+        self.w_bit = w_bit
+        self.group_size = self.groupsize
+        self.split_k_iters = 8
+        self.pack_mode = "GEMV"
+        assert in_features % self.group_size == 0
+        assert out_features % (32 // w_bit) == 0
+        zw = codec.awq_gemv_zeros_width(in_features, self.group_size)
+        self.g_idx = self._default_g_idx()
+        self.register_buffer("qweight", torch.zeros((out_features, in_features // 8), dtype=torch.int32))
+        self.register_buffer("qzeros", torch.zeros((out_features, zw), dtype=torch.int32))
+        self.register_buffer("scales", torch.zeros((out_features, zw * 8), dtype=self.dtype))
+        if bias:
+            self.register_buffer("bias", torch.zeros((out_features), dtype=self.dtype))
+        else:
+            self.bias = None
+
+    def pack(self, linear, scales, zeros, g_idx=None):
+        dev = _pack_device()
+        s_t = scales.t().contiguous().to(dev).float()
+        z_t = zeros.t().contiguous().to(dev).float()
+        q = codec.quantize_weight(linear.weight.data.t().to(dev).float(), s_t, z_t, self._default_g_idx().to(dev), self.maxq)
+        qw, qz, sc = codec.awq_gemv_pack(q, z_t.round().to(torch.int32), s_t.to(self.dtype), self.group_size)
+        self.qweight, self.qzeros, self.scales = qw.cpu(), qz.cpu(), sc.cpu()
+        if linear.bias is not None:
+            self.bias = linear.bias.detach().clone().to(self.dtype).cpu()
+        self._desc = None
+
+    def unpack(self):
+        if getattr(self, "_consolidated", False):
+            qw, qz, sc = self._native_tensors()
+        else:
+            qw, qz, sc = self.qweight, self.qzeros, self.scales
+        q, z, s = codec.awq_gemv_unpack(qw, qz, sc, self.infeatures, self.group_size)
+        gi = self._default_g_idx().long().to(q.device)
+        w = ((q.float() - z.float()[gi]) * s.float()[gi]).to(torch.float16)
+        return w.t().contiguous().cpu(), s.cpu(), z.cpu()
+
+
+class QuantLinearORT(_B200QuantLinearBase):
+    """pack_mode=ORT: com.microsoft::MatMulNBits blobs (quant_linear_onnxruntime.py:85-174), 4-bit: qweight u8 [N, G, group/2],
+    qzeros u8 [N * ceil(G/2)] (two zero points per byte), scales [N * G], g_idx i32 [K].  The reference runs it through
+    ort_ops.Dequantize4Bits (csrc/ort_cuda/dq.cu:79-213) or a torch dequant, then torch.matmul (:31-43)."""
+    _layout = LAYOUT_ORT
+
+    def __init__(self, bits, groupsize, infeatures, outfeatures, bias, dtype=None):
+        super().__init__()
+        if bits != 4:
+            raise NotImplementedError("only 4bit is supported by ONNXRUNTIME for now.")     # quant_linear_onnxruntime.py:114
+        self._init_common(bits, groupsize, infeatures, outfeatures, dtype)
+        self.pack_mode = "ORT"
+        G = infeatures // self.groupsize
+        self.register_buffer("qweight", torch.zeros((outfeatures, G, self.groupsize // 2), dtype=torch.uint8))
+        self.register_buffer("qzeros", torch.zeros((G + (G & 1)) * (outfeatures // 8 * bits), dtype=torch.uint8))
+        self.register_buffer("scales", torch.zeros(math.ceil(infeatures / self.groupsize) * outfeatures, dtype=self.dtype))
+        self.register_buffer("g_idx", self._default_g_idx())
+        if bias:
+            self.register_buffer("bias", torch.zeros((outfeatures), dtype=self.dtype))
+        else:
+            self.bias = None
+
+    def pack(self, linear, scales, zeros, g_idx=None):
+        dev = _pack_device()
+        g = self._default_g_idx() if g_idx is None else g_idx.to(torch.int32).cpu()
+        s_t = scales.t().contiguous().to(dev).float()
+        z_t = zeros.t().contiguous().to(dev).float()
+        q = codec.quantize_weight(linear.weight.data.t().to(dev).float(), s_t, z_t, g.to(dev), self.maxq)
+        qw, qz, sc = codec.ort_pack(q, z_t.round().to(torch.int32), s_t.to(self.dtype), self.groupsize)
+        self.qweight, self.qzeros, self.scales, self.g_idx = qw.cpu(), qz.cpu(), sc.cpu(), g
+        if linear.bias is not None:
+            self.bias = linear.bias.detach().clone().to(self.dtype).cpu()
+        self._desc, self.act_order = None, None
+
+    def unpack(self):
+        if getattr(self, "_consolidated", False):
+            qw, qz, sc = self._native_tensors()
+        else:
+            qw, qz, sc = self.qweight, self.qzeros, self.scales
+        q, z, s = codec.ort_unpack(qw, qz, sc, self.infeatures, self.outfeatures, self.groupsize)
+        gi = self.g_idx.long().to(q.device)
+        w = ((q.float() - z.float()[gi]) * s.float()[gi]).to(torch.float16)
+        return w.t().contiguous().cpu(), s.cpu(), z.cpu()
+
+
 class QuantLinearMarlin(_B200QuantLinearBase):
     """pack_mode=MARLIN: symmetric int4, qweight i32 [K/16, 2N], scales fp16 [G, N] permuted."""
     _layout = LAYOUT_MARLIN
@@ -571,12 +675,16 @@ def select_quant_linear(pack_mode: str, wbits: int, quant_method: str):
     out of scope (VPTQ, ORT); AUTO prefers the AWQ layout for 4-bit as the reference does on sm>=75."""
     pack_mode = pack_mode.upper()
     quant_method = quant_method.lower()
-    if quant_method == "vptq" or pack_mode == "ORT":
-        raise NotImplementedError(f"pack_mode={pack_mode}/quant_method={quant_method} is outside the b200q hot path")
+    if quant_method == "vptq":
+        raise NotImplementedError(f"quant_method={quant_method} is outside the b200q hot path")
+    if pack_mode == "ORT":
+        return QuantLinearORT
     if quant_method == "hqq":
         return QuantLinearHQQ
     if pack_mode == "MARLIN":
         return QuantLinearMarlin
+    if pack_mode == "GEMV":                      # not reachable in the reference's table; offered for checkpoints in that layout
+        return WQLinear_GEMV
     if pack_mode == "GEMM" or (pack_mode == "AUTO" and wbits == 4):
         return WQLinear_GEMM
     return QuantLinearGPTQ

@@ -160,6 +160,50 @@ def main():
                     p + "int_w": layer.unpack_qweight("cpu").numpy()})
     np.savez_compressed(os.path.join(OUT, "awq.npz"), **out)
 
+    # ---- 4b. AWQ GEMV layout: the reference's own packer (quant_linear_awq.py:186-254).  accelerate_pack_on_device is
+    #      declared without @classmethod and passes `linear.weight.device` where the ctor expects a dtype, so it is
+    #      driven with cls given explicitly and a stand-in `linear` whose weight.device IS the dtype ----------------
+    out = {}
+    for ci, (gs, K, N) in enumerate([(128, 256, 64), (64, 256, 32), (32, 128, 64), (128, 2048, 32)]):
+        G = K // gs
+        W, s, z = synth(K, N, G, 4, 650 + ci)
+        # the reference's GEMV packer does not clamp (a rounded 16 would spill into the next nibble): give it weights that
+        # sit exactly on the 4-bit grid
+        se, ze = s.repeat_interleave(gs, dim=1), z.repeat_interleave(gs, dim=1)
+        W = (torch.clamp(torch.round(W / se + ze), 0, 15) - ze) * se
+        fake = types.SimpleNamespace(in_features=K, out_features=N, bias=None,
+                                     weight=types.SimpleNamespace(data=W.clone(), device=torch.float16))
+        layer = awq.WQLinear_GEMV.accelerate_pack_on_device(awq.WQLinear_GEMV, fake, 4, gs, False, s, z)
+        intw = torch.round((W + (z * s).repeat_interleave(gs, dim=1)) / s.repeat_interleave(gs, dim=1)).to(torch.int32)   # test input record
+        p = f"c{ci}_"
+        out.update({p + "meta": np.array([4, gs, K, N]), p + "qweight": layer.qweight.numpy(), p + "qzeros": layer.qzeros.numpy(),
+                    p + "scales": layer.scales.numpy(), p + "int_w": intw.t().contiguous().numpy(),
+                    p + "int_z": z.to(torch.int32).t().contiguous().numpy(), p + "nat_scales": s.half().t().contiguous().numpy()})
+    np.savez_compressed(os.path.join(OUT, "awq_gemv.npz"), **out)
+
+    # ---- 4c. ORT MatMulNBits blobs: the reference's QuantLinearORT.pack + its torch forward (quant_linear_onnxruntime.py) ----
+    import importlib
+    ort = importlib.import_module("qllm.modeling.q_layers.quant_linear_onnxruntime")
+    out = {}
+    for ci, (gs, K, N) in enumerate([(128, 256, 64), (32, 128, 32), (64, 384, 64)]):
+        G = K // gs
+        W, s, z = synth(K, N, G, 4, 680 + ci)
+        se, ze = s.repeat_interleave(gs, dim=1), z.repeat_interleave(gs, dim=1)
+        W = (torch.clamp(torch.round(W / se + ze), 0, 15) - ze) * se           # on the 4-bit grid (the packer does not clamp)
+        lin = torch.nn.Linear(K, N, bias=False)
+        lin.weight.data = W.clone()
+        layer = ort.QuantLinearORT(4, gs, K, N, False, dtype=torch.float32)
+        layer.pack(lin, s, z.to(torch.int32), None)          # integer zeros: a float tensor would select the float-zero blob form (:119,:130)
+        x = torch.randn(3, K, generator=torch.Generator().manual_seed(ci))
+        y = layer(x)
+        intw = torch.round((W + ze * se) / se).to(torch.int32)
+        p = f"c{ci}_"
+        out.update({p + "meta": np.array([4, gs, K, N]), p + "qweight": layer.qweight.numpy(), p + "qzeros": layer.qzeros.numpy(),
+                    p + "scales": layer.scales.numpy(), p + "int_w": intw.t().contiguous().numpy(),
+                    p + "int_z": z.to(torch.int32).t().contiguous().numpy(), p + "nat_scales": s.t().contiguous().numpy(),
+                    p + "x": x.numpy(), p + "y32": y.detach().numpy()})
+    np.savez_compressed(os.path.join(OUT, "ort.npz"), **out)
+
     # ---- 5. Marlin layout: pack only (unpack is NotImplemented; quant_linear_marlin.py) -------
     out = {}
     marlin.torch = _TorchCpuProxy()

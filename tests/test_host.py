@@ -42,8 +42,10 @@ def test_select_quant_linear_table():
     assert s("AUTO", 3, "gptq") is qllm_b200.QuantLinearGPTQ
     assert s("MARLIN", 4, "gptq") is qllm_b200.QuantLinearMarlin
     assert s("GPTQ", 4, "hqq") is qllm_b200.QuantLinearHQQ
+    assert s("ORT", 4, "gptq") is qllm_b200.QuantLinearORT            # modelutils.py:50-51
+    assert s("GEMV", 4, "awq") is qllm_b200.WQLinear_GEMV             # not in the reference's table (dead there); offered here
     with pytest.raises(NotImplementedError):
-        s("ORT", 4, "gptq")
+        s("GPTQ", 4, "vptq")
 
 
 @pytest.mark.parametrize("cls,bits,gs,K,N,shapes", [

@@ -149,3 +149,43 @@ def test_cpu_baseline_port_pinned_to_reference_forward(golden_dir):
         assert np.abs(y16 - ref).max() <= 2e-2 * np.abs(ref).max(), f"case {i}: fp16 forward"
         pinned += 1
     assert pinned >= 3
+
+
+def test_awq_gemv_layout_matches_reference_packer(golden_dir):
+    """WQLinear_GEMV buffers written by the reference's own accelerate_pack_on_device (quant_linear_awq.py:186-254):
+    the oracle's unpack recovers the integers bit-exactly and its pack reproduces the reference's bytes."""
+    d = _load(golden_dir, "awq_gemv.npz")
+    i = 0
+    while f"c{i}_meta" in d:
+        bits, gs, K, N = (int(v) for v in d[f"c{i}_meta"])
+        p = f"c{i}_"
+        q, z, s = O.awq_gemv_unpack(d[p + "qweight"], d[p + "qzeros"], d[p + "scales"], K, gs)
+        assert np.array_equal(q, d[p + "int_w"]), f"case {i}: qweight"
+        assert np.array_equal(z, d[p + "int_z"]), f"case {i}: qzeros"
+        assert np.array_equal(s.view(np.uint16), d[p + "nat_scales"].view(np.uint16)), f"case {i}: scales"
+        qw, qz, sp = O.awq_gemv_pack(q, z, s, gs)
+        assert np.array_equal(qw, d[p + "qweight"]) and np.array_equal(qz, d[p + "qzeros"])
+        assert np.array_equal(sp.view(np.uint16), d[p + "scales"].view(np.uint16))
+        assert d[p + "qzeros"].shape[1] == O.awq_gemv_zeros_width(K, gs)
+        i += 1
+    assert i == 4
+
+
+def test_ort_blob_layout_matches_reference(golden_dir):
+    """QuantLinearORT buffers written by the reference's pack() and outputs of its torch forward
+    (dequantize_blockwise_4bits + matmul, quant_linear_onnxruntime.py:31-82): unpack / pack bit-exact, forward within 1e-3."""
+    d = _load(golden_dir, "ort.npz")
+    i = 0
+    while f"c{i}_meta" in d:
+        bits, gs, K, N = (int(v) for v in d[f"c{i}_meta"])
+        p = f"c{i}_"
+        q, z, s = O.ort_unpack(d[p + "qweight"], d[p + "qzeros"], d[p + "scales"], K, N, gs)
+        assert np.array_equal(q, d[p + "int_w"]) and np.array_equal(z, d[p + "int_z"])
+        assert np.array_equal(s, d[p + "nat_scales"])
+        qw, qz, sp = O.ort_pack(q, z, s, gs)
+        assert np.array_equal(qw, d[p + "qweight"]) and np.array_equal(qz, d[p + "qzeros"]) and np.array_equal(sp, d[p + "scales"])
+        W = O.dequant(q, z, s, O.default_g_idx(K, gs), "exact")
+        y = O.matmul_ref(d[p + "x"], W, None, acc=np.float64)
+        assert np.abs(y - d[p + "y32"]).max() <= 1e-3 * np.abs(d[p + "y32"]).max()
+        i += 1
+    assert i == 3

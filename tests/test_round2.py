@@ -133,3 +133,142 @@ def test_gemm_first_call_under_graph_capture():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(y, y_eager)
+
+
+# ---- the AWQ-GEMV layout (WQLinear_GEMV) -------------------------------------------------------
+@pytest.mark.parametrize("gs,K,N", [(128, 512, 128), (64, 512, 64), (32, 256, 96), (128, 4096, 256)])
+def test_awq_gemv_layout(gs, K, N):
+    L = O.make_layer("GEMV", 4, gs, K, N, seed=K + N + gs, bias=True)
+    layer = layer_from_dict(L)
+    q, z = layer.unpack_int()                                             # read in place (generic element decoders)
+    assert np.array_equal(q.cpu().numpy(), L["q"]) and np.array_equal(z.cpu().numpy(), L["z"])
+    W = layer.dequantize().cpu().numpy()
+    assert np.array_equal(W.view(np.uint16), O.dequant(L["q"], L["z"], L["s"], L["g_idx"], "engine").view(np.uint16))
+    for M in (1, 2, 7, 40, 300):                                          # every kernel class, on the exact K-packed re-layout
+        x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+        y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+        assert rel_err(y, oracle_forward(L, x)) < TOL
+    sd = layer.state_dict()                                               # checkpoint bytes restored exactly
+    assert np.array_equal(sd["qweight"].cpu().numpy(), L["qweight"])
+    assert np.array_equal(sd["qzeros"].cpu().numpy(), L["qzeros"])
+    assert np.array_equal(sd["scales"].cpu().numpy().view(np.uint16), L["scales"].view(np.uint16))
+
+
+def test_awq_gemv_vs_reference_cuda():
+    """The reference's own WQLinear_GEMV kernels (gemv_forward_cuda, gemv_cuda.cu:60-186; gemmv2_forward_cuda) on the same bytes."""
+    import glob, os, sys
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not glob.glob(os.path.join(ref_dir, "awq_inference_engine*.so")):
+        pytest.skip("oracle/_ref not built")
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    import awq_inference_engine as awq
+    K, N, gs = 1024, 512, 128
+    L = O.make_layer("GEMV", 4, gs, K, N, seed=77)
+    layer = layer_from_dict(L)
+    for M in (1, 4):
+        x = torch.randn(M, K, dtype=torch.float16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(M))
+        ref = awq.gemv_forward_cuda(x, layer.qweight, layer.scales, layer.qzeros, gs) if layer.qweight.numel() else None
+        if ref is None:
+            qw, qz, sc = layer._native_tensors()
+            ref = awq.gemv_forward_cuda(x, qw, sc, qz, gs)
+        torch.cuda.synchronize()
+        y = layer(x)
+        torch.cuda.synchronize()
+        err = ((y.double() - ref.double()).abs().max() / ref.double().abs().max()).item()
+        assert err < 2e-3, err
+
+
+# ---- SURVEY 8 f2: pack-mode conversion as an exact integer re-layout on the GPU -----------------------------------
+@pytest.mark.parametrize("src,dst", [("GPTQ", "GEMM"), ("GPTQ", "GEMV"), ("GEMM", "GPTQ"), ("GEMM", "MARLIN"), ("MARLIN", "GEMM"),
+                                      ("GEMV", "GEMM"), ("MARLIN", "GPTQ"), ("GPTQ", "MARLIN")])
+def test_pack_mode_conversion_is_exact(src, dst):
+    """convert_layer == what the TARGET class's own pack() would have written for the same integers (oracle packers,
+    pinned to the reference's pack() by tests/golden), and the converted layer computes the same outputs."""
+    import qllm_b200
+    K, N, gs = 512, 256, 128
+    sym = "MARLIN" in (src, dst)
+    rng = np.random.default_rng(11)
+    base = O.make_layer("MARLIN" if sym else "GPTQ", 4, gs, K, N, seed=42)          # fixes q, s (and z == 8 when symmetric)
+    q, s = base["q"], base["s"]
+    z = np.full((K // gs, N), 8, dtype=np.int32) if sym else base["z"]
+
+    def packed(layout):
+        if layout == "GPTQ":
+            return O.gptq_pack_qweight(q, 4), O.gptq_pack_qzeros(z, 4), s
+        if layout == "GEMM":
+            return O.awq_pack_qweight(q), O.awq_pack_qzeros(z), s
+        if layout == "GEMV":
+            return O.awq_gemv_pack(q, z, s, gs)
+        qw, sp = O.marlin_pack(q, s, gs)
+        return qw, None, sp
+
+    qw, qz, sc = packed(src)
+    L = dict(layout=src, bits=4, group_size=gs, K=K, N=N, bias=None, g_idx=O.default_g_idx(K, gs), qweight=qw, qzeros=qz, scales=sc)
+    layer = layer_from_dict(L)
+    new = qllm_b200.convert_layer(layer, dst)
+    assert type(new).__name__ == {"GPTQ": "QuantLinearGPTQ", "GEMM": "WQLinear_GEMM", "GEMV": "WQLinear_GEMV", "MARLIN": "QuantLinearMarlin"}[dst]
+    tw, tz, ts = packed(dst)
+    assert np.array_equal(new.qweight.cpu().numpy(), tw)
+    if tz is not None:
+        assert np.array_equal(new.qzeros.cpu().numpy(), tz)
+    assert np.array_equal(new.scales.cpu().numpy().view(np.uint16), np.asarray(ts).view(np.uint16))
+    x = torch.randn(3, K, dtype=torch.float16, device="cuda")
+    ref = O.matmul_ref(x.cpu().numpy(), O.dequant(q, z, s, O.default_g_idx(K, gs), "engine"), None, acc=np.float64)
+    assert rel_err(new(x).float().cpu().numpy(), ref) < TOL
+
+
+def test_marlin_conversion_needs_symmetric_zeros():
+    import qllm_b200
+    layer = layer_from_dict(O.make_layer("GPTQ", 4, 128, 256, 256, seed=3))
+    with pytest.raises(ValueError):
+        qllm_b200.convert_layer(layer, "MARLIN")
+
+
+def test_repack_to_new_mode_on_a_module_tree():
+    import qllm_b200
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = layer_from_dict(O.make_layer("GEMM", 4, 128, 256, 128, seed=1))
+            self.b = layer_from_dict(O.make_layer("GEMM", 4, 128, 128, 256, seed=2))
+
+        def forward(self, x):
+            return self.b(self.a(x))
+
+    m = Block()
+    x = torch.randn(2, 256, dtype=torch.float16, device="cuda")
+    y0 = m(x)
+    qllm_b200.repack_to_new_mode(m, "GPTQ")
+    assert isinstance(m.a, qllm_b200.QuantLinearGPTQ) and isinstance(m.b, qllm_b200.QuantLinearGPTQ)
+    assert torch.allclose(m(x).float(), y0.float(), rtol=0, atol=2e-3 * y0.float().abs().max().item())
+
+
+# ---- SURVEY 8 f4: ORT MatMulNBits blobs (QuantLinearORT) ----------------------------------------------------------
+@pytest.mark.parametrize("gs,K,N,act", [(128, 512, 128, False), (32, 256, 96, False), (64, 192, 64, False), (128, 512, 64, True)])
+def test_ort_blob_layout(gs, K, N, act):
+    L = O.make_layer("ORT", 4, gs, K, N, seed=K + N + gs, bias=True, act_order=act)
+    layer = layer_from_dict(L)
+    q, z = layer.unpack_int()
+    assert np.array_equal(q.cpu().numpy(), L["q"]) and np.array_equal(z.cpu().numpy(), L["z"])
+    W = layer.dequantize().cpu().numpy()
+    assert np.array_equal(W.view(np.uint16), O.dequant(L["q"], L["z"], L["s"], L["g_idx"], "engine").view(np.uint16))
+    for M in (1, 6, 40):
+        x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+        y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+        assert rel_err(y, oracle_forward(L, x)) < TOL
+    if not act:                                                           # one packed copy; checkpoint bytes restored exactly
+        assert layer.qweight.numel() == 0
+        sd = layer.state_dict()
+        assert np.array_equal(sd["qweight"].cpu().numpy(), L["qweight"]) and np.array_equal(sd["qzeros"].cpu().numpy(), L["qzeros"])
+        assert np.array_equal(sd["scales"].cpu().numpy().view(np.uint16), L["scales"].view(np.uint16))
+
+
+def test_ort_conversion_targets():
+    import qllm_b200
+    L = O.make_layer("GEMM", 4, 128, 256, 128, seed=5)
+    new = qllm_b200.convert_layer(layer_from_dict(L), "ORT")
+    qw, qz, sp = O.ort_pack(L["q"], L["z"], L["s"], 128)
+    assert np.array_equal(new.qweight.cpu().numpy(), qw) and np.array_equal(new.qzeros.cpu().numpy(), qz)
+    assert np.array_equal(new.scales.cpu().numpy().view(np.uint16), sp.view(np.uint16))

@@ -6,7 +6,8 @@ import torch
 
 from oracle import qlinear_oracle as O
 
-CLS = {"GPTQ": "QuantLinearGPTQ", "HQQ": "QuantLinearHQQ", "GEMM": "WQLinear_GEMM", "MARLIN": "QuantLinearMarlin"}
+CLS = {"GPTQ": "QuantLinearGPTQ", "HQQ": "QuantLinearHQQ", "GEMM": "WQLinear_GEMM", "MARLIN": "QuantLinearMarlin",
+       "GEMV": "WQLinear_GEMV", "ORT": "QuantLinearORT"}
 
 
 def layer_from_dict(L, device="cuda", dtype=torch.float16):
@@ -18,7 +19,7 @@ def layer_from_dict(L, device="cuda", dtype=torch.float16):
     if L["qzeros"] is not None:
         layer.qzeros = torch.from_numpy(np.ascontiguousarray(L["qzeros"]))
     layer.scales = torch.from_numpy(L["scales"])
-    if L["layout"] == "GPTQ":
+    if L["layout"] in ("GPTQ", "ORT"):
         layer.g_idx = torch.from_numpy(L["g_idx"].astype(np.int32))
     if L["bias"] is not None:
         layer.bias = torch.from_numpy(L["bias"])
