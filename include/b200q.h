@@ -98,6 +98,27 @@ typedef struct b200q_layer {
 int b200q_linear(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy,
                  void* workspace, size_t workspace_bytes, b200q_stream_t stream);
 
+/*
+ * b200q_linear with the element-wise neighbours of the Linear fused in.  In an HF decoder
+ * block the QuantLinear calls are surrounded by  down_proj(act_fn(gate_proj(x)) * up_proj(x))  and  residual + o_proj(..) /
+ * residual + down_proj(..)  -- separate element-wise kernels in the reference's model code, each a launch plus an HBM
+ * round trip of the activations:
+ *   x_mul    != NULL: the layer's input is  silu(x) * x_mul  (x = gate_proj output, x_mul = up_proj output, both fp16
+ *                     [M, ldx]); rounded exactly as the two fp16 ops round (silu to fp16, product to fp16);
+ *   residual != NULL: y = fp16(fp16(x @ W + bias) + residual), residual fp16 [M, ldres] -- bit-identical to the separate add.
+ * The integer decode kernel folds x_mul into its x-load stage and both decode kernels and the tcgen05 GEMM add the
+ * residual in their epilogue; other kernels get a small element-wise pass ahead / behind (same results).
+ * Workspace: b200q_workspace_bytes_ex().
+ */
+typedef struct b200q_fusion {
+  const void* x_mul;
+  const void* residual;
+  int64_t ldres;
+} b200q_fusion;
+int b200q_linear_ex(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy, const b200q_fusion* fusion,
+                    void* workspace, size_t workspace_bytes, b200q_stream_t stream);
+size_t b200q_workspace_bytes_ex(const b200q_layer* layer, int64_t M, const b200q_fusion* fusion);
+
 /* Same contract, forcing the decode (GEMV-class) kernel; M must be <= b200q_gemv_max_m(). */
 int b200q_gemv(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy,
                void* workspace, size_t workspace_bytes, b200q_stream_t stream);

@@ -5,7 +5,7 @@ if the library has not been built the import raises: there is no CPU or PyTorch 
 """
 from ._lib import lib, check, Layer  # noqa: F401  (raises ImportError when the .so is missing)
 from .q_layers import (QuantLinearGPTQ, QuantLinearHQQ, QuantLinearMarlin, QuantLinearORT, WQLinear_GEMM, WQLinear_GEMV,  # noqa: F401
-                       fuse_siblings, linear_group, make_mixbits_quant_linear, select_quant_linear)
+                       fuse_siblings, fused_mlp, linear_group, make_mixbits_quant_linear, select_quant_linear)
 
 from .chain import DecodeChain  # noqa: F401,E402
 from .repack import convert_layer, repack_to_new_mode  # noqa: F401,E402

@@ -25,6 +25,11 @@ class ChainStep(ctypes.Structure):
                 ("ldx", ctypes.c_int64), ("y", ctypes.POINTER(ctypes.c_void_p)), ("ldy", ctypes.POINTER(ctypes.c_int64))]
 
 
+class Fusion(ctypes.Structure):
+    """struct b200q_fusion"""
+    _fields_ = [("x_mul", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("ldres", ctypes.c_int64)]
+
+
 class PeerSync(ctypes.Structure):
     """struct b200q_peer_sync"""
     _fields_ = [("n_peers", ctypes.c_int32), ("self_rank", ctypes.c_int32), ("counters", ctypes.POINTER(ctypes.c_void_p)),
@@ -37,7 +42,7 @@ EXPORTS = ["b200q_linear", "b200q_linear_group", "b200q_gemv", "b200q_gemm", "b2
            "b200q_workspace_bytes", "b200q_gemv_max_m", "b200q_select_kernel", "b200q_launch_count",
            "b200q_strerror", "b200q_last_cuda_error", "b200q_version", "b200q_debug_set_timeline", "b200q_repack_gptq4", "b200q_debug_decode_plan", "b200q_debug_set_option", "b200q_linear_group_sharded", "b200q_sharded_posts",
            "b200q_peer_epoch_advance", "b200q_peer_wait", "b200q_peer_untag", "b200q_repack_actorder",
-           "b200q_repack_from_gptq4", "b200q_chain_plan_bytes", "b200q_chain_plan", "b200q_chain_run", "b200q_debug_set_chain_timeline"]
+           "b200q_repack_from_gptq4", "b200q_linear_ex", "b200q_workspace_bytes_ex", "b200q_chain_plan_bytes", "b200q_chain_plan", "b200q_chain_run", "b200q_debug_set_chain_timeline"]
 
 
 def _load():
@@ -61,6 +66,10 @@ def _load():
     for name in ("b200q_linear", "b200q_gemv", "b200q_gemm"):
         getattr(lib, name).argtypes = fwd
         getattr(lib, name).restype = ctypes.c_int
+    lib.b200q_linear_ex.argtypes = [LP, P, I64, I64, P, I64, ctypes.POINTER(Fusion), P, SZ, P]
+    lib.b200q_linear_ex.restype = ctypes.c_int
+    lib.b200q_workspace_bytes_ex.argtypes = [LP, I64, ctypes.POINTER(Fusion)]
+    lib.b200q_workspace_bytes_ex.restype = SZ
     lib.b200q_linear_sharded.argtypes = [LP, P, I64, I64, ctypes.POINTER(P), ctypes.c_int32, I64, I64, P, SZ, P]
     lib.b200q_linear_sharded.restype = ctypes.c_int
     lib.b200q_linear_group.argtypes = [ctypes.POINTER(LP), ctypes.c_int32, P, I64, I64, ctypes.POINTER(P),

@@ -187,8 +187,13 @@ static size_t gather_bytes(const LayerView& V, int64_t M) {
   return V.x_perm ? (((size_t)M * (size_t)V.K * 2 + 255) & ~(size_t)255) : 0;
 }
 
+static size_t silu_bytes(const LayerView& V, int64_t M, const b200q_fusion* fu) {
+  return (fu && fu->x_mul) ? (((size_t)M * (size_t)V.K * 2 + 255) & ~(size_t)255) : 0;
+}
+
 static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, const PeerOut* peers, void* y,
-               int64_t ldy, int64_t n_offset, void* ws, size_t ws_bytes, b200q_stream_t stream, int force) {
+               int64_t ldy, int64_t n_offset, void* ws, size_t ws_bytes, b200q_stream_t stream, int force,
+               const b200q_fusion* fu = nullptr) {
   const int v = validate(layer);
   if (v != B200Q_OK) return v;
   if (!x || (!y && !peers)) return B200Q_ERR_NULL;
@@ -197,13 +202,29 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   if (M < 1 || ldx < layer->K || ldy < n_offset + layer->N) return B200Q_ERR_SHAPE;
   gemv_variant();                          // one-time parse of the B200Q_* switches
   LayerView V = make_view(layer);
-  const size_t base = workspace_for(V, M), need = base + gather_bytes(V, M);
+  const size_t base = workspace_for(V, M), need = base + gather_bytes(V, M) + silu_bytes(V, M, fu);
   if (need > 0 && (!ws || ws_bytes < need)) return B200Q_ERR_WORKSPACE;
   if (ws && ((uintptr_t)ws & 15)) return B200Q_ERR_ALIGNMENT;
+  const __half* x_mul = fu ? (const __half*)fu->x_mul : nullptr;
+  const __half* residual = fu ? (const __half*)fu->residual : nullptr;
+  const int64_t ldres = fu ? fu->ldres : 0;
+  if (residual && (ldres < layer->N || peers)) return B200Q_ERR_SHAPE;
+  if (x_mul) {
+    // act(gate) * up: folded into the x stage of the integer-path decode kernel; every other kernel reads a fused copy
+    LinearArgs probe = {};
+    probe.L = V; probe.x = (const __half*)x; probe.ldx = ldx; probe.M = (int)M; probe.x_mul = x_mul;
+    const bool folded = force != KERNEL_GEMM_TC && M <= kGemvMaxM && g_use_stream && gemv_imma_supported(&probe, 1);
+    if (!folded) {
+      __half* xs = (__half*)((char*)ws + base + gather_bytes(V, M));
+      const cudaError_t e = launch_silu_mul((const __half*)x, x_mul, ldx, xs, M, V.K, (cudaStream_t)stream);
+      if (e != cudaSuccess) return cuda_status(e);
+      x = xs; ldx = V.K; x_mul = nullptr;
+    }
+  }
   if (V.x_perm) {
     // the integer-path decode kernel gathers x through x_perm in its own load stage; everything else reads a gathered copy
     LinearArgs probe = {};
-    probe.L = V; probe.x = (const __half*)x; probe.ldx = ldx; probe.M = (int)M;
+    probe.L = V; probe.x = (const __half*)x; probe.ldx = ldx; probe.M = (int)M; probe.x_mul = x_mul;
     const bool folded = force != KERNEL_GEMM_TC && M <= kGemvMaxM && g_use_stream && (gemv_variant(), true) && gemv_imma_supported(&probe, 1);
     if (!folded) {
       if (M > 0x7fffffff / 2) return B200Q_ERR_SHAPE;
@@ -215,12 +236,20 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   }
   const int kern = select(V, M, (const __half*)x, ldx, force);
   if (kern < 0) return kern;
-  LinearArgs a;
+  LinearArgs a = {};
   a.L = V; a.x = (const __half*)x; a.ldx = ldx; a.M = (int)M; a.y = (__half*)y; a.ldy = ldy; a.n_offset = n_offset;
   a.workspace = ws; a.workspace_bytes = ws_bytes; a.stream = (cudaStream_t)stream;
+  a.x_mul = x_mul; a.residual = residual; a.ldres = ldres;
+  // kernels that do not carry the residual epilogue get it as a small pass behind them
+  auto with_residual = [&](cudaError_t e) {
+    if (e != cudaSuccess || !residual) return cuda_status(e);
+    return cuda_status(launch_residual_add((__half*)y, ldy, residual, ldres, M, V.N, (cudaStream_t)stream));
+  };
   if (kern == KERNEL_GEMV_MMA) {
     if (g_use_stream && gemv_imma_supported(&a, 1)) return cuda_status(launch_gemv_imma(&a, 1, peers));
+    a.x_mul = nullptr;                                      // (never set here: only the integer-path kernel folds it)
     if (g_use_stream && gemv_stream_supported(&a, 1)) return cuda_status(launch_gemv_stream(&a, 1, peers));
+    a.residual = nullptr;
     if (gemv_variant() == 2) {
       // Measured on B200 (profiles/README.md): the MMA kernel with the packed slice staged in shared memory wins
       // while its slice leaves >= 2 CTAs per SM; for long-K layers (slice > 112 KB) the register-prefetch FMA
@@ -228,12 +257,16 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
       const bool rp_ok = gemv_rp_supported(V, (int)M, a.x, ldx);
       const bool fma_ok = gemv_fma_supported(V, (int)M, a.x, ldx);
       const bool prefer_fma = fma_ok && (!rp_ok || g_force_fma || gemv_rp_smem_bytes(V, (int)M) > 112 * 1024);
-      if (prefer_fma) return cuda_status(launch_gemv_fma(a, peers));
-      if (rp_ok) return cuda_status(launch_gemv_rp(a, peers));
+      if (prefer_fma) return with_residual(launch_gemv_fma(a, peers));
+      if (rp_ok) return with_residual(launch_gemv_rp(a, peers));
     }
-    return cuda_status(launch_gemv_mma(a, peers));
+    return with_residual(launch_gemv_mma(a, peers));
   }
-  if (kern == KERNEL_GEMM_TC) return cuda_status(launch_gemm_tc(a, peers));
+  if (kern == KERNEL_GEMM_TC) {
+    if (residual && (((uintptr_t)residual & 15) != 0 || (ldres % 8) != 0)) { a.residual = nullptr; return with_residual(launch_gemm_tc(a, peers)); }
+    return cuda_status(launch_gemm_tc(a, peers));
+  }
+  a.residual = nullptr;
   // generic: slabs of <= 16 activation rows
   for (int64_t m0 = 0; m0 < M; m0 += kGenericMaxM) {
     LinearArgs s = a;
@@ -245,7 +278,7 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
     const cudaError_t e = launch_gemv_generic(s, &po);
     if (e != cudaSuccess) return cuda_status(e);
   }
-  return B200Q_OK;
+  return with_residual(cudaSuccess);
 }
 }  // namespace b200q
 
@@ -256,6 +289,18 @@ extern "C" {
 int b200q_linear(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy, void* workspace,
                  size_t workspace_bytes, b200q_stream_t stream) {
   return run(layer, x, M, ldx, nullptr, y, ldy, 0, workspace, workspace_bytes, stream, 0);
+}
+
+int b200q_linear_ex(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy, const b200q_fusion* fusion,
+                    void* workspace, size_t workspace_bytes, b200q_stream_t stream) {
+  return run(layer, x, M, ldx, nullptr, y, ldy, 0, workspace, workspace_bytes, stream, 0, fusion);
+}
+
+size_t b200q_workspace_bytes_ex(const b200q_layer* layer, int64_t M, const b200q_fusion* fusion) {
+  if (validate(layer) != B200Q_OK || M < 1) return 0;
+  gemv_variant();
+  const LayerView V = make_view(layer);
+  return workspace_for(V, M) + gather_bytes(V, M) + silu_bytes(V, M, fusion);
 }
 
 int b200q_gemv(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy, void* workspace,

@@ -133,6 +133,12 @@ __device__ __forceinline__ __half dequant_one(const LayerView& L, uint32_t q, fl
   return __float2half_rn(d * s);
 }
 
+// act(gate) * up as the unfused torch ops compute it in fp16: silu evaluated in fp32 and rounded, the product rounded again
+__device__ __forceinline__ float silu_mul_f16(float g, float u) {
+  const float s = __half2float(__float2half_rn(g / (1.0f + expf(-g))));
+  return __half2float(__float2half_rn(s * u));
+}
+
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -47,6 +47,8 @@ struct TcParams {
   int M;
   PeerOut out;
   int64_t ldy, n_offset;
+  const __half* residual;                   // NULL, or [M, ldres]: added to the rounded output in the epilogue (b200q_linear_ex)
+  int64_t ldres;
   int kblocks, gshift, group32, nsx, nsw;   // nsx / nsw: X and W ring depths actually used
   int ksplit, kb_per;                       // split-K over gridDim.z (small M): k-blocks per split; partial tiles + last-arriver reduction
   float* partial;                           // [ksplit][M][N] fp32 (workspace, behind the counter region)
@@ -462,7 +464,19 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         const int idx = tih + 128 * j, row = idx >> 4, ch = idx & 15;
         const int tok = tok0 + c0 + row;
         if (tok < p.M && n0 + 8 * ch < p.L.N) {
-          const uint4 val = *reinterpret_cast<const uint4*>(stg + (size_t)row * (kBN + 8) + 8 * ch);
+          uint4 val = *reinterpret_cast<const uint4*>(stg + (size_t)row * (kBN + 8) + 8 * ch);
+          if (p.residual) {                         // y = fp16(fp16(acc + bias) + residual), as the unfused fp16 add rounds
+            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)tok * p.ldres + n0 + 8 * ch));
+            const __half2* a2 = reinterpret_cast<const __half2*>(&val);
+            const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+            __half2 o2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fa = __half22float2(a2[e]), fr = __half22float2(r2[e]);
+              o2[e] = __floats2half2_rn(fa.x + fr.x, fa.y + fr.y);
+            }
+            val = *reinterpret_cast<const uint4*>(o2);
+          }
           for (int qd = 0; qd < p.out.n; ++qd)
             *reinterpret_cast<uint4*>(p.out.y[qd] + (size_t)tok * p.ldy + p.n_offset + n0 + 8 * ch) = val;
         }
@@ -495,7 +509,8 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             for (int z = 0; z < p.ksplit; ++z) acc += __ldcg(p.partial + ((size_t)z * p.M + tok) * p.L.N + nn);
             const float bv = __half2float(bsrc[nn]);
             if (has_bias) acc += bv;
-            const __half h = __float2half_rn(acc);
+            __half h = __float2half_rn(acc);
+            if (p.residual) h = __float2half_rn(__half2float(h) + __half2float(p.residual[(size_t)tok * p.ldres + nn]));
             for (int qd = 0; qd < p.out.n; ++qd) p.out.y[qd][(size_t)tok * p.ldy + p.n_offset + nn] = h;
           }
         }
@@ -623,6 +638,8 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   p.L = L; p.M = a.M;
   if (peers) p.out = *peers; else { p.out.n = 1; p.out.y[0] = a.y; }
   p.ldy = a.ldy; p.n_offset = a.n_offset;
+  p.residual = a.residual; p.ldres = a.ldres;
+  if (a.residual && (((uintptr_t)a.residual & 15) != 0 || (a.ldres % 8) != 0)) return cudaErrorInvalidValue;
   p.kblocks = L.K / kBK;
   p.ksplit = tc_ksplit(L, a.M);
   p.kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;

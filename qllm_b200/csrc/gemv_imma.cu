@@ -185,6 +185,19 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
           }
           const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
           xv[0] = __low2float(h01); xv[1] = __high2float(h01); xv[2] = __low2float(h23); xv[3] = __high2float(h23);
+          if (p.xmul) {                                                  // fused act(gate) * up: x = silu(x) * x_mul, rounded as the fp16 ops round
+            uint2 rm;
+            if (p.xperm) {
+              const int4 pi = *reinterpret_cast<const int4*>(p.xperm + (size_t)ks * 32 + 4 * lane);
+              const unsigned short* xr = reinterpret_cast<const unsigned short*>(p.xmul + (size_t)m * p.ldx);
+              rm = make_uint2((uint32_t)xr[pi.x] | ((uint32_t)xr[pi.y] << 16), (uint32_t)xr[pi.z] | ((uint32_t)xr[pi.w] << 16));
+            } else {
+              rm = *reinterpret_cast<const uint2*>(p.xmul + xo);
+            }
+            const __half2 u01 = *reinterpret_cast<const __half2*>(&rm.x), u23 = *reinterpret_cast<const __half2*>(&rm.y);
+            xv[0] = silu_mul_f16(xv[0], __low2float(u01)); xv[1] = silu_mul_f16(xv[1], __high2float(u01));
+            xv[2] = silu_mul_f16(xv[2], __low2float(u23)); xv[3] = silu_mul_f16(xv[3], __high2float(u23));
+          }
         }
         // a NaN / Inf activation poisons its part (fmaxf drops NaN and the fixed-point conversion would turn Inf into
         // finite garbage; the reference's fp16 FMA chains propagate both): every output of the layer becomes NaN
@@ -428,7 +441,7 @@ static bool im_plan(const LinearArgs* a, int n, ImPlan& pl) {
 bool gemv_imma_supported(const LinearArgs* a, int n) {
   ImPlan pl;
   if (!im_plan(a, n, pl)) return false;
-  if (((uintptr_t)a[0].x & 7) != 0 || (a[0].ldx % 4) != 0) return false;
+  if (((uintptr_t)a[0].x & 7) != 0 || (a[0].ldx % 4) != 0 || ((uintptr_t)a[0].x_mul & 7) != 0) return false;
   for (int i = 0; i < n; ++i)
     if (((uintptr_t)a[i].L.qw & 15) != 0 || ((uintptr_t)a[i].L.s & 15) != 0) return false;
   return true;
@@ -488,6 +501,7 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers, c
     d.cta0 = i < n ? pl.cta0[i] : (1 << 30);
     if (peers) d.out = peers[k]; else { d.out.n = 1; d.out.y[0] = a[k].y; }
     d.ldy = a[k].ldy; d.n_offset = a[k].n_offset;
+    d.residual = a[k].residual; d.ldres = a[k].ldres;
   }
   if (sync) {
     p.sync = *sync;
@@ -497,7 +511,8 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers, c
     if (sync->n_peers > 1 && sync->post_slot >= 0 && (!a[0].workspace || a[0].workspace_bytes < kCounterBytes)) return cudaErrorInvalidValue;
   }
   p.layout = L.layout; p.bits = L.bits; p.group = L.group; p.K = L.K; p.G = L.G; p.zero_bias = L.zero_bias;
-  p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M; p.xperm = L.x_perm;
+  p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M; p.xperm = L.x_perm; p.xmul = a[0].x_mul;
+  if (p.xmul && sync && sync->x_tagged) return cudaErrorInvalidValue;     // tagged activations carry no second operand
   if (L.x_perm && sync && sync->x_tagged) return cudaErrorInvalidValue;    // gather through x_perm reads plain fp16 activations
   p.cluster = pl.cluster; p.tpc = pl.tpc; p.depth = pl.depth; p.steps_total = pl.steps_total; p.group_shift = pl.group_shift;
   p.gcap = pl.gcap; p.split_q = pl.split_q; p.split_r = pl.split_r; p.part_cap = pl.part_cap;

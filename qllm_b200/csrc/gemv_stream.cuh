@@ -15,6 +15,8 @@ struct StLayer {
   int N, cta0;              // output columns; first CTA-group index of this layer
   PeerOut out;
   int64_t ldy, n_offset;
+  const __half* residual;   // NULL, or [M, ldres]: added to the rounded output (b200q_linear_ex)
+  int64_t ldres;
 };
 
 struct StParams {
@@ -23,6 +25,7 @@ struct StParams {
   int layout, bits, group, K, G, zero_bias;      // shared by the layers of a group
   const __half* x;
   const int* xperm;                              // act-order re-layout: x is read through this map (integer-path kernel only)
+  const __half* xmul;                            // NULL, or the `up` half of silu(x) * up (integer-path kernel only)
   int64_t ldx;
   int M;
   int cluster, tpc, depth, steps_total, group_shift, gcap, split_q, split_r, part_cap;
@@ -188,7 +191,8 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
     if (idx < totalv && n < ncols_cta) {
       float o = v[r];
       if (SL.bias) o += __half2float(__ldg(SL.bias + n0 + n));
-      const __half h = __float2half_rn(o);
+      __half h = __float2half_rn(o);
+      if (SL.residual) h = __float2half_rn(__half2float(h) + __half2float(__ldg(SL.residual + (size_t)m * SL.ldres + n0 + n)));
       if (PEER && p.sync.y_tagged) {                        // one 4-byte store per element and replica: value and tag land together
         const uint32_t w = ytag | (uint32_t)__half_as_ushort(h);
         for (int q = 0; q < SL.out.n; ++q)

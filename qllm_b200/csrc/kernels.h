@@ -23,6 +23,10 @@ struct LinearArgs {
   void* workspace;
   size_t workspace_bytes;
   cudaStream_t stream;
+  // fused neighbours of the Linear (b200q_linear_ex; NULL = none)
+  const __half* x_mul;       // the layer's input is fp16(fp16(silu(x)) * x_mul), same strides as x (LlamaMLP.down_proj(act(gate) * up))
+  const __half* residual;    // y = fp16(fp16(x @ W + bias) + residual): the decoder block's skip connection
+  int64_t ldres;
 };
 
 static constexpr int kMaxPeers = 8;
@@ -55,6 +59,8 @@ cudaError_t launch_unpack(const LayerView& L, int32_t* q_out, int32_t* z_out, cu
 cudaError_t launch_dequant(const LayerView& L, __half* w_out, cudaStream_t st);
 cudaError_t launch_repack_actorder(const LayerView& L, const int* perm, uint32_t* qw_out, cudaStream_t st);
 cudaError_t launch_gather_x(const __half* x, int64_t ldx, const int* perm, __half* out, int M, int K, cudaStream_t st);
+cudaError_t launch_silu_mul(const __half* x, const __half* x_mul, int64_t ldx, __half* out, int64_t M, int K, cudaStream_t st);
+cudaError_t launch_residual_add(__half* y, int64_t ldy, const __half* res, int64_t ldres, int64_t M, int N, cudaStream_t st);
 cudaError_t launch_repack_gptq4(const LayerView& L, uint32_t* qw_out, uint32_t* qz_out, __half* s_out, cudaStream_t st);
 cudaError_t launch_repack_from_gptq4(const LayerView& L, int target, uint32_t* qw_out, uint32_t* qz_out, __half* s_out, cudaStream_t st);
 

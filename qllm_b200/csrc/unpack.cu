@@ -171,6 +171,37 @@ cudaError_t launch_gather_x(const __half* x, int64_t ldx, const int* perm, __hal
   return cudaGetLastError();
 }
 
+// Fallback halves of the fused neighbours for kernels that do not carry them: out = silu(x) * x_mul ahead of the kernel,
+// y += residual behind it (the integer decode kernel and the tcgen05 GEMM fuse them instead).
+__global__ void __launch_bounds__(256) silu_mul_kernel(const __half* __restrict__ x, const __half* __restrict__ xm, int64_t ldx,
+                                                       __half* __restrict__ out, int64_t M, int K) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * K) return;
+  const int64_t m = idx / K;
+  const int k = (int)(idx - m * K);
+  out[idx] = __float2half_rn(silu_mul_f16(__half2float(x[m * ldx + k]), __half2float(xm[m * ldx + k])));
+}
+cudaError_t launch_silu_mul(const __half* x, const __half* x_mul, int64_t ldx, __half* out, int64_t M, int K, cudaStream_t st) {
+  const int64_t total = M * K;
+  silu_mul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, x_mul, ldx, out, M, K);
+  count_launch();
+  return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256) residual_add_kernel(__half* __restrict__ y, int64_t ldy, const __half* __restrict__ res, int64_t ldres,
+                                                           int64_t M, int N) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int64_t m = idx / N;
+  const int n = (int)(idx - m * N);
+  y[m * ldy + n] = __float2half_rn(__half2float(y[m * ldy + n]) + __half2float(res[m * ldres + n]));
+}
+cudaError_t launch_residual_add(__half* y, int64_t ldy, const __half* res, int64_t ldres, int64_t M, int N, cudaStream_t st) {
+  const int64_t total = M * N;
+  residual_add_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, ldy, res, ldres, M, N);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_unpack(const LayerView& L, int32_t* q_out, int32_t* z_out, cudaStream_t st) {
   const size_t total = (size_t)L.K * (L.N >> 3);
   unpack_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, q_out, nullptr);

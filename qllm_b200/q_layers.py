@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import codec
-from ._lib import (LAYOUT_AWQ_GEMM, LAYOUT_AWQ_GEMV, LAYOUT_GPTQ, LAYOUT_HQQ, LAYOUT_MARLIN, LAYOUT_ORT, Layer, check, lib)
+from ._lib import (LAYOUT_AWQ_GEMM, LAYOUT_AWQ_GEMV, LAYOUT_GPTQ, LAYOUT_HQQ, LAYOUT_MARLIN, LAYOUT_ORT, Fusion, Layer, check, lib)
 
 _RELAYOUT = (LAYOUT_AWQ_GEMM, LAYOUT_MARLIN, LAYOUT_AWQ_GEMV, LAYOUT_ORT)      # layouts that run on their exact K-packed re-layout
 
@@ -268,6 +268,44 @@ class _B200QuantLinearBase(nn.Module):
             st = lib.b200q_linear(ctypes.byref(desc), x2.data_ptr(), M, x2.stride(0), y.data_ptr(), y.stride(0),
                                   ws.data_ptr(), ws.numel(), torch.cuda.current_stream(x.device).cuda_stream)
             check(st, type(self).__name__ + ".forward")
+        if y.dtype != x.dtype:
+            y = y.to(x.dtype)
+        return y.reshape(out_shape)
+
+    def forward_fused(self, x, x_mul=None, residual=None):
+        """forward() with the Linear's element-wise neighbours fused in (b200q_linear_ex):
+        y = (silu(x) * x_mul if x_mul is not None else x) @ W + bias (+ residual).  Same results as the separate fp16 ops."""
+        out_shape = x.shape[:-1] + (self.outfeatures,)
+        def prep(t):
+            t2 = t.reshape(-1, t.shape[-1])
+            if t2.dtype != torch.float16:
+                t2 = t2.to(torch.float16)
+            return t2 if t2.stride(-1) == 1 else t2.contiguous()
+        x2 = prep(x)
+        M = x2.shape[0]
+        fu = Fusion()
+        keep = []
+        if x_mul is not None:
+            xm = prep(x_mul)
+            if xm.stride(0) != x2.stride(0):
+                xm, x2 = xm.contiguous(), x2.contiguous()
+            keep.append(xm)
+            fu.x_mul = xm.data_ptr()
+        if residual is not None:
+            r2 = prep(residual)
+            keep.append(r2)
+            fu.residual, fu.ldres = r2.data_ptr(), r2.stride(0)
+        y = torch.empty((M, self.outfeatures), dtype=torch.float16, device=x.device)
+        if M > 0:
+            desc = self._decode_descriptor(8) if self._layout in _RELAYOUT else self._fast_descriptor()
+            if M > lib.b200q_gemv_max_m() and lib.b200q_select_kernel(ctypes.byref(desc), M) != 2:
+                desc = self._gemm_descriptor()
+            elif M <= 2:
+                desc = self._decode_descriptor(M)
+            ws = _workspace(x.device, lib.b200q_workspace_bytes_ex(ctypes.byref(desc), M, ctypes.byref(fu)))
+            check(lib.b200q_linear_ex(ctypes.byref(desc), x2.data_ptr(), M, x2.stride(0), y.data_ptr(), y.stride(0), ctypes.byref(fu),
+                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream(x.device).cuda_stream),
+                  type(self).__name__ + ".forward_fused")
         if y.dtype != x.dtype:
             y = y.to(x.dtype)
         return y.reshape(out_shape)
@@ -620,6 +658,14 @@ def linear_group(layers, x):
             y = y.to(x.dtype)
         outs.append(y.reshape(x.shape[:-1] + (l.outfeatures,)))
     return outs
+
+
+def fused_mlp(gate_proj, up_proj, down_proj, x, residual=None):
+    """LlamaMLP.forward -- down_proj(silu(gate_proj(x)) * up_proj(x)) (+ residual) -- in two engine calls at decode sizes:
+    gate|up as one sibling-group launch, then down_proj with the activation folded into its x stage and the skip
+    connection into its epilogue (no element-wise kernels, no extra activation round trips)."""
+    g, u = linear_group([gate_proj, up_proj], x)
+    return down_proj.forward_fused(g, x_mul=u, residual=residual)
 
 
 class _SiblingGroup:
