@@ -424,11 +424,9 @@ def run_b200q(args, rank, world, local_rank):
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
-        t_w = time.perf_counter()
-        for _ in range(warm):
-            graph.replay()
-        barrier()
-        while time.perf_counter() - t_w < 0.35:      # nvidia-smi's first sample takes ~0.2 s: keep the GPU under the same load until it reports
+        # W warm-up steps, then keep the GPU under the same load until nvidia-smi's first sample (~0.2 s) has been taken.
+        # A FIXED count: every rank must replay the same number of steps (the fused hand-off pairs them up).
+        for _ in range(warm + 300):
             graph.replay()
         barrier()
         e0.record()
