@@ -321,9 +321,9 @@ void b200q_debug_set_chain_timeline(void* device_buf);
 int b200q_debug_decode_plan(const b200q_layer* layer, int64_t M, int32_t out[4]);
 
 /* Diagnostic / tuning only: override a dispatch or planner switch at run time (same switches as the B200Q_*
- * environment variables): "force_cluster", "max_cluster", "planner", "fill_cap", "force_fma",
- * "fma_max_m", "tt256_min_m", "stream" (0 = pre-streaming decode kernels), "st_cluster", "st_depth", "st_tpc",
- * "st_target", "st_ring_kb".  Returns B200Q_ERR_UNSUPPORTED for an unknown name. */
+ * environment variables): "stream" (0 = bulk-copy decode kernel only), "st_cluster", "st_depth", "st_tpc", "st_target",
+ * "st_ring_kb", "st_lean", "imma", "im_cluster", "im_depth", "im_tpc", "im_target", "tt256_min_m", "gemm_pdl",
+ * "gemm_splitk", "sync_flags", "chain_ctas", "chain_slots", "chain_window".  Returns B200Q_ERR_UNSUPPORTED for an unknown name. */
 int b200q_debug_set_option(const char* name, double value);
 
 const char* b200q_strerror(int status);

@@ -8,7 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.environ.get("B200Q_LIB") or os.path.join(PKG, "libb200q.so")   # B200Q_LIB: A/B runs of two builds on one box
-SOURCES = ["api.cu", "unpack.cu", "gemv_generic.cu", "gemv_mma.cu", "gemv_rp.cu", "gemv_stream.cu", "gemv_imma.cu", "gemv_fma.cu",
+SOURCES = ["api.cu", "unpack.cu", "gemv_generic.cu", "gemv_mma.cu", "gemv_stream.cu", "gemv_imma.cu",
            "gemm_tcgen05.cu", "decode_chain.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "--compiler-options", "-fPIC"]

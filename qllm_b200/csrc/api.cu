@@ -95,15 +95,15 @@ static constexpr int kGenericMaxM = 16;
 
 enum { KERNEL_GEMV_MMA = 1, KERNEL_GEMM_TC = 2, KERNEL_GENERIC = 3 };
 
-// Tuning/diagnostic switches, read once: B200Q_GEMV=v1 selects the bulk-copy/mbarrier decode kernel
-// (gemv_mma.cu), =v2 the register-prefetch variant of gemv_rp.cu; default is its cp.async/smem variant.
-static bool g_force_fma = false;
-static bool g_use_stream = true;       // B200Q_GEMV=rp (or v1 / v2) selects the pre-streaming decode kernels
+// Tuning/diagnostic switches, read once.  B200Q_GEMV=v1 (or the "stream" option = 0) takes the streaming decode kernels
+// out of the dispatch: what remains is the bulk-copy / mbarrier kernel of gemv_mma.cu, which is also the fallback for the
+// group sizes the streaming kernels do not tile (below 32 at 4-bit, 64 at 2-bit, 16 at 8-bit).
+static bool g_use_stream = true;
 static int gemv_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200Q_GEMV");
-    v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+    v = 1;
     if (e && (e[0] == 'v' || e[0] == 'r')) g_use_stream = false;
     const char* so[6] = {"B200Q_ST_CLUSTER", "B200Q_ST_DEPTH", "B200Q_ST_TPC", "B200Q_ST_TARGET", "B200Q_ST_RING_KB", "B200Q_ST_LEAN"};
     for (int i = 0; i < 6; ++i) {
@@ -115,31 +115,12 @@ static int gemv_variant() {
       const char* sv = getenv(io[i]);
       if (sv) gemv_imma_set_option(i, atoi(sv));
     }
-    if (e && e[0] == 'v') gemv_fma_set_max_m(0);        // any explicit B200Q_GEMV=v* disables the FMA kernel
-    const char* fm = getenv("B200Q_FMA_MAX_M");
-    if (fm) gemv_fma_set_max_m(atoi(fm));
-    g_force_fma = getenv("B200Q_FORCE_FMA") != nullptr;
-    const char* kb = getenv("B200Q_SLICE_KB");
-    gemv_rp_set_smem(!(e && e[0] == 'v' && e[1] == '2'), kb ? atoi(kb) : 0);   // v2 = register prefetch, default = smem
-    const char* ms = getenv("B200Q_MIN_STEPS");
-    if (ms) gemv_rp_set_min_steps(atoi(ms));
     const char* t = getenv("B200Q_TT256_MIN_M");
     if (t) gemm_tc_set_tt256_min_m(atoi(t));
     const char* gp = getenv("B200Q_GEMM_PDL");
     if (gp) gemm_tc_set_pdl(atoi(gp));
     const char* gk = getenv("B200Q_GEMM_SPLITK");
     if (gk) gemm_tc_set_splitk(atoi(gk));
-    const char* c = getenv("B200Q_MAX_CLUSTER");
-    if (c) gemv_rp_set_max_cluster(atoi(c));
-    const char* fc = getenv("B200Q_FORCE_CLUSTER");
-    if (fc) gemv_rp_set_force_cluster(atoi(fc));
-    const char* pm = getenv("B200Q_PLANNER");          // 0 = legacy power-of-two rule; "1,<cap>" = wave-aware with a slot-fill cap
-    if (pm) {
-      double cap = 0;
-      int mode = 1;
-      sscanf(pm, "%d,%lf", &mode, &cap);
-      gemv_rp_set_planner(mode, cap);
-    }
   }
   return v;
 }
@@ -154,7 +135,6 @@ static bool decode_supported(const LayerView& V, int M, const __half* x, int64_t
     const LinearArgs a = probe_args(V, M, x, ldx);
     if (gemv_imma_supported(&a, 1) || gemv_stream_supported(&a, 1)) return true;
   }
-  if (gemv_variant() == 2 && (gemv_fma_supported(V, M, x, ldx) || gemv_rp_supported(V, M, x, ldx))) return true;
   return gemv_mma_supported(V, M, x, ldx);
 }
 
@@ -250,16 +230,6 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
     a.x_mul = nullptr;                                      // (never set here: only the integer-path kernel folds it)
     if (g_use_stream && gemv_stream_supported(&a, 1)) return cuda_status(launch_gemv_stream(&a, 1, peers));
     a.residual = nullptr;
-    if (gemv_variant() == 2) {
-      // Measured on B200 (profiles/README.md): the MMA kernel with the packed slice staged in shared memory wins
-      // while its slice leaves >= 2 CTAs per SM; for long-K layers (slice > 112 KB) the register-prefetch FMA
-      // kernel wins at M <= 2.
-      const bool rp_ok = gemv_rp_supported(V, (int)M, a.x, ldx);
-      const bool fma_ok = gemv_fma_supported(V, (int)M, a.x, ldx);
-      const bool prefer_fma = fma_ok && (!rp_ok || g_force_fma || gemv_rp_smem_bytes(V, (int)M) > 112 * 1024);
-      if (prefer_fma) return with_residual(launch_gemv_fma(a, peers));
-      if (rp_ok) return with_residual(launch_gemv_rp(a, peers));
-    }
     return with_residual(launch_gemv_mma(a, peers));
   }
   if (kern == KERNEL_GEMM_TC) {
@@ -648,13 +618,7 @@ int b200q_debug_set_option(const char* name, double value) {
   if (!name) return B200Q_ERR_NULL;
   gemv_variant();                                    // environment defaults first, then the override
   const std::string n(name);
-  if (n == "force_cluster") gemv_rp_set_force_cluster((int)value);
-  else if (n == "max_cluster") gemv_rp_set_max_cluster((int)value);
-  else if (n == "planner") gemv_rp_set_planner((int)value, 0);
-  else if (n == "fill_cap") gemv_rp_set_planner(1, value);
-  else if (n == "force_fma") g_force_fma = value != 0;
-  else if (n == "fma_max_m") gemv_fma_set_max_m((int)value);
-  else if (n == "tt256_min_m") gemm_tc_set_tt256_min_m((int)value);
+  if (n == "tt256_min_m") gemm_tc_set_tt256_min_m((int)value);
   else if (n == "stream") g_use_stream = value != 0;
   else if (n == "st_cluster") gemv_stream_set_option(0, (int)value);
   else if (n == "st_depth") gemv_stream_set_option(1, (int)value);
@@ -690,14 +654,11 @@ int b200q_debug_decode_plan(const b200q_layer* layer, int64_t M, int32_t out[4])
     for (int i = 0; i < 4; ++i) out[i] = o[i];
     return B200Q_OK;
   }
-  if (!gemv_rp_describe(V, (int)M, o)) return B200Q_ERR_UNSUPPORTED;
-  for (int i = 0; i < 4; ++i) out[i] = o[i];
-  return B200Q_OK;
+  return B200Q_ERR_UNSUPPORTED;
 }
 
 void b200q_debug_set_timeline(void* device_buf, size_t bytes) {
   gemv_variant();
-  gemv_rp_set_debug((unsigned long long*)device_buf, bytes / 8);
   gemv_stream_set_debug((unsigned long long*)device_buf, bytes / 8);
   gemv_imma_set_debug((unsigned long long*)device_buf, bytes / 8);
   gemm_tc_set_debug(bytes >= 64 * 1024 ? (unsigned long long*)device_buf : nullptr);

@@ -68,22 +68,11 @@ cudaError_t launch_repack_from_gptq4(const LayerView& L, int target, uint32_t* q
 size_t gemv_generic_workspace(const LayerView& L, int M);
 cudaError_t launch_gemv_generic(const LinearArgs& a, const PeerOut* peers);
 
-// gemv_mma.cu : fast decode path (bulk-copy pipeline + mma.sync), M <= 8
+// gemv_mma.cu : bulk-copy (cp.async.bulk + mbarrier) pipeline + mma.sync, M <= 8: fallback for the group sizes the streaming
+// kernels do not tile, and the whole decode path when the streaming kernels are switched off (B200Q_GEMV=v1)
 bool gemv_mma_supported(const LayerView& L, int M, const __half* x, int64_t ldx);
 size_t gemv_mma_workspace(const LayerView& L, int M);
 cudaError_t launch_gemv_mma(const LinearArgs& a, const PeerOut* peers);
-
-// gemv_rp.cu : latency-optimised decode path (register prefetch + cluster split-K), M <= 8
-bool gemv_rp_supported(const LayerView& L, int M, const __half* x, int64_t ldx);
-cudaError_t launch_gemv_rp(const LinearArgs& a, const PeerOut* peers);
-void gemv_rp_set_max_cluster(int c);
-int gemv_rp_smem_bytes(const LayerView& L, int M);
-void gemv_rp_set_smem(bool on, int slice_kb);
-void gemv_rp_set_min_steps(int n);
-void gemv_rp_set_force_cluster(int c);
-bool gemv_rp_describe(const LayerView& L, int M, int out[4]);
-void gemv_rp_set_planner(int mode, double fill_cap);
-void gemv_rp_set_debug(unsigned long long* buf, size_t cap_entries);
 
 // gemv_stream.cu : streaming decode path (per-warp cp.async rings, sibling layers fused in one launch), M <= 8
 static constexpr int kMaxGroupLayers = 3;
@@ -107,11 +96,6 @@ int decode_chain_plan(const LinearArgs* const* groups, const int* n_layers, int 
 cudaError_t launch_decode_chain(const void* plan_host, const void* plan_dev, void* ws, size_t ws_bytes, cudaStream_t st);
 void decode_chain_set_option(int which, int value);
 void decode_chain_set_debug(unsigned long long* buf);   // diagnostic: 16 x u64 per (group, CTA)
-
-// gemv_fma.cu : M <= 2 decode path (CUDA-core fp16x2 FMA, register prefetch, cluster split-K)
-bool gemv_fma_supported(const LayerView& L, int M, const __half* x, int64_t ldx);
-cudaError_t launch_gemv_fma(const LinearArgs& a, const PeerOut* peers);
-void gemv_fma_set_max_m(int m);
 
 // first kCounterBytes of every workspace are arrival counters that must stay zero between calls
 static constexpr size_t kCounterBytes = 4096;

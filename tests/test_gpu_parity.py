@@ -350,7 +350,8 @@ def test_stream_kernel_plan_variations(opt, val, layout, K, N):
 @pytest.mark.parametrize("layout,bits,gs,K,N", [("GEMM", 4, 128, 1024, 1024), ("GPTQ", 4, 128, 1024, 512), ("GPTQ", 2, 64, 1024, 128),
                                                 ("MARLIN", 4, 128, 1024, 512), ("GEMM", 4, 128, 11008, 4096)])
 def test_pre_streaming_decode_kernels_still_agree(layout, bits, gs, K, N):
-    """B200Q_GEMV=rp path (whole-slice prefetch kernels) kept as an alternative: same oracle, same bar."""
+    """The one remaining non-streaming decode kernel (gemv_mma.cu: cp.async.bulk + mbarrier pipeline, the fallback for the
+    group sizes the streaming kernels do not tile) on shapes the streaming kernels also cover: same oracle, same bar."""
     import qllm_b200
     lib = qllm_b200.lib
     L = O.make_layer(layout, bits, gs, K, N, seed=K + N + 1) if K * N < 2 ** 22 else None
