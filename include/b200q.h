@@ -284,7 +284,7 @@ int b200q_repack_from_gptq4(const b200q_layer* layer, int32_t target_layout, voi
 
 /*
  * Act-order (desc_act) checkpoints: qweight_out[K*b/32, N] = the layer's packed rows re-ordered so that packed row j
- * holds original row perm[j] (exact integer re-layout, bits 2/4/8).  With perm = a stable argsort of g_idx the groups
+ * holds original row perm[j] (exact integer re-layout, any bit width 2..8).  With perm = a stable argsort of g_idx the groups
  * become contiguous, so {qweight_out, the ORIGINAL qzeros and scales, g_idx = NULL, x_perm = perm} is an ordinary
  * grouped layer whose activations are gathered through x_perm: inside the x-load stage of the integer-path decode
  * kernel (M <= 2), by a small gather pass into the workspace ahead of every other kernel (b200q_workspace_bytes accounts

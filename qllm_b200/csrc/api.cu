@@ -524,7 +524,7 @@ int b200q_repack_actorder(const b200q_layer* layer, const int32_t* perm, void* q
   if (v != B200Q_OK) return v;
   if (!perm || !qweight_out) return B200Q_ERR_NULL;
   if (layer->layout != B200Q_LAYOUT_GPTQ && layer->layout != B200Q_LAYOUT_HQQ) return B200Q_ERR_UNSUPPORTED;
-  if (layer->bits != 2 && layer->bits != 4 && layer->bits != 8) return B200Q_ERR_UNSUPPORTED;
+  if (32 % layer->bits != 0 && layer->K % 32 != 0) return B200Q_ERR_SHAPE;      // 3/5/6/7-bit: 32-row packs
   return cuda_status(launch_repack_actorder(make_view(layer), perm, (uint32_t*)qweight_out, (cudaStream_t)stream));
 }
 

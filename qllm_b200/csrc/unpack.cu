@@ -146,7 +146,32 @@ __global__ void __launch_bounds__(256) repack_actorder_kernel(LayerView L, const
   qw_out[idx] = w;
 }
 
+// 3 / 5 / 6 / 7-bit streams: 32 consecutive rows fill exactly `bits` words (compress_weight.py:27-43); one thread re-packs one
+// such block of one column, LSB first.
+__global__ void __launch_bounds__(256) repack_actorder_anybit_kernel(LayerView L, const int* __restrict__ perm, uint32_t* __restrict__ qw_out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)(L.K / 32) * L.N) return;
+  const int kb = (int)(idx / L.N), n = (int)(idx % L.N);
+  const uint32_t mask = (1u << L.bits) - 1u;
+  unsigned long long acc = 0;
+  int have = 0, w = 0;
+  for (int i = 0; i < 32; ++i) {
+    acc |= (unsigned long long)(load_q(L, perm[32 * kb + i], n) & mask) << have;
+    have += L.bits;
+    if (have >= 32) {
+      qw_out[((size_t)kb * L.bits + w) * L.N + n] = (uint32_t)acc;
+      acc >>= 32; have -= 32; ++w;
+    }
+  }
+}
+
 cudaError_t launch_repack_actorder(const LayerView& L, const int* perm, uint32_t* qw_out, cudaStream_t st) {
+  if (32 % L.bits != 0) {
+    const size_t blocks = (size_t)(L.K / 32) * L.N;
+    repack_actorder_anybit_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, st>>>(L, perm, qw_out);
+    count_launch();
+    return cudaGetLastError();
+  }
   const size_t total = (size_t)(L.K * L.bits / 32) * L.N;
   repack_actorder_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, perm, qw_out);
   count_launch();

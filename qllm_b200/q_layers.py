@@ -126,7 +126,7 @@ class _B200QuantLinearBase(nn.Module):
         checkpoints whose groups all own exactly `groupsize` rows -- {row-permuted qweight, original qzeros/scales,
         g_idx = NULL, x_perm = stable argsort(g_idx)}, built once (exact integer re-layout on the GPU)."""
         desc = self._descriptor()
-        if not (ACTORDER_RELAYOUT and self.act_order and self._layout == LAYOUT_GPTQ and self.bits in (2, 4, 8)):
+        if not (ACTORDER_RELAYOUT and self.act_order and self._layout == LAYOUT_GPTQ):
             return desc
         key = self._desc_key
         if getattr(self, "_ao_key", None) != key:

@@ -311,3 +311,18 @@ def test_fused_mlp_helper():
         want = down(torch.nn.functional.silu(gate(x)) * up(x)) + x
         got = qllm_b200.fused_mlp(gate, up, down, x, residual=x)
         assert ((got.float() - want.float()).abs().max() / want.float().abs().max()).item() < 2e-3
+
+
+@pytest.mark.parametrize("bits", [3, 5, 6])
+def test_act_order_relayout_any_bit_width(bits):
+    """desc_act checkpoints at 3 / 5 / 6 bits: the row-permuted re-layout re-packs the 32-row bit-stream blocks exactly."""
+    K, N, gs = 256, 64, 64
+    L = O.make_layer("GPTQ", bits, gs, K, N, seed=bits, act_order=True)
+    layer = layer_from_dict(L)
+    for M in (1, 20):
+        x = np.random.default_rng(M).standard_normal((M, K)).astype(np.float16)
+        y = layer(torch.from_numpy(x).cuda()).float().cpu().numpy()
+        assert rel_err(y, oracle_forward(L, x)) < TOL
+    qw, perm = layer._ao
+    q = O.gptq_unpack_qweight(qw.cpu().numpy(), bits, K)
+    assert np.array_equal(q, L["q"][perm.cpu().numpy()])            # packed row j holds original row perm[j]
