@@ -514,20 +514,32 @@ def prefill_tflops(dev, P, M=512, iters=20):
     copies = 6                                         # 6 blocks x 101 MB of packed weights > L2
     layers = [[rand_layer("GPTQ", BITS, GROUP, K, N, dev, 100 * c + i) for i, (_, K, N) in enumerate(SHAPES)] for c in range(copies)]
     xs = {K: torch.randn(M, K, dtype=torch.float16, device=dev) for K in (HIDDEN, INTER)}
+    group = os.environ.get("B200Q_BENCH_NO_GROUP") is None
+
+    def block(ls):
+        """q|k|v and gate|up share their input: one b200q_linear_group call each (the later siblings' GEMMs are released by a
+        flag instead of the kernel boundary); o and down are single calls.  7 GEMM launches either way."""
+        if not group:
+            for l in ls:
+                l(xs[l.infeatures])
+            return
+        qllm_b200.linear_group(ls[0:3], xs[HIDDEN])
+        ls[3](xs[HIDDEN])
+        qllm_b200.linear_group(ls[4:6], xs[HIDDEN])
+        ls[6](xs[INTER])
+
     for c in range(copies):
-        for l in layers[c]:
-            l(xs[l.infeatures])
+        block(layers[c])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for it in range(iters):
-        for l in layers[it % copies]:
-            l(xs[l.infeatures])
+        block(layers[it % copies])
     e1.record()
     torch.cuda.synchronize()
     flops = iters * sum(2.0 * M * K * N for _, K, N in SHAPES)
     tf = flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
-    return {"workload": "Llama-2-7B block, GPTQ int4 g128, M=512 per call (7 GEMMs)", "tflops": tf,
+    return {"workload": "Llama-2-7B block, GPTQ int4 g128, M=512 per call (7 GEMMs)", "tflops": tf, "sibling_groups": group,
             "frac_of_bf16_peak": tf / P["bf16_tflops"], "peak": P["bf16_tflops"], "kernel": "gemm_tc_gptq4_kernel (tcgen05)"}
 
 
@@ -562,12 +574,19 @@ def run_prefill(args, rank, world, local_rank):
     y_pinned = torch.empty(M, HIDDEN, dtype=torch.float16).pin_memory()
     h.copy_(h0)
 
+    group = os.environ.get("B200Q_BENCH_NO_GROUP") is None
+
     def forward():
         x = h
         for b in blocks:
-            q, k, v = b["q"](x), b["k"](x), b["v"](x)
-            o = b["o"](v)
-            gt, up = b["gate"](o), b["up"](o)
+            if group:          # q|k|v and gate|up share their input: b200q_linear_group (still one GEMM launch per layer)
+                q, k, v = qllm_b200.linear_group([b["q"], b["k"], b["v"]], x)
+                o = b["o"](v)
+                gt, up = qllm_b200.linear_group([b["gate"], b["up"]], o)
+            else:
+                q, k, v = b["q"](x), b["k"](x), b["v"](x)
+                o = b["o"](v)
+                gt, up = b["gate"](o), b["up"](o)
             x = b["down"](gt)
         return x
 
@@ -612,7 +631,7 @@ def run_prefill(args, rank, world, local_rank):
         "config": {"workload": f"Llama-2-7B int4 g128 GPTQ, prefill tile M={M} rows per QuantLinear call: the 224 layers of the model "
                                "(q,k,v -> o -> gate,up -> down), one CUDA graph", "M": M, "layers": BLOCKS * len(SHAPES),
                    "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
-                   "l2_policy": "inputs (3.4 GB packed weights) larger than L2", "cuda_graph": True,
+                   "l2_policy": "inputs (3.4 GB packed weights) larger than L2", "cuda_graph": True, "sibling_groups": group,
                    "outputs_finite": bool(torch.isfinite(out.float()).all().item())},
         "clocks": clk.summary(),
         "e2e": {"value": flops / e2e_s / 1e12 * world, "unit": "TFLOP/s", "h2d_bytes_per_step": M * HIDDEN * 2, "d2h_bytes_per_step": M * HIDDEN * 2},

@@ -106,8 +106,9 @@ int b200q_linear(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx
  *   x_mul    != NULL: the layer's input is  silu(x) * x_mul  (x = gate_proj output, x_mul = up_proj output, both fp16
  *                     [M, ldx]); rounded exactly as the two fp16 ops round (silu to fp16, product to fp16);
  *   residual != NULL: y = fp16(fp16(x @ W + bias) + residual), residual fp16 [M, ldres] -- bit-identical to the separate add.
- * The integer decode kernel folds x_mul into its x-load stage and both decode kernels and the tcgen05 GEMM add the
- * residual in their epilogue; other kernels get a small element-wise pass ahead / behind (same results).
+ * The integer decode kernel folds x_mul into its x-load stage, and it and the tcgen05 GEMM add the residual in their
+ * epilogue (separate template instantiations: the plain paths carry none of it); other kernels get a small element-wise
+ * pass ahead / behind (same results).
  * Workspace: b200q_workspace_bytes_ex().
  */
 typedef struct b200q_fusion {

@@ -99,6 +99,7 @@ enum { KERNEL_GEMV_MMA = 1, KERNEL_GEMM_TC = 2, KERNEL_GENERIC = 3 };
 // out of the dispatch: what remains is the bulk-copy / mbarrier kernel of gemv_mma.cu, which is also the fallback for the
 // group sizes the streaming kernels do not tile (below 32 at 4-bit, 64 at 2-bit, 16 at 8-bit).
 static bool g_use_stream = true;
+static bool g_gemm_siblings = true;    // option "gemm_siblings" = 0: b200q_linear_group at M > 64 is a plain loop of launches
 static int gemv_variant() {
   static int v = -1;
   if (v < 0) {
@@ -228,8 +229,8 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   if (kern == KERNEL_GEMV_MMA) {
     if (g_use_stream && gemv_imma_supported(&a, 1)) return cuda_status(launch_gemv_imma(&a, 1, peers));
     a.x_mul = nullptr;                                      // (never set here: only the integer-path kernel folds it)
-    if (g_use_stream && gemv_stream_supported(&a, 1)) return cuda_status(launch_gemv_stream(&a, 1, peers));
-    a.residual = nullptr;
+    a.residual = nullptr;                                   // ... and only it and the tcgen05 GEMM carry the residual epilogue
+    if (g_use_stream && gemv_stream_supported(&a, 1)) return with_residual(launch_gemv_stream(&a, 1, peers));
     return with_residual(launch_gemv_mma(a, peers));
   }
   if (kern == KERNEL_GEMM_TC) {
@@ -316,6 +317,21 @@ int b200q_linear_group(const b200q_layer* const* layers, int32_t n_layers, const
   }
   if (fused && gemv_imma_supported(a, n_layers)) return cuda_status(launch_gemv_imma(a, n_layers, nullptr));
   if (fused && gemv_stream_supported(a, n_layers)) return cuda_status(launch_gemv_stream(a, n_layers, nullptr));
+  // M > 64 on the tcgen05 GEMM: one launch per sibling, the later ones released by the first sibling's flag instead of by
+  // the kernel boundary (gemm_tcgen05.cu, "sibling release"), so their CTAs overlap the previous sibling's last wave
+  bool sib = g_gemm_siblings && n_layers >= 2 && M > 64 && workspace && workspace_bytes >= kCounterBytes &&
+             !((uintptr_t)workspace & 15) && check_arch() == B200Q_OK;
+  for (int i = 0; sib && i < n_layers; ++i)
+    sib = !a[i].L.x_perm && !a[i].L.g_idx && select(a[i].L, M, (const __half*)x, ldx, 0) == KERNEL_GEMM_TC && workspace_for(a[i].L, M) == 0;
+  if (sib) {
+    for (int i = 0; i < n_layers; ++i) {
+      a[i].M = (int)M;
+      a[i].sib_role = i == 0 ? 1 : 2; a[i].sib_index = i - 1; a[i].sib_count = n_layers - 1;
+      const cudaError_t e = launch_gemm_tc(a[i], nullptr);
+      if (e != cudaSuccess) return cuda_status(e);
+    }
+    return B200Q_OK;
+  }
   for (int i = 0; i < n_layers; ++i) {      // not fusable (shape / layout mix / M): same result, one launch per layer
     const int st = run(layers[i], x, M, ldx, nullptr, y[i], ldy[i], 0, workspace, workspace_bytes, stream, 0);
     if (st != B200Q_OK) return st;
@@ -634,6 +650,9 @@ int b200q_debug_set_option(const char* name, double value) {
   else if (n == "sync_flags") g_sync_flags = (int)value;
   else if (n == "gemm_pdl") gemm_tc_set_pdl((int)value);
   else if (n == "gemm_splitk") gemm_tc_set_splitk((int)value);
+  else if (n == "gemm_siblings") g_gemm_siblings = value != 0;
+  else if (n == "gemm_force_tt") gemm_tc_set_force(0, (int)value);
+  else if (n == "gemm_force_ksplit") gemm_tc_set_force(1, (int)value);
   else if (n == "chain_ctas") decode_chain_set_option(0, (int)value);
   else if (n == "chain_slots") decode_chain_set_option(1, (int)value);
   else if (n == "chain_barrier") decode_chain_set_option(2, (int)value);

@@ -51,6 +51,14 @@ struct TcParams {
   int64_t ldres;
   int kblocks, gshift, group32, nsx, nsw;   // nsx / nsw: X and W ring depths actually used
   int ksplit, kb_per;                       // split-K over gridDim.z (small M): k-blocks per split; partial tiles + last-arriver reduction
+  int csplit, off_part;                     // cluster split-K (M > 64): 2 = the CTA pair (cluster dims 1,1,2) halves K and swaps half-tiles
+                                            // of fp32 partial sums through distributed shared memory; off_part: [TT/2][128] fp32
+  // sibling release (b200q_linear_group, M > 64): q/k/v or gate/up read the same x, so only the first sibling orders itself
+  // behind the stream (griddepcontrol.wait) and then raises dep_flag[2 i] for sibling i; a later sibling's X producer polls
+  // its flag instead, so its CTAs fill the SMs the previous sibling's last wave leaves idle.  dep_flag[1] counts the pollers;
+  // the last one clears the flag (both words are back at zero when the kernel ends: CUDA-graph replays need no reset).
+  unsigned int* dep_flag;
+  int dep_role, dep_n;
   float* partial;                           // [ksplit][M][N] fp32 (workspace, behind the counter region)
   unsigned int* counters;                   // arrival counter per output tile (workspace head, left zeroed)
   int kbc, nchunks, gcap;                   // group tables are staged per chunk of kbc k-blocks (<= gcap groups): long-K / small-group layers
@@ -64,6 +72,24 @@ __device__ __forceinline__ unsigned long long tc_gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));      // SM clock: every stamp comes from CTA (0,0), i.e. one SM
   return t;
+}
+// thread-block cluster pieces of the split-K pair (non-.aligned forms: the role branches reach them warp by warp)
+__device__ __forceinline__ void tc_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t tc_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t tc_mapa(uint32_t local_smem, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tc_st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 // stamps (SM cycles): [kb][0..3] lead warp of the dequant team that owns kb (packed words landed, ALU done, A stage
 // free, TMEM store retired + signalled), [kb][4..7] MMA thread (X landed, A landed, MMAs issued, commits issued)
@@ -217,7 +243,31 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
 
   if (warp == kWXProd) {                   // X producer: the ring only spans TMA latency + MMA lag
     if (lane == 0) {
-      pdl_wait();                          // x may be the previous kernel's output
+      if (p.dep_role == 2) {               // x is not the previous kernel's output: that kernel is a sibling reading the same x
+        unsigned int v;
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        for (;;) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.dep_flag) : "memory");
+          if (v) break;
+          __nanosleep(64);
+          if ((++spins & 1023u) == 0) {     // bounded (2 s): a missing first sibling must not hang the GPU
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) break;
+          }
+        }
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicInc(p.dep_flag + 1, total - 1u) == total - 1u)
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.dep_flag), "r"(0u) : "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");      // the TMA loads below follow the acquire
+      } else {
+        pdl_wait();                        // x may be the previous kernel's output
+        if (p.dep_role == 1 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+          for (int i = 0; i < p.dep_n; ++i)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.dep_flag + 2 * i), "r"(1u) : "memory");
+      }
       int s = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         // X stage s was last read by the MMAs of k-block kb - nsx, whose completion is signalled on that k-block's
@@ -433,9 +483,8 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     const float bias = (p.L.bias && (n0 + n) < p.L.N) ? __half2float(__ldg(p.L.bias + n0 + n)) : 0.f;
     __half* stg = reinterpret_cast<__half*>(xst) + (size_t)eidx * 32 * (kBN + 8);     // [32 tok][128+8 n], X stages are free now
     const int tih = q * 32 + lane;                                                     // thread index within this slot's 4 warps
-#pragma unroll 1
-    for (int c0 = eidx * 32; c0 < TT && ok; c0 += 64 * kDqPar) {
-      uint32_t v[32];
+    // accumulator chunk c0 (32 tokens x this lane's column), both issuers' accumulators summed
+    auto load_acc = [&](int c0, uint32_t (&v)[32]) {
       tc_ld32(tmem + lane_addr + c0, v);
       if (NI == 2 && nkb > 1) {                   // the second issuer's accumulator exists only if it had a k-block
         uint32_t v2[32];
@@ -445,6 +494,36 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
       } else {
         tc_wait_ld();
+      }
+    };
+    // Cluster split-K: the two CTAs of a pair hold partial sums of the same 128 x TT tile over the two halves of K.  Each
+    // finalises one half of the tokens: it sends the other half of its partial tile into the peer's (now idle) stage memory
+    // through distributed shared memory and adds what the peer sent to its own accumulators in the loop below.
+    int c_begin = 0, c_end = TT;
+    const float* part = reinterpret_cast<const float*>(smem + p.off_part);             // [TT/2][128] fp32, written by the peer
+    if (TT >= 128 && p.csplit == 2) {
+      const uint32_t crank = tc_cluster_rank();
+      tc_cluster_sync();                          // both CTAs' MMAs have completed: stage memory is free on either side
+      const uint32_t remote = tc_mapa(smem_u32(part), crank ^ 1u);
+      const int pbase = (int)(crank ^ 1u) * (TT / 2);
+#pragma unroll 1
+      for (int j = eidx; j < TT / 64; j += 2 * kDqPar) {
+        uint32_t v[32];
+        load_acc(pbase + 32 * j, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tc_st_cluster_f32(remote + (uint32_t)(((32 * j + i) * kBN + n) * 4), __uint_as_float(v[i]));
+      }
+      tc_cluster_sync();                          // the peer's half-tile has landed here (release / acquire at cluster scope)
+      c_begin = (int)crank * (TT / 2);
+      c_end = c_begin + TT / 2;
+    }
+#pragma unroll 1
+    for (int c0 = c_begin + eidx * 32; c0 < c_end && ok; c0 += 64 * kDqPar) {
+      uint32_t v[32];
+      load_acc(c0, v);
+      if (TT >= 128 && p.csplit == 2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + part[(c0 - c_begin + i) * kBN + n]);
       }
       if (p.ksplit > 1) {                         // split-K: fp32 partial tile of this split, coalesced along n
         float* slab = p.partial + (size_t)blockIdx.z * (size_t)p.M * p.L.N;
@@ -518,6 +597,10 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     }
     tc_fence_before();
   }
+  if (TT >= 128 && p.csplit == 2 && warp >= kDqWarps * kDqPar) {      // producer / issuer warps: the pair's two barriers count every thread
+    tc_cluster_sync();
+    tc_cluster_sync();
+  }
   __syncthreads();
   if (tid == 0) TC_STAMP(p.kblocks, 4);                                                        // epilogue stored
   if (warp == kWAlloc) {
@@ -590,9 +673,46 @@ static bool cached_tmap_2d(EncodeTiledFn enc, CUtensorMap* out, CUtensorMapDataT
 
 static int g_tc_pdl = 1;                  // B200Q_GEMM_PDL=0 / option "gemm_pdl": plain stream-ordered launches
 void gemm_tc_set_pdl(int on) { g_tc_pdl = on; }
-static int g_tc_tt256_min_m = 1024;
+static int g_tc_splitk = 1;               // B200Q_GEMM_SPLITK=0 / option "gemm_splitk": no K split (workspace form at M <= 64, CTA pairs above)
+static int g_tc_tt256_min_m = 0;           // option "tt256_min_m" / B200Q_TT256_MIN_M: > 0 forces 256-token tiles from that M on
 void gemm_tc_set_tt256_min_m(int m) { g_tc_tt256_min_m = m; }
-static int pick_tt(int64_t M) { return M <= 32 ? 32 : (M <= 64 ? 64 : (M >= g_tc_tt256_min_m ? 256 : 128)); }
+static int g_tc_force_tt = 0, g_tc_force_ks = 0;      // diagnostic: options "gemm_force_tt" / "gemm_force_ksplit" (0 = automatic)
+void gemm_tc_set_force(int which, int v) { (which == 0 ? g_tc_force_tt : g_tc_force_ks) = v; }
+
+// Tile choice for M > 64: token-tile width TT (each packed weight is dequantised once per token tile, so 256 halves the
+// dequant work that bounds the 128-wide tile) and cs = 2 to halve K across a CTA pair when the grid would leave SMs idle.
+// Modelled time = waves x (k-blocks per CTA x time per k-block + fixed); the constants are fitted to the B200 measurements
+// of tools/sweep_gemm_tiles.py (profiles/r2_sweep_gemm_tiles.txt): 0.27 us per k-block at TT = 128 (dequant issue-bound),
+// 0.37 us at TT = 256 with the chip full (tensor pipe at power-capped clocks; 0.31 us when at most half the SMs run),
+// 5 us fixed per launch (prologue + epilogue as they overlap in a chain), 3.3 us more for the pair's exchange.
+struct TcTile { int tt, cs; };
+static TcTile tc_pick(const LayerView& L, int64_t M) {
+  TcTile best = {M <= 32 ? 32 : (M <= 64 ? 64 : 128), 1};
+  if (g_tc_force_tt == 32 || g_tc_force_tt == 64 || g_tc_force_tt == 128 || g_tc_force_tt == 256) best.tt = g_tc_force_tt;
+  const int kblocks = L.K / kBK;
+  const int64_t tiles = (L.N + kBN - 1) / kBN;
+  if (M <= 64) return best;
+  if (g_tc_force_tt || g_tc_force_ks) {
+    if (!g_tc_force_tt) best.tt = (g_tc_tt256_min_m > 0 && M >= g_tc_tt256_min_m) ? 256 : 128;
+    best.cs = (g_tc_force_ks == 2 && best.tt >= 128 && kblocks >= 16) ? 2 : 1;
+    return best;
+  }
+  double best_t = 1e30;
+  for (int tt = 128; tt <= 256; tt *= 2) {
+    if (g_tc_tt256_min_m > 0 && (tt == 256) != (M >= g_tc_tt256_min_m)) continue;
+    for (int cs = 1; cs <= 2; ++cs) {
+      if (cs == 2 && (!g_tc_splitk || kblocks < 16)) continue;
+      const int64_t ctas = tiles * ((M + tt - 1) / tt) * cs;
+      const int slots = cs == 2 ? 144 : 148;                        // CTA pairs may not cover every GPC's last SM
+      const double waves = (double)((ctas + slots - 1) / slots);
+      const double per_kb = tt == 128 ? 0.27 : (ctas <= 74 ? 0.31 : 0.37);
+      const double t = waves * ((double)((kblocks + cs - 1) / cs) * per_kb + 5.0 + (cs == 2 ? 3.3 : 0.0));
+      if (t < best_t * 0.97) { best_t = t; best.tt = tt; best.cs = cs; }   // ties go to the simpler configuration (tried first)
+    }
+  }
+  return best;
+}
+static int pick_tt(const LayerView& L, int64_t M) { return tc_pick(L, M).tt; }
 
 bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t ldx) {
   if (!(L.layout == B200Q_LAYOUT_GPTQ || L.layout == B200Q_LAYOUT_HQQ) || L.g_idx || L.x_perm) return false;
@@ -605,11 +725,10 @@ bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t l
 
 // Split-K for small M (one token tile): a 128-column CTA is bound by its own dequant rate (~8192 weights per ~400
 // cycles), so N / 128 CTAs leave most SMs idle; splitting K fills them (K = 14336, N = 4096, M = 16: 67 -> ~17 us).
-static int g_tc_splitk = 1;               // B200Q_GEMM_SPLITK=0 / option "gemm_splitk"
 void gemm_tc_set_splitk(int on) { g_tc_splitk = on; }
 static int tc_ksplit(const LayerView& L, int64_t M) {
-  if (!g_tc_splitk || M > 64) return 1;
   const int tiles = (L.N + kBN - 1) / kBN, kblocks = L.K / kBK;
+  if (!g_tc_splitk || M > 64) return 1;
   int ks = 148 / tiles;
   if (ks > 8) ks = 8;
   if (ks > kblocks / 8) ks = kblocks / 8;
@@ -642,12 +761,20 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   if (a.residual && (((uintptr_t)a.residual & 15) != 0 || (a.ldres % 8) != 0)) return cudaErrorInvalidValue;
   p.kblocks = L.K / kBK;
   p.ksplit = tc_ksplit(L, a.M);
-  p.kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;
+  p.csplit = (TT >= 128 && !peers) ? tc_pick(L, a.M).cs : 1;
+  p.kb_per = (p.kblocks + p.ksplit * p.csplit - 1) / (p.ksplit * p.csplit);
   p.partial = nullptr; p.counters = nullptr;
   if (p.ksplit > 1) {
     if (!a.workspace || a.workspace_bytes < gemm_tc_workspace(L, a.M)) return cudaErrorInvalidValue;
     p.counters = reinterpret_cast<unsigned int*>(a.workspace);
     p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + kCounterBytes);
+  }
+  p.dep_role = 0; p.dep_n = 0; p.dep_flag = nullptr;
+  if (a.sib_role && p.ksplit == 1 && a.workspace && a.workspace_bytes >= kCounterBytes && a.sib_count >= 1 && a.sib_count <= 2) {
+    p.dep_role = a.sib_role; p.dep_n = a.sib_count;
+    p.dep_flag = reinterpret_cast<unsigned int*>(a.workspace) + 1008 + (a.sib_role == 2 ? 2 * a.sib_index : 0);
+  } else if (a.sib_role) {
+    return cudaErrorInvalidValue;          // the caller checked all of this: a half-armed sibling chain must not launch
   }
   p.gshift = -1;
   p.group32 = (L.group % 32 == 0) ? 1 : 0;
@@ -682,6 +809,10 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   p.off_zq = off; off += p.gcap * zq_row;
   off = (off + 15) & ~15;
   p.off_bar = off; off += 1024;
+  // cluster split-K: the received half-tile of partial sums sits behind the epilogue's six transpose slots, inside the (by
+  // then idle) X / W stage memory
+  p.off_part = p.off_x + ((2 * kDqPar * 32 * (kBN + 8) * 2 + 1023) & ~1023);
+  if (p.csplit == 2 && p.off_part + (TT / 2) * kBN * 4 > p.off_sc) { p.csplit = 1; p.kb_per = p.kblocks; }
   const int smem_bytes = off + 1024;   // slack for 1024-byte alignment of the dynamic window
   static bool attr_done[64] = {};
   int dev = 0;
@@ -694,18 +825,20 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   for (int i = 0; i < p.out.n; ++i)
     if (((uintptr_t)p.out.y[i] & 15) != 0) return cudaErrorInvalidValue;
   if ((a.ldy % 8) != 0 || (a.n_offset % 8) != 0) return cudaErrorInvalidValue;     // 16-byte epilogue stores
-  dim3 grid((L.N + kBN - 1) / kBN, (a.M + TT - 1) / TT, p.ksplit);
+  dim3 grid((L.N + kBN - 1) / kBN, (a.M + TT - 1) / TT, p.ksplit * p.csplit);
   count_launch();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = a.stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = g_tc_pdl ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = 1; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 2;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = p.csplit == 2 ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, gemm_tc_gptq_kernel<TT, BITS, FZ, DBG>, xmap, wmap, p);
 }
 
@@ -713,9 +846,9 @@ cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers) {
   // M is chunked so that a.M fits int and grid.y <= 65535
   const bool fz = a.L.layout == B200Q_LAYOUT_HQQ;
   // diagnostic timeline build: only the TT=128 4-bit integer-zero instantiation carries the stamps
-  if (g_tc_dbg && !fz && a.L.bits == 4 && pick_tt(a.M) == 128) return tc_launch<128, 4, false, true>(a, peers);
+  if (g_tc_dbg && !fz && a.L.bits == 4 && pick_tt(a.L, a.M) == 128) return tc_launch<128, 4, false, true>(a, peers);
 #define B200Q_TC_DISPATCH(BITS)                                  \
-  switch (pick_tt(a.M)) {                                       \
+  switch (pick_tt(a.L, a.M)) {                                       \
     case 32: return (fz ? tc_launch<32, BITS, true>(a, peers) : tc_launch<32, BITS, false>(a, peers));              \
     case 64: return (fz ? tc_launch<64, BITS, true>(a, peers) : tc_launch<64, BITS, false>(a, peers));              \
     case 256: return (fz ? tc_launch<256, BITS, true>(a, peers) : tc_launch<256, BITS, false>(a, peers));            \

@@ -595,10 +595,9 @@ cudaError_t launch_gemv_stream(const LinearArgs* a, int n, const PeerOut* peers)
     d.cta0 = i < n ? pl.cta0[i] : (1 << 30);
     if (peers && n == 1) d.out = *peers; else { d.out.n = 1; d.out.y[0] = a[k].y; }
     d.ldy = a[k].ldy; d.n_offset = a[k].n_offset;
-    d.residual = a[k].residual; d.ldres = a[k].ldres;
   }
   p.layout = L.layout; p.bits = L.bits; p.group = L.group; p.K = L.K; p.G = L.G; p.zero_bias = L.zero_bias;
-  p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M; p.xmul = nullptr;
+  p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M;
   p.cluster = pl.cluster; p.tpc = pl.tpc; p.depth = pl.depth; p.steps_total = pl.steps_total; p.group_shift = pl.group_shift;
   p.split_q = pl.steps_total / (pl.cluster * kWarps); p.split_r = pl.steps_total % (pl.cluster * kWarps);
   p.gcap = pl.gcap; p.x_stride = pl.x_stride; p.red_stride = pl.tpc * pl.NT * a[0].M;

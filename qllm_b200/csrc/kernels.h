@@ -27,6 +27,10 @@ struct LinearArgs {
   const __half* x_mul;       // the layer's input is fp16(fp16(silu(x)) * x_mul), same strides as x (LlamaMLP.down_proj(act(gate) * up))
   const __half* residual;    // y = fp16(fp16(x @ W + bias) + residual): the decoder block's skip connection
   int64_t ldres;
+  // sibling GEMMs of one b200q_linear_group call at M > 64 (same x, launched back to back): 1 = first sibling, raises the
+  // later ones' flags once its own stream dependency is met; 2 = later sibling number sib_index (0-based), whose
+  // activation loads wait for that flag instead of for the kernel in front of it
+  int sib_role, sib_index, sib_count;
 };
 
 static constexpr int kMaxPeers = 8;
@@ -105,6 +109,7 @@ bool gemm_tc_supported(const LayerView& L, int64_t M, const __half* x, int64_t l
 size_t gemm_tc_workspace(const LayerView& L, int64_t M);
 cudaError_t launch_gemm_tc(const LinearArgs& a, const PeerOut* peers);
 void gemm_tc_set_tt256_min_m(int m);
+void gemm_tc_set_force(int which, int v);   // diagnostic: 0 = token-tile width, 1 = K splits
 void gemm_tc_set_pdl(int on);
 void gemm_tc_set_splitk(int on);
 void gemm_tc_set_debug(unsigned long long* buf);

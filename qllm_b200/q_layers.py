@@ -629,26 +629,34 @@ class QuantLinearMarlin(_B200QuantLinearBase):
         return w.t().contiguous().cpu(), s.cpu(), torch.full_like(s, 8, dtype=torch.int32).cpu()
 
 
+GROUP_GEMM_MIN_M = 64      # above this the library runs sibling GEMMs with the flag release (below: plain per-layer calls)
+
+
 def linear_group(layers, x):
     """[layer(x) for layer in layers] for sibling QuantLinears that share their input (q/k/v, gate/up), as one
     launch of b200q_linear_group at decode sizes (identical results; falls back per layer inside the library)."""
     K = layers[0].infeatures
     x2 = x.reshape(-1, x.shape[-1])
-    descs = [l._decode_descriptor(x2.shape[0]) for l in layers]
+    M = x2.shape[0]
+    if M == 0 or any(l.infeatures != K for l in layers) or (lib.b200q_gemv_max_m() < M <= GROUP_GEMM_MIN_M):
+        return [_B200QuantLinearBase.forward(l, x) for l in layers]      # not l(x): that would re-enter the sibling group
+    if M > lib.b200q_gemv_max_m():
+        # prefill sizes: one tcgen05 GEMM per sibling, the later ones released by a flag instead of the kernel boundary
+        descs = [l._decode_descriptor(8) if l._layout in _RELAYOUT else l._fast_descriptor() for l in layers]
+        descs = [l._gemm_descriptor() if lib.b200q_select_kernel(ctypes.byref(d), M) != 2 else d for l, d in zip(layers, descs)]
+    else:
+        descs = [l._decode_descriptor(M) for l in layers]
     if x2.dtype != torch.float16:
         x2 = x2.to(torch.float16)
     if x2.stride(-1) != 1:
         x2 = x2.contiguous()
-    M = x2.shape[0]
-    if M == 0 or M > lib.b200q_gemv_max_m() or any(l.infeatures != K for l in layers):
-        return [_B200QuantLinearBase.forward(l, x) for l in layers]      # not l(x): that would re-enter the sibling group
     n = len(layers)
     ys = [torch.empty((M, l.outfeatures), dtype=torch.float16, device=x.device) for l in layers]
     LP = ctypes.POINTER(Layer)
     arr = (LP * n)(*[ctypes.pointer(d) for d in descs])
     yp = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
     ld = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
-    need = max(lib.b200q_workspace_bytes(ctypes.byref(d), M) for d in descs)
+    need = max(4096, max(lib.b200q_workspace_bytes(ctypes.byref(d), M) for d in descs))
     ws = _workspace(x.device, need)
     check(lib.b200q_linear_group(arr, n, x2.data_ptr(), M, x2.stride(0), yp, ld, ws.data_ptr(), ws.numel(),
                                  torch.cuda.current_stream(x.device).cuda_stream), "b200q_linear_group")
@@ -683,7 +691,7 @@ class _SiblingGroup:
         if self.key == key and id(layer) in self.parked:
             return self.parked.pop(id(layer))
         rows = x.reshape(-1, x.shape[-1]).shape[0]
-        if layer is not self.layers[0] or rows == 0 or rows > lib.b200q_gemv_max_m() or not x.is_cuda:
+        if layer is not self.layers[0] or rows == 0 or lib.b200q_gemv_max_m() < rows <= GROUP_GEMM_MIN_M or not x.is_cuda:
             return _B200QuantLinearBase.forward(layer, x)
         outs = linear_group(self.layers, x)
         self.key = key

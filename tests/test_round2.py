@@ -326,3 +326,84 @@ def test_act_order_relayout_any_bit_width(bits):
     qw, perm = layer._ao
     q = O.gptq_unpack_qweight(qw.cpu().numpy(), bits, K)
     assert np.array_equal(q, L["q"][perm.cpu().numpy()])            # packed row j holds original row perm[j]
+
+
+# ---- sibling GEMMs at prefill sizes: b200q_linear_group with the flag release (gemm_tcgen05.cu) -------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [65, 200, 512])
+def test_sibling_group_prefill_matches_single_calls(M):
+    """q|k|v through one b200q_linear_group call at M > 64 == three b200q_linear calls, bit for bit; the flag / counter
+    words in the workspace are back at zero afterwards, also after CUDA-graph replays."""
+    import qllm_b200
+    from qllm_b200 import q_layers
+    K = 2048
+    layers = [layer_from_dict(O.make_layer("GPTQ", 4, 128, K, N, seed=N)) for N in (1024, 512, 1536)]
+    x = torch.randn(M, K, dtype=torch.float16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(M))
+    single = [q_layers._B200QuantLinearBase.forward(l, x) for l in layers]
+    torch.cuda.synchronize()
+    for _ in range(3):
+        outs = qllm_b200.linear_group(layers, x)
+        torch.cuda.synchronize()
+        for a, b in zip(outs, single):
+            assert torch.equal(a, b)
+    ws = q_layers._workspace(x.device, 4096)
+    assert int(ws[:4096].view(torch.int32).abs().sum().item()) == 0
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        qllm_b200.linear_group(layers, x)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            outs = qllm_b200.linear_group(layers, x)
+        for _ in range(4):
+            for o in outs:
+                o.zero_()
+            g.replay()
+            s.synchronize()
+            for a, b in zip(outs, single):
+                assert torch.equal(a, b)
+        wsg = q_layers._workspace(x.device, 4096)
+        assert int(wsg[:4096].view(torch.int32).abs().sum().item()) == 0
+
+
+@pytest.mark.gpu
+def test_sibling_group_prefill_switch_off():
+    import qllm_b200
+    from qllm_b200 import q_layers
+    K, M = 1024, 300
+    layers = [layer_from_dict(O.make_layer("GPTQ", 4, 128, K, N, seed=N + 1)) for N in (512, 768)]
+    x = torch.randn(M, K, dtype=torch.float16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    on = qllm_b200.linear_group(layers, x)
+    qllm_b200.check(qllm_b200.lib.b200q_debug_set_option(b"gemm_siblings", 0.0))
+    try:
+        off = qllm_b200.linear_group(layers, x)
+    finally:
+        qllm_b200.check(qllm_b200.lib.b200q_debug_set_option(b"gemm_siblings", 1.0))
+    torch.cuda.synchronize()
+    for a, b in zip(on, off):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,N,M", [(4096, 4096, 512), (11008, 4096, 300), (4096, 4096, 129)])
+def test_gemm_cluster_split_k_matches_unsplit(K, N, M):
+    """The CTA-pair split of K (halves exchanged through distributed shared memory) against the unsplit kernel and the
+    float64 arbiter; the pair sums its two fp32 halves in a fixed order, so repeated calls are bit-identical."""
+    import qllm_b200
+    layer = layer_from_dict(O.make_layer("GPTQ", 4, 128, K, N, seed=K + N + M))
+    x = torch.randn(M, K, dtype=torch.float16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    opt = lambda k, v: qllm_b200.check(qllm_b200.lib.b200q_debug_set_option(k, float(v)))
+    try:
+        opt(b"gemm_force_tt", 128); opt(b"gemm_force_ksplit", 1)
+        base = layer(x).clone()
+        outs = {}
+        for tt in (128, 256):
+            opt(b"gemm_force_tt", tt); opt(b"gemm_force_ksplit", 2)
+            outs[tt] = layer(x).clone()
+            assert torch.equal(outs[tt], layer(x))
+    finally:
+        opt(b"gemm_force_tt", 0); opt(b"gemm_force_ksplit", 0)
+    torch.cuda.synchronize()
+    ref = x.double() @ layer.dequantize().double()
+    for y in (base, outs[128], outs[256]):
+        assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < 1e-3

@@ -24,7 +24,9 @@ W = O.dequant(L["q"], L["z"], L["s"], L["g_idx"], "engine")
 ref = A.double().cpu().numpy() @ W.astype(np.float64)
 print("ok rel_err", float(np.abs(C.double().cpu().numpy() - ref).max() / np.abs(ref).max()))
 '''
-for (M, K, N, gs) in ((1, 512, 256, 128), (16, 512, 256, 128), (200, 1024, 512, 128), (1, 256, 256, -1)):
+for (M, K, N, gs) in ((1, 512, 256, 128), (16, 512, 256, 128), (200, 1024, 512, 128), (1, 256, 256, -1), (1, 1024, 512, 128),
+                      (16, 1024, 512, 128), (1, 4096, 4096, 128), (16, 4096, 4096, 128), (512, 4096, 4096, 128), (64, 2048, 1024, -1)):
     r = subprocess.run([sys.executable, "-c", CHILD % (ROOT, ROOT, M, K, N, gs)], capture_output=True, text=True, timeout=300)
-    tail = (r.stdout.strip().splitlines() or [""])[-1] + " | " + (r.stderr.strip().splitlines() or [""])[-1][:300]
+    err = [l for l in r.stderr.strip().splitlines() if "Error" in l or "error" in l]
+    tail = (r.stdout.strip().splitlines() or [""])[-1] + " | " + (err[-1][:200] if err else "")
     print(f"M={M} K={K} N={N} group={gs}: rc={r.returncode} {tail}", flush=True)

@@ -1,0 +1,76 @@
+// Does the size of a kernel's parameter block cost device time per launch?  (round 2: the decode kernel's StParams grew
+// from 1560 to 1616 bytes and an A/B on one box showed ~0.18 us per launch with identical SASS otherwise.)
+// A CUDA graph of 128 back-to-back launches (programmatic stream serialization like the decode path, 444 CTAs x 256
+// threads, 72 KB dynamic shared memory) of a kernel that reads a few words of a W-byte __grid_constant__ block.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 param_size_probe.cu -o param_size_probe
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+
+template <int W>
+struct Blk { int v[W / 4]; };
+
+template <int W>
+__global__ void __launch_bounds__(256, 3) probe_kernel(const __grid_constant__ Blk<W> p, int* out) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  extern __shared__ int sm[];
+  const int i = (threadIdx.x * 7 + blockIdx.x) % (W / 4);
+  sm[threadIdx.x] = p.v[i];
+  __syncthreads();
+  if (sm[(threadIdx.x + 1) & 255] == 0x7fffffff) out[0] = 1;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <int W>
+static void run(int* out, bool pdl) {
+  Blk<W> b;
+  for (int i = 0; i < W / 4; ++i) b.v[i] = i;
+  CK(cudaFuncSetAttribute(probe_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+  cudaStream_t st;
+  CK(cudaStreamCreate(&st));
+  cudaGraph_t g;
+  cudaGraphExec_t ge;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  for (int l = 0; l < 128; ++l) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(444); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 72 * 1024; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, probe_kernel<W>, b, out));
+  }
+  CK(cudaStreamEndCapture(st, &g));
+  CK(cudaGraphInstantiate(&ge, g, 0));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 20; ++i) CK(cudaGraphLaunch(ge, st));
+  CK(cudaStreamSynchronize(st));
+  float best = 1e9f, sum = 0;
+  const int reps = 10;
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(e0, st));
+    for (int i = 0; i < 20; ++i) CK(cudaGraphLaunch(ge, st));
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= 20 * 128;
+    best = ms < best ? ms : best; sum += ms;
+  }
+  printf("param_bytes %5d  pdl %d  us_per_launch  best %.3f  mean %.3f\n", W + 8, (int)pdl, best * 1e3, sum / reps * 1e3);
+  CK(cudaGraphExecDestroy(ge)); CK(cudaGraphDestroy(g)); CK(cudaStreamDestroy(st));
+}
+
+int main() {
+  int* out;
+  CK(cudaMalloc(&out, 4));
+  for (int pdl = 1; pdl >= 0; --pdl) {
+    run<64>(out, pdl); run<96>(out, pdl); run<128>(out, pdl); run<160>(out, pdl); run<192>(out, pdl); run<224>(out, pdl); run<256>(out, pdl);
+    run<320>(out, pdl); run<384>(out, pdl); run<512>(out, pdl); run<704>(out, pdl); run<1024>(out, pdl); run<1536>(out, pdl); run<1552>(out, pdl);
+    run<1608>(out, pdl); run<2048>(out, pdl); run<3072>(out, pdl); run<4000>(out, pdl);
+  }
+  return 0;
+}
