@@ -506,7 +506,7 @@ def run_b200q(args, rank, world, local_rank):
     print(json.dumps(result), flush=True)
 
 
-def prefill_tflops(dev, P, M=512, iters=20):
+def prefill_tflops(dev, P, M=512, iters=8):
     """configs[2]: GPTQ layout, M=512 rows per call, the 7 shapes of one decoder block (tcgen05 GEMM)."""
     import torch
     import qllm_b200
@@ -528,16 +528,26 @@ def prefill_tflops(dev, P, M=512, iters=20):
         qllm_b200.linear_group(ls[4:6], xs[HIDDEN])
         ls[6](xs[INTER])
 
-    for c in range(copies):
-        block(layers[c])
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for it in range(iters):
-        block(layers[it % copies])
-    e1.record()
-    torch.cuda.synchronize()
-    flops = iters * sum(2.0 * M * K * N for _, K, N in SHAPES)
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for c in range(copies):
+            block(layers[c])
+        s.synchronize()
+        graph = torch.cuda.CUDAGraph()               # the six blocks as one graph (programmatic-launch edges), like the decode step
+        with torch.cuda.graph(graph, stream=s):
+            for c in range(copies):
+                block(layers[c])
+        for _ in range(3):
+            graph.replay()
+        s.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(iters):
+            graph.replay()
+        e1.record()
+        s.synchronize()
+    flops = iters * copies * sum(2.0 * M * K * N for _, K, N in SHAPES)
     tf = flops / (e0.elapsed_time(e1) * 1e-3) / 1e12
     return {"workload": "Llama-2-7B block, GPTQ int4 g128, M=512 per call (7 GEMMs)", "tflops": tf, "sibling_groups": group,
             "frac_of_bf16_peak": tf / P["bf16_tflops"], "peak": P["bf16_tflops"], "kernel": "gemm_tc_gptq4_kernel (tcgen05)"}

@@ -704,6 +704,9 @@ static TcTile tc_pick(const LayerView& L, int64_t M) {
       if (cs == 2 && (!g_tc_splitk || kblocks < 16)) continue;
       const int64_t ctas = tiles * ((M + tt - 1) / tt) * cs;
       const int slots = cs == 2 ? 144 : 148;                        // CTA pairs may not cover every GPC's last SM
+      // (whole waves also for the siblings of a b200q_linear_group call: choosing by SM time there, on the idea that the
+      // neighbours fill every partial wave, measured 894 against 958 TFLOP/s on the 7B block -- a dependent launch only
+      // starts once the previous grid's last wave is running)
       const double waves = (double)((ctas + slots - 1) / slots);
       const double per_kb = tt == 128 ? 0.27 : (ctas <= 74 ? 0.31 : 0.37);
       const double t = waves * ((double)((kblocks + cs - 1) / cs) * per_kb + 5.0 + (cs == 2 ? 3.3 : 0.0));

@@ -332,7 +332,8 @@ def test_act_order_relayout_any_bit_width(bits):
 @pytest.mark.gpu
 @pytest.mark.parametrize("M", [65, 200, 512])
 def test_sibling_group_prefill_matches_single_calls(M):
-    """q|k|v through one b200q_linear_group call at M > 64 == three b200q_linear calls, bit for bit; the flag / counter
+    """q|k|v through one b200q_linear_group call at M > 64 against three b200q_linear calls (same kernel; a sibling may get
+    another tile shape, i.e. another fp32 summation order: 1e-3) and bit-identical from call to call; the flag / counter
     words in the workspace are back at zero afterwards, also after CUDA-graph replays."""
     import qllm_b200
     from qllm_b200 import q_layers
@@ -341,11 +342,16 @@ def test_sibling_group_prefill_matches_single_calls(M):
     x = torch.randn(M, K, dtype=torch.float16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(M))
     single = [q_layers._B200QuantLinearBase.forward(l, x) for l in layers]
     torch.cuda.synchronize()
+    first = None
     for _ in range(3):
         outs = qllm_b200.linear_group(layers, x)
         torch.cuda.synchronize()
-        for a, b in zip(outs, single):
-            assert torch.equal(a, b)
+        if first is None:
+            first = [o.clone() for o in outs]
+        for a, b, c in zip(outs, single, first):
+            assert torch.equal(a, c)
+            assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) < 1e-3
+    single = first
     ws = q_layers._workspace(x.device, 4096)
     assert int(ws[:4096].view(torch.int32).abs().sum().item()) == 0
     s = torch.cuda.Stream()
@@ -381,7 +387,7 @@ def test_sibling_group_prefill_switch_off():
         qllm_b200.check(qllm_b200.lib.b200q_debug_set_option(b"gemm_siblings", 1.0))
     torch.cuda.synchronize()
     for a, b in zip(on, off):
-        assert torch.equal(a, b)
+        assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) < 1e-3
 
 
 @pytest.mark.gpu
