@@ -581,16 +581,30 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         // always valid (row 0 of the scales when there is no bias) and select afterwards
         const bool has_bias = p.L.bias != nullptr;
         const __half* bsrc = has_bias ? p.L.bias : p.L.s;
-        for (int idx = tid; idx < rows * kBN; idx += kDqT) {
-          const int tok = tok0 + idx / kBN, nn = n0 + idx % kBN;
-          if (nn < p.L.N) {
-            float acc = 0.f;
-            for (int z = 0; z < p.ksplit; ++z) acc += __ldcg(p.partial + ((size_t)z * p.M + tok) * p.L.N + nn);
-            const float bv = __half2float(bsrc[nn]);
-            if (has_bias) acc += bv;
-            __half h = __float2half_rn(acc);
-            if (p.residual) h = __float2half_rn(__half2float(h) + __half2float(p.residual[(size_t)tok * p.ldres + nn]));
-            for (int qd = 0; qd < p.out.n; ++qd) p.out.y[qd][(size_t)tok * p.ldy + p.n_offset + nn] = h;
+        // four columns per thread, every split's 16-byte load in flight before the first add (the slabs come from L2; a
+        // dependent scalar loop here cost more than the main loop at small M); summed in split order -> deterministic
+        for (int idx = tid; idx < rows * (kBN / 4); idx += kDqT) {
+          const int tok = tok0 + idx / (kBN / 4), nn = n0 + 4 * (idx % (kBN / 4));
+          if (nn < p.L.N) {                       // N % 8 == 0: the four columns are in range together
+            float4 v[8];
+#pragma unroll
+            for (int z = 0; z < 8; ++z)
+              if (z < p.ksplit) v[z] = __ldcg(reinterpret_cast<const float4*>(p.partial + ((size_t)z * p.M + tok) * p.L.N + nn));
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int z = 0; z < 8; ++z)
+              if (z < p.ksplit) { acc[0] += v[z].x; acc[1] += v[z].y; acc[2] += v[z].z; acc[3] += v[z].w; }
+            __half h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float bv = __half2float(bsrc[nn + e]);
+              h[e] = __float2half_rn(has_bias ? acc[e] + bv : acc[e]);
+              if (p.residual) h[e] = __float2half_rn(__half2float(h[e]) + __half2float(p.residual[(size_t)tok * p.ldres + nn + e]));
+            }
+            const uint2 pk = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
+                                        (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
+            for (int qd = 0; qd < p.out.n; ++qd)
+              *reinterpret_cast<uint2*>(p.out.y[qd] + (size_t)tok * p.ldy + p.n_offset + nn) = pk;
           }
         }
       }
