@@ -16,7 +16,7 @@ template <int W>
 __global__ void __launch_bounds__(256, 3) probe_kernel(const __grid_constant__ Blk<W> p, int* out) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   extern __shared__ int sm[];
-  const int i = (threadIdx.x * 7 + blockIdx.x) % (W / 4);
+  const int i = (blockIdx.x * 7 + (threadIdx.x >> 5)) % (W / 4);      // warp-uniform: one constant-bank access per warp
   sm[threadIdx.x] = p.v[i];
   __syncthreads();
   if (sm[(threadIdx.x + 1) & 255] == 0x7fffffff) out[0] = 1;
