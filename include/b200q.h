@@ -135,7 +135,12 @@ int b200q_gemm(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
  * (quant_linear_awq.py:142-148 et al., called from the HF attention / MLP modules); at decode sizes each
  * call is launch- and latency-bound, so the host shim (qllm_b200.fuse_siblings) routes them here.  All
  * layers must agree on (layout, bits, group_size, K, zero_bias); otherwise, or for M above
- * b200q_gemv_max_m(), the call degrades to one b200q_linear per layer with identical results.
+ * b200q_gemv_max_m(), the call is one kernel per layer with the results of b200q_linear.
+ * M > 64 with every layer on the tcgen05 GEMM (no g_idx / x_perm) and a workspace of at least 4096 bytes: the GEMMs are
+ * launched back to back and only the first orders itself behind the stream; the later siblings' activation loads wait for a
+ * flag the first one raises (they read the same x), so their CTAs run beside the previous sibling's last wave instead of
+ * waiting for it to end.  The flag and its counter live in workspace words 1008..1013 and are zero again when the call's
+ * kernels have finished (CUDA-graph replays need no reset).  Option "gemm_siblings" = 0 turns this off.
  */
 int b200q_linear_group(const b200q_layer* const* layers, int32_t n_layers, const void* x, int64_t M, int64_t ldx,
                        void* const* y, const int64_t* ldy, void* workspace, size_t workspace_bytes,
