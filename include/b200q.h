@@ -109,12 +109,21 @@ int b200q_linear(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx
  * The integer decode kernel folds x_mul into its x-load stage, and it and the tcgen05 GEMM add the residual in their
  * epilogue (separate template instantiations: the plain paths carry none of it); other kernels get a small element-wise
  * pass ahead / behind (same results).
+ *   act_dtype = B200Q_ACT_BF16: x, x_mul, residual and y are bfloat16 (same strides, in elements).  The arithmetic is the
+ *                     reference's for a bf16 model: the input is rounded to fp16 (auto_cast, quant_linear_awq.py:29-36), the
+ *                     Linear runs in fp16, the result is rounded to bf16 (out.to(x.dtype), :146); the fused neighbours round
+ *                     as the model's bf16 torch ops do (silu to bf16, product to bf16, residual sum to bf16).  The integer
+ *                     decode kernel reads and writes bf16 directly; the other kernels get a conversion pass through the
+ *                     workspace.  No cast kernels on the host side.
  * Workspace: b200q_workspace_bytes_ex().
  */
+enum b200q_act_dtype { B200Q_ACT_F16 = 0, B200Q_ACT_BF16 = 1 };
 typedef struct b200q_fusion {
   const void* x_mul;
   const void* residual;
   int64_t ldres;
+  int32_t act_dtype; /* b200q_act_dtype of x, x_mul, residual and y (bf16 callers without a cast on the host side) */
+  int32_t reserved;  /* 0 */
 } b200q_fusion;
 int b200q_linear_ex(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy, const b200q_fusion* fusion,
                     void* workspace, size_t workspace_bytes, b200q_stream_t stream);

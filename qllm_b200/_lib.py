@@ -27,7 +27,8 @@ class ChainStep(ctypes.Structure):
 
 class Fusion(ctypes.Structure):
     """struct b200q_fusion"""
-    _fields_ = [("x_mul", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("ldres", ctypes.c_int64)]
+    _fields_ = [("x_mul", ctypes.c_void_p), ("residual", ctypes.c_void_p), ("ldres", ctypes.c_int64),
+                ("act_dtype", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class PeerSync(ctypes.Structure):

@@ -168,8 +168,14 @@ static size_t gather_bytes(const LayerView& V, int64_t M) {
   return V.x_perm ? (((size_t)M * (size_t)V.K * 2 + 255) & ~(size_t)255) : 0;
 }
 
+static bool act_bf16(const b200q_fusion* fu) { return fu && fu->act_dtype == B200Q_ACT_BF16; }
+// scratch behind the kernel's own workspace: a fused / converted fp16 copy of x, and (bf16 callers of a kernel without
+// native bf16 I/O) the fp16 result ahead of its conversion
 static size_t silu_bytes(const LayerView& V, int64_t M, const b200q_fusion* fu) {
-  return (fu && fu->x_mul) ? (((size_t)M * (size_t)V.K * 2 + 255) & ~(size_t)255) : 0;
+  return (fu && (fu->x_mul || act_bf16(fu))) ? (((size_t)M * (size_t)V.K * 2 + 255) & ~(size_t)255) : 0;
+}
+static size_t y16_bytes(const LayerView& V, int64_t M, const b200q_fusion* fu) {
+  return act_bf16(fu) ? (((size_t)M * (size_t)V.N * 2 + 255) & ~(size_t)255) : 0;
 }
 
 static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, const PeerOut* peers, void* y,
@@ -183,14 +189,38 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   if (M < 1 || ldx < layer->K || ldy < n_offset + layer->N) return B200Q_ERR_SHAPE;
   gemv_variant();                          // one-time parse of the B200Q_* switches
   LayerView V = make_view(layer);
-  const size_t base = workspace_for(V, M), need = base + gather_bytes(V, M) + silu_bytes(V, M, fu);
+  const size_t base = workspace_for(V, M), need = base + gather_bytes(V, M) + silu_bytes(V, M, fu) + y16_bytes(V, M, fu);
   if (need > 0 && (!ws || ws_bytes < need)) return B200Q_ERR_WORKSPACE;
   if (ws && ((uintptr_t)ws & 15)) return B200Q_ERR_ALIGNMENT;
   const __half* x_mul = fu ? (const __half*)fu->x_mul : nullptr;
   const __half* residual = fu ? (const __half*)fu->residual : nullptr;
   const int64_t ldres = fu ? fu->ldres : 0;
   if (residual && (ldres < layer->N || peers)) return B200Q_ERR_SHAPE;
-  if (x_mul) {
+  if (fu && fu->act_dtype != B200Q_ACT_F16 && fu->act_dtype != B200Q_ACT_BF16) return B200Q_ERR_UNSUPPORTED;
+  bool bf16 = act_bf16(fu);
+  if (bf16 && peers) return B200Q_ERR_UNSUPPORTED;
+  void* y_user = y;
+  int64_t ldy_user = ldy;
+  bool bf16_post = false;                   // the kernel writes fp16 into the workspace, a pass converts (and adds the residual)
+  if (bf16) {
+    // bfloat16 activations: the integer-path decode kernel converts in its load stage and epilogue; every other kernel
+    // works on an fp16 copy of x and leaves an fp16 result for the conversion pass
+    LinearArgs probe = {};
+    probe.L = V; probe.x = (const __half*)x; probe.ldx = ldx; probe.M = (int)M; probe.x_mul = x_mul;
+    const bool native = force != KERNEL_GEMM_TC && M <= kGemvMaxM && g_use_stream && gemv_imma_supported(&probe, 1);
+    if (!native) {
+      __half* xs = (__half*)((char*)ws + base + gather_bytes(V, M));
+      const cudaError_t e = launch_bf16_in(x, x_mul, ldx, xs, M, V.K, (cudaStream_t)stream);
+      if (e != cudaSuccess) return cuda_status(e);
+      x = xs; ldx = V.K; x_mul = nullptr;
+      y = (char*)ws + base + gather_bytes(V, M) + silu_bytes(V, M, fu);
+      ldy = V.N;
+      bf16 = false; bf16_post = true;
+    }
+  }
+  const __half* residual_user = residual;
+  if (bf16_post) residual = nullptr;        // added by the conversion pass, in bf16
+  if (x_mul && !bf16) {
     // act(gate) * up: folded into the x stage of the integer-path decode kernel; every other kernel reads a fused copy
     LinearArgs probe = {};
     probe.L = V; probe.x = (const __half*)x; probe.ldx = ldx; probe.M = (int)M; probe.x_mul = x_mul;
@@ -220,11 +250,16 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   LinearArgs a = {};
   a.L = V; a.x = (const __half*)x; a.ldx = ldx; a.M = (int)M; a.y = (__half*)y; a.ldy = ldy; a.n_offset = n_offset;
   a.workspace = ws; a.workspace_bytes = ws_bytes; a.stream = (cudaStream_t)stream;
-  a.x_mul = x_mul; a.residual = residual; a.ldres = ldres;
+  a.x_mul = x_mul; a.residual = residual; a.ldres = ldres; a.act_bf16 = bf16 ? 1 : 0;
+  // bf16 callers of a kernel without native bf16 I/O: fp16 result in the workspace -> bf16 y (+ residual, as the bf16 add rounds)
+  auto finish = [&](int st) {
+    if (st != B200Q_OK || !bf16_post) return st;
+    return cuda_status(launch_bf16_out((const __half*)y, y_user, ldy_user, residual_user, ldres, M, V.N, (cudaStream_t)stream));
+  };
   // kernels that do not carry the residual epilogue get it as a small pass behind them
   auto with_residual = [&](cudaError_t e) {
-    if (e != cudaSuccess || !residual) return cuda_status(e);
-    return cuda_status(launch_residual_add((__half*)y, ldy, residual, ldres, M, V.N, (cudaStream_t)stream));
+    if (e != cudaSuccess || !residual) return finish(cuda_status(e));
+    return finish(cuda_status(launch_residual_add((__half*)y, ldy, residual, ldres, M, V.N, (cudaStream_t)stream)));
   };
   if (kern == KERNEL_GEMV_MMA) {
     if (g_use_stream && gemv_imma_supported(&a, 1)) return cuda_status(launch_gemv_imma(&a, 1, peers));
@@ -235,7 +270,7 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   }
   if (kern == KERNEL_GEMM_TC) {
     if (residual && (((uintptr_t)residual & 15) != 0 || (ldres % 8) != 0)) { a.residual = nullptr; return with_residual(launch_gemm_tc(a, peers)); }
-    return cuda_status(launch_gemm_tc(a, peers));
+    return finish(cuda_status(launch_gemm_tc(a, peers)));
   }
   a.residual = nullptr;
   // generic: slabs of <= 16 activation rows
@@ -271,7 +306,7 @@ size_t b200q_workspace_bytes_ex(const b200q_layer* layer, int64_t M, const b200q
   if (validate(layer) != B200Q_OK || M < 1) return 0;
   gemv_variant();
   const LayerView V = make_view(layer);
-  return workspace_for(V, M) + gather_bytes(V, M) + silu_bytes(V, M, fusion);
+  return workspace_for(V, M) + gather_bytes(V, M) + silu_bytes(V, M, fusion) + y16_bytes(V, M, fusion);
 }
 
 int b200q_gemv(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, void* y, int64_t ldy, void* workspace,

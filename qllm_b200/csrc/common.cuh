@@ -139,6 +139,21 @@ __device__ __forceinline__ float silu_mul_f16(float g, float u) {
   return __half2float(__float2half_rn(s * u));
 }
 
+// bfloat16 <-> float on raw bits (round to nearest even; NaN stays NaN)
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
+__device__ __forceinline__ uint32_t float_to_bf16_bits(float f) {
+  const uint32_t u = __float_as_uint(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (u >> 16) | 0x40u;       // quiet NaN
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+__device__ __forceinline__ float round_bf16(float f) { return bf16_bits_to_float(float_to_bf16_bits(f)); }
+// a bf16 model's act(gate) * up feeding a QuantLinear: silu and the product rounded to bf16 (the torch ops), then the
+// reference's cast of the layer input to fp16 (auto_cast, quant_linear_awq.py:29-36)
+__device__ __forceinline__ float silu_mul_bf16_to_f16(float g, float u) {
+  const float s = round_bf16(g / (1.0f + expf(-g)));
+  return __half2float(__float2half_rn(round_bf16(s * u)));
+}
+
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);

@@ -185,6 +185,11 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
           }
           const __half2 h01 = *reinterpret_cast<const __half2*>(&raw.x), h23 = *reinterpret_cast<const __half2*>(&raw.y);
           xv[0] = __low2float(h01); xv[1] = __high2float(h01); xv[2] = __low2float(h23); xv[3] = __high2float(h23);
+          const bool bf16 = FUSED && st_bf16(p.layer[0]);
+          if (bf16) {                                                    // bf16 activations: the reference's cast to fp16, in the load
+            xv[0] = bf16_bits_to_float(raw.x & 0xffffu); xv[1] = bf16_bits_to_float(raw.x >> 16);
+            xv[2] = bf16_bits_to_float(raw.y & 0xffffu); xv[3] = bf16_bits_to_float(raw.y >> 16);
+          }
           const __half* const xmul = FUSED ? (const __half*)p.layer[0].out.y[3] : nullptr;
           if (FUSED && xmul) {                                         // fused act(gate) * up: x = silu(x) * x_mul, rounded as the fp16 ops round
             uint2 rm;
@@ -195,9 +200,17 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
             } else {
               rm = *reinterpret_cast<const uint2*>(xmul + xo);
             }
-            const __half2 u01 = *reinterpret_cast<const __half2*>(&rm.x), u23 = *reinterpret_cast<const __half2*>(&rm.y);
-            xv[0] = silu_mul_f16(xv[0], __low2float(u01)); xv[1] = silu_mul_f16(xv[1], __high2float(u01));
-            xv[2] = silu_mul_f16(xv[2], __low2float(u23)); xv[3] = silu_mul_f16(xv[3], __high2float(u23));
+            if (bf16) {
+              xv[0] = silu_mul_bf16_to_f16(xv[0], bf16_bits_to_float(rm.x & 0xffffu)); xv[1] = silu_mul_bf16_to_f16(xv[1], bf16_bits_to_float(rm.x >> 16));
+              xv[2] = silu_mul_bf16_to_f16(xv[2], bf16_bits_to_float(rm.y & 0xffffu)); xv[3] = silu_mul_bf16_to_f16(xv[3], bf16_bits_to_float(rm.y >> 16));
+            } else {
+              const __half2 u01 = *reinterpret_cast<const __half2*>(&rm.x), u23 = *reinterpret_cast<const __half2*>(&rm.y);
+              xv[0] = silu_mul_f16(xv[0], __low2float(u01)); xv[1] = silu_mul_f16(xv[1], __high2float(u01));
+              xv[2] = silu_mul_f16(xv[2], __low2float(u23)); xv[3] = silu_mul_f16(xv[3], __high2float(u23));
+            }
+          } else if (bf16) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xv[e] = __half2float(__float2half_rn(xv[e]));
           }
         }
         // a NaN / Inf activation must poison its part (the fixed-point conversion would turn it into finite garbage; the
@@ -512,7 +525,7 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers, c
   }
   p.layout = L.layout; p.bits = L.bits; p.group = L.group; p.K = L.K; p.G = L.G; p.zero_bias = L.zero_bias;
   p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M; p.xperm = L.x_perm;
-  if (a[0].x_mul && sync && sync->x_tagged) return cudaErrorInvalidValue;     // tagged activations carry no second operand
+  if ((a[0].x_mul || a[0].act_bf16) && sync) return cudaErrorInvalidValue;     // tagged activations carry no second operand
   if (L.x_perm && sync && sync->x_tagged) return cudaErrorInvalidValue;    // gather through x_perm reads plain fp16 activations
   p.cluster = pl.cluster; p.tpc = pl.tpc; p.depth = pl.depth; p.steps_total = pl.steps_total; p.group_shift = pl.group_shift;
   p.gcap = pl.gcap; p.split_q = pl.split_q; p.split_r = pl.split_r; p.part_cap = pl.part_cap;
@@ -528,13 +541,13 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers, c
     if (p.M == 1) return pl.depth == 2 ? im_launch_k<1, 2, true>(p, pl, a[0].stream) : im_launch_k<1, 4, true>(p, pl, a[0].stream);
     return pl.depth == 2 ? im_launch_k<2, 2, true>(p, pl, a[0].stream) : im_launch_k<2, 4, true>(p, pl, a[0].stream);
   }
-  bool fused = a[0].x_mul != nullptr;
+  bool fused = a[0].x_mul != nullptr || a[0].act_bf16 != 0;
   for (int i = 0; i < n; ++i) fused = fused || a[i].residual != nullptr;
   if (fused) {
     if (peers) return cudaErrorInvalidValue;                            // the fusion operands live in the peer slots
     for (int i = 0; i < kMaxGroupLayers; ++i) {
       const int k = i < n ? i : n - 1;
-      st_set_fusion(p.layer[i], a[k].residual, a[k].ldres, a[0].x_mul);
+      st_set_fusion(p.layer[i], a[k].residual, a[k].ldres, a[0].x_mul, a[0].act_bf16 != 0);
     }                                                           // b200q_linear_ex: prologue / epilogue compiled in
     if (p.M == 1) return pl.depth == 2 ? im_launch_k<1, 2, false, true>(p, pl, a[0].stream) : im_launch_k<1, 4, false, true>(p, pl, a[0].stream);
     return pl.depth == 2 ? im_launch_k<2, 2, false, true>(p, pl, a[0].stream) : im_launch_k<2, 4, false, true>(p, pl, a[0].stream);

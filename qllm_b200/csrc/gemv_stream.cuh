@@ -18,13 +18,15 @@ struct StLayer {
 };
 // b200q_linear_ex operands ride in peer slots the single-GPU (FUSED) instantiations never use -- the parameter block stays at
 // its round-1 size (56 more bytes measured 0.4 % of the decode bench): out.y[1] = residual ([M, ldres] fp16 or NULL),
-// out.y[2] = ldres, layer[0].out.y[3] = x_mul.  out.n stays 1.
+// out.y[2] = ldres, layer[0].out.y[3] = x_mul, layer[0].out.y[4] = flags (bit 0: activations are bfloat16).  out.n stays 1.
 __host__ __device__ __forceinline__ const __half* st_residual(const StLayer& SL) { return SL.out.y[1]; }
 __host__ __device__ __forceinline__ int64_t st_ldres(const StLayer& SL) { return (int64_t)(uintptr_t)SL.out.y[2]; }
-__host__ inline void st_set_fusion(StLayer& SL, const __half* residual, int64_t ldres, const __half* x_mul) {
+__host__ __device__ __forceinline__ bool st_bf16(const StLayer& SL0) { return ((uintptr_t)SL0.out.y[4] & 1u) != 0; }
+__host__ inline void st_set_fusion(StLayer& SL, const __half* residual, int64_t ldres, const __half* x_mul, bool bf16) {
   SL.out.y[1] = const_cast<__half*>(residual);
   SL.out.y[2] = reinterpret_cast<__half*>((uintptr_t)ldres);
   SL.out.y[3] = const_cast<__half*>(x_mul);
+  SL.out.y[4] = reinterpret_cast<__half*>((uintptr_t)(bf16 ? 1 : 0));
 }
 
 struct StParams {
@@ -200,7 +202,14 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
       float o = v[r];
       if (SL.bias) o += __half2float(__ldg(SL.bias + n0 + n));
       __half h = __float2half_rn(o);
-      if (FUSED && st_residual(SL)) h = __float2half_rn(__half2float(h) + __half2float(__ldg(st_residual(SL) + (size_t)m * st_ldres(SL) + n0 + n)));
+      if (FUSED && st_bf16(p.layer[0])) {                    // bf16 caller: fp16 result -> bf16, residual summed as the bf16 add rounds
+        float v = round_bf16(__half2float(h));
+        if (st_residual(SL))
+          v = round_bf16(v + bf16_bits_to_float(__ldg(reinterpret_cast<const unsigned short*>(st_residual(SL)) + (size_t)m * st_ldres(SL) + n0 + n)));
+        h = __ushort_as_half((unsigned short)float_to_bf16_bits(v));
+      } else if (FUSED && st_residual(SL)) {
+        h = __float2half_rn(__half2float(h) + __half2float(__ldg(st_residual(SL) + (size_t)m * st_ldres(SL) + n0 + n)));
+      }
       if (PEER && p.sync.y_tagged) {                        // one 4-byte store per element and replica: value and tag land together
         const uint32_t w = ytag | (uint32_t)__half_as_ushort(h);
         for (int q = 0; q < SL.out.n; ++q)

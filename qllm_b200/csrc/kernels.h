@@ -31,6 +31,7 @@ struct LinearArgs {
   // later ones' flags once its own stream dependency is met; 2 = later sibling number sib_index (0-based), whose
   // activation loads wait for that flag instead of for the kernel in front of it
   int sib_role, sib_index, sib_count;
+  int act_bf16;              // x, x_mul, residual, y are bfloat16 (b200q_fusion.act_dtype); only the integer-path decode kernel takes it
 };
 
 static constexpr int kMaxPeers = 8;
@@ -65,6 +66,10 @@ cudaError_t launch_repack_actorder(const LayerView& L, const int* perm, uint32_t
 cudaError_t launch_gather_x(const __half* x, int64_t ldx, const int* perm, __half* out, int M, int K, cudaStream_t st);
 cudaError_t launch_silu_mul(const __half* x, const __half* x_mul, int64_t ldx, __half* out, int64_t M, int K, cudaStream_t st);
 cudaError_t launch_residual_add(__half* y, int64_t ldy, const __half* res, int64_t ldres, int64_t M, int N, cudaStream_t st);
+// bf16 callers of the kernels without native bf16 I/O: x (and silu(x) * x_mul, rounded as bf16 ops round) -> fp16 copy;
+// fp16 result (+ bf16 residual, rounded as the bf16 add rounds) -> bf16 y
+cudaError_t launch_bf16_in(const void* x, const void* x_mul, int64_t ldx, __half* out, int64_t M, int K, cudaStream_t st);
+cudaError_t launch_bf16_out(const __half* y16, void* y, int64_t ldy, const void* res, int64_t ldres, int64_t M, int N, cudaStream_t st);
 cudaError_t launch_repack_gptq4(const LayerView& L, uint32_t* qw_out, uint32_t* qz_out, __half* s_out, cudaStream_t st);
 cudaError_t launch_repack_from_gptq4(const LayerView& L, int target, uint32_t* qw_out, uint32_t* qz_out, __half* s_out, cudaStream_t st);
 

@@ -227,6 +227,38 @@ cudaError_t launch_residual_add(__half* y, int64_t ldy, const __half* res, int64
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) bf16_in_kernel(const unsigned short* __restrict__ x, const unsigned short* __restrict__ xm, int64_t ldx,
+                                                      __half* __restrict__ out, int64_t M, int K) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * K) return;
+  const int64_t m = idx / K;
+  const int k = (int)(idx - m * K);
+  const float g = bf16_bits_to_float(x[m * ldx + k]);
+  out[idx] = xm ? __float2half_rn(silu_mul_bf16_to_f16(g, bf16_bits_to_float(xm[m * ldx + k]))) : __float2half_rn(g);
+}
+cudaError_t launch_bf16_in(const void* x, const void* x_mul, int64_t ldx, __half* out, int64_t M, int K, cudaStream_t st) {
+  const int64_t total = M * K;
+  bf16_in_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const unsigned short*)x, (const unsigned short*)x_mul, ldx, out, M, K);
+  count_launch();
+  return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256) bf16_out_kernel(const __half* __restrict__ y16, unsigned short* __restrict__ y, int64_t ldy,
+                                                       const unsigned short* __restrict__ res, int64_t ldres, int64_t M, int N) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int64_t m = idx / N;
+  const int n = (int)(idx - m * N);
+  float v = round_bf16(__half2float(y16[idx]));
+  if (res) v = round_bf16(v + bf16_bits_to_float(res[m * ldres + n]));
+  y[m * ldy + n] = (unsigned short)float_to_bf16_bits(v);
+}
+cudaError_t launch_bf16_out(const __half* y16, void* y, int64_t ldy, const void* res, int64_t ldres, int64_t M, int N, cudaStream_t st) {
+  const int64_t total = M * N;
+  bf16_out_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y16, (unsigned short*)y, ldy, (const unsigned short*)res, ldres, M, N);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_unpack(const LayerView& L, int32_t* q_out, int32_t* z_out, cudaStream_t st) {
   const size_t total = (size_t)L.K * (L.N >> 3);
   unpack_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L, q_out, nullptr);

@@ -249,6 +249,8 @@ class _B200QuantLinearBase(nn.Module):
         return super().__call__(x)
 
     def forward(self, x):
+        if x.dtype == torch.bfloat16 and x.is_cuda:      # bf16 model: the library converts (in the decode kernel itself at M <= 2)
+            return self.forward_fused(x)
         desc = self._decode_descriptor(8) if self._layout in _RELAYOUT else self._fast_descriptor()
         out_shape = x.shape[:-1] + (self.outfeatures,)
         x2 = x.reshape(-1, x.shape[-1])
@@ -276,14 +278,18 @@ class _B200QuantLinearBase(nn.Module):
         """forward() with the Linear's element-wise neighbours fused in (b200q_linear_ex):
         y = (silu(x) * x_mul if x_mul is not None else x) @ W + bias (+ residual).  Same results as the separate fp16 ops."""
         out_shape = x.shape[:-1] + (self.outfeatures,)
+        # bf16 in, bf16 out without a cast on this side (b200q_fusion.act_dtype): every operand must be bf16 then
+        bf16 = x.dtype == torch.bfloat16 and all(t is None or t.dtype == torch.bfloat16 for t in (x_mul, residual))
+        act = torch.bfloat16 if bf16 else torch.float16
         def prep(t):
             t2 = t.reshape(-1, t.shape[-1])
-            if t2.dtype != torch.float16:
-                t2 = t2.to(torch.float16)
+            if t2.dtype != act:
+                t2 = t2.to(act)
             return t2 if t2.stride(-1) == 1 else t2.contiguous()
         x2 = prep(x)
         M = x2.shape[0]
         fu = Fusion()
+        fu.act_dtype = 1 if bf16 else 0
         keep = []
         if x_mul is not None:
             xm = prep(x_mul)
@@ -295,7 +301,7 @@ class _B200QuantLinearBase(nn.Module):
             r2 = prep(residual)
             keep.append(r2)
             fu.residual, fu.ldres = r2.data_ptr(), r2.stride(0)
-        y = torch.empty((M, self.outfeatures), dtype=torch.float16, device=x.device)
+        y = torch.empty((M, self.outfeatures), dtype=act, device=x.device)
         if M > 0:
             desc = self._decode_descriptor(8) if self._layout in _RELAYOUT else self._fast_descriptor()
             if M > lib.b200q_gemv_max_m() and lib.b200q_select_kernel(ctypes.byref(desc), M) != 2:

@@ -413,3 +413,46 @@ def test_gemm_cluster_split_k_matches_unsplit(K, N, M):
     ref = x.double() @ layer.dequantize().double()
     for y in (base, outs[128], outs[256]):
         assert ((y.double() - ref).abs().max() / ref.abs().max()).item() < 1e-3
+
+
+# ---- bf16 activations through the C ABI (b200q_fusion.act_dtype) ------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout,bits,gs,M", [("GPTQ", 4, 128, 1), ("GPTQ", 4, 128, 2), ("GEMM", 4, 128, 1), ("GPTQ", 4, 128, 5),
+                                              ("GPTQ", 8, 128, 3), ("GPTQ", 3, 128, 2), ("GPTQ", 4, 128, 100), ("HQQ", 4, 64, 300),
+                                              ("MARLIN", 4, 128, 1), ("GPTQ", 4, 128, 64)])
+def test_bf16_forward_equals_reference_casts(layout, bits, gs, M):
+    """bf16 in / bf16 out == the reference's handling of a bf16 model (auto_cast to fp16, out.to(x.dtype),
+    quant_linear_awq.py:29-36,:146), bit for bit, in the decode kernel (native) and through the conversion passes."""
+    K, N = 1024, 512
+    layer = layer_from_dict(O.make_layer(layout, bits, gs, K, N, seed=bits + M))
+    x = (torch.randn(M, K, device="cuda", generator=torch.Generator(device="cuda").manual_seed(M)) * 3).to(torch.bfloat16)
+    x[0, 5] = 7.0e4                        # beyond fp16: the reference's cast makes it inf
+    x[-1, 9] = 3.0e-6                      # fp16 sub-normal after the cast
+    y = layer(x)
+    assert y.dtype == torch.bfloat16 and y.shape == (M, N)
+    ref = layer(x.to(torch.float16)).to(torch.bfloat16)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(y.float(), nan=1e30), torch.nan_to_num(ref.float(), nan=1e30))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [1, 2, 6, 128])
+def test_bf16_fused_mlp_and_residual(M):
+    """b200q_linear_ex in bf16: silu(gate) * up and the residual add rounded as the model's bf16 torch ops round them."""
+    import torch.nn.functional as F
+    K, N = 1024, 512
+    layer = layer_from_dict(O.make_layer("GPTQ", 4, 128, K, N, seed=M + 40))
+    g = torch.Generator(device="cuda").manual_seed(M)
+    gate = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    up = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    y = layer.forward_fused(gate, x_mul=up, residual=res)
+    assert y.dtype == torch.bfloat16
+    ref = res + layer((F.silu(gate) * up).to(torch.float16)).to(torch.bfloat16)
+    torch.cuda.synchronize()
+    err = (y.float() - ref.float()).abs().max().item() / ref.float().abs().max().item()
+    assert err < 2.0 ** -7                 # expf vs torch's exp may move a bf16 rounding by one ulp here and there
+    y2 = layer.forward_fused(gate, residual=res)
+    ref2 = res + layer(gate.to(torch.float16)).to(torch.bfloat16)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, ref2)
