@@ -243,6 +243,15 @@ class _B200QuantLinearBase(nn.Module):
 
     # -- forward ------------------------------------------------------------------------------
     def __call__(self, x):
+        if NVTX:             # B200Q_NVTX=1: one range per QuantLinear call (shows up in nsys / ncu --nvtx timelines)
+            torch.cuda.nvtx.range_push(f"b200q.{type(self).__name__} {tuple(x.shape)}x{self.infeatures}->{self.outfeatures} w{self.bits}g{self.groupsize}")
+            try:
+                return self._call(x)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return self._call(x)
+
+    def _call(self, x):
         grp = getattr(self, "_sibling_group", None)
         if grp is not None:
             return grp.forward_of(self, x)
@@ -635,6 +644,7 @@ class QuantLinearMarlin(_B200QuantLinearBase):
         return w.t().contiguous().cpu(), s.cpu(), torch.full_like(s, 8, dtype=torch.int32).cpu()
 
 
+NVTX = os.environ.get("B200Q_NVTX", "0") not in ("", "0")
 GROUP_GEMM_MIN_M = 64      # above this the library runs sibling GEMMs with the flag release (below: plain per-layer calls)
 
 
