@@ -202,6 +202,7 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   void* y_user = y;
   int64_t ldy_user = ldy;
   bool bf16_post = false;                   // the kernel writes fp16 into the workspace, a pass converts (and adds the residual)
+  bool gemm_bf16_out = false;               // ... or the tcgen05 GEMM's epilogue does
   if (bf16) {
     // bfloat16 activations: the integer-path decode kernel converts in its load stage and epilogue; every other kernel
     // works on an fp16 copy of x and leaves an fp16 result for the conversion pass
@@ -213,9 +214,17 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
       const cudaError_t e = launch_bf16_in(x, x_mul, ldx, xs, M, V.K, (cudaStream_t)stream);
       if (e != cudaSuccess) return cuda_status(e);
       x = xs; ldx = V.K; x_mul = nullptr;
-      y = (char*)ws + base + gather_bytes(V, M) + silu_bytes(V, M, fu);
-      ldy = V.N;
-      bf16 = false; bf16_post = true;
+      // the tcgen05 GEMM rounds to bf16 (and adds a bf16 residual) in its own epilogue; the rest leave fp16 for a pass
+      LayerView Vg = V;
+      Vg.x_perm = nullptr;
+      gemm_bf16_out = select(Vg, M, (const __half*)x, ldx, force) == KERNEL_GEMM_TC &&
+                      (!residual || (((uintptr_t)residual & 15) == 0 && (ldres % 8) == 0));
+      bf16 = false;
+      if (!gemm_bf16_out) {
+        y = (char*)ws + base + gather_bytes(V, M) + silu_bytes(V, M, fu);
+        ldy = V.N;
+        bf16_post = true;
+      }
     }
   }
   const __half* residual_user = residual;
@@ -250,7 +259,7 @@ static int run(const b200q_layer* layer, const void* x, int64_t M, int64_t ldx, 
   LinearArgs a = {};
   a.L = V; a.x = (const __half*)x; a.ldx = ldx; a.M = (int)M; a.y = (__half*)y; a.ldy = ldy; a.n_offset = n_offset;
   a.workspace = ws; a.workspace_bytes = ws_bytes; a.stream = (cudaStream_t)stream;
-  a.x_mul = x_mul; a.residual = residual; a.ldres = ldres; a.act_bf16 = bf16 ? 1 : 0;
+  a.x_mul = x_mul; a.residual = residual; a.ldres = ldres; a.act_bf16 = (bf16 || gemm_bf16_out) ? 1 : 0;
   // bf16 callers of a kernel without native bf16 I/O: fp16 result in the workspace -> bf16 y (+ residual, as the bf16 add rounds)
   auto finish = [&](int st) {
     if (st != B200Q_OK || !bf16_post) return st;

@@ -49,6 +49,7 @@ struct TcParams {
   int64_t ldy, n_offset;
   const __half* residual;                   // NULL, or [M, ldres]: added to the rounded output in the epilogue (b200q_linear_ex)
   int64_t ldres;
+  int out_bf16;                             // y (and residual) are bfloat16: the fp16 result is rounded to bf16 in the epilogue
   int kblocks, gshift, group32, nsx, nsw;   // nsx / nsw: X and W ring depths actually used
   int ksplit, kb_per;                       // split-K over gridDim.z (small M): k-blocks per split; partial tiles + last-arriver reduction
   int csplit, off_part;                     // cluster split-K (M > 64): 2 = the CTA pair (cluster dims 1,1,2) halves K and swaps half-tiles
@@ -535,7 +536,11 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
         continue;
       }
 #pragma unroll
-      for (int i = 0; i < 32; ++i) stg[(size_t)i * (kBN + 8) + n] = __float2half_rn(__uint_as_float(v[i]) + bias);
+      for (int i = 0; i < 32; ++i) {
+        __half h = __float2half_rn(__uint_as_float(v[i]) + bias);
+        if (p.out_bf16) h = __ushort_as_half((unsigned short)float_to_bf16_bits(__half2float(h)));   // bf16 caller: out.to(x.dtype)
+        stg[(size_t)i * (kBN + 8) + n] = h;
+      }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + eidx) : "memory");
       // 32 token rows x 256 B: 16 chunks of 16 B per row, 128 threads -> 4 chunks each
 #pragma unroll
@@ -546,6 +551,18 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
           uint4 val = *reinterpret_cast<const uint4*>(stg + (size_t)row * (kBN + 8) + 8 * ch);
           if (p.residual) {                         // y = fp16(fp16(acc + bias) + residual), as the unfused fp16 add rounds
             const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)tok * p.ldres + n0 + 8 * ch));
+            if (p.out_bf16) {                       // bf16 model: the skip connection is a bf16 add
+              const uint32_t* a1 = reinterpret_cast<const uint32_t*>(&val);
+              const uint32_t* r1 = reinterpret_cast<const uint32_t*>(&rv);
+              uint32_t o1[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t lo = float_to_bf16_bits(bf16_bits_to_float(a1[e] & 0xffffu) + bf16_bits_to_float(r1[e] & 0xffffu));
+                const uint32_t hi = float_to_bf16_bits(bf16_bits_to_float(a1[e] >> 16) + bf16_bits_to_float(r1[e] >> 16));
+                o1[e] = lo | (hi << 16);
+              }
+              val = *reinterpret_cast<const uint4*>(o1);
+            } else {
             const __half2* a2 = reinterpret_cast<const __half2*>(&val);
             const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
             __half2 o2[4];
@@ -555,6 +572,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
               o2[e] = __floats2half2_rn(fa.x + fr.x, fa.y + fr.y);
             }
             val = *reinterpret_cast<const uint4*>(o2);
+            }
           }
           for (int qd = 0; qd < p.out.n; ++qd)
             *reinterpret_cast<uint4*>(p.out.y[qd] + (size_t)tok * p.ldy + p.n_offset + n0 + 8 * ch) = val;
@@ -599,7 +617,13 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
             for (int e = 0; e < 4; ++e) {
               const float bv = __half2float(bsrc[nn + e]);
               h[e] = __float2half_rn(has_bias ? acc[e] + bv : acc[e]);
-              if (p.residual) h[e] = __float2half_rn(__half2float(h[e]) + __half2float(p.residual[(size_t)tok * p.ldres + nn + e]));
+              if (p.out_bf16) {
+                float v = round_bf16(__half2float(h[e]));
+                if (p.residual) v = round_bf16(v + bf16_bits_to_float(reinterpret_cast<const unsigned short*>(p.residual)[(size_t)tok * p.ldres + nn + e]));
+                h[e] = __ushort_as_half((unsigned short)float_to_bf16_bits(v));
+              } else if (p.residual) {
+                h[e] = __float2half_rn(__half2float(h[e]) + __half2float(p.residual[(size_t)tok * p.ldres + nn + e]));
+              }
             }
             const uint2 pk = make_uint2((uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16),
                                         (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16));
@@ -774,7 +798,7 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   p.L = L; p.M = a.M;
   if (peers) p.out = *peers; else { p.out.n = 1; p.out.y[0] = a.y; }
   p.ldy = a.ldy; p.n_offset = a.n_offset;
-  p.residual = a.residual; p.ldres = a.ldres;
+  p.residual = a.residual; p.ldres = a.ldres; p.out_bf16 = a.act_bf16;
   if (a.residual && (((uintptr_t)a.residual & 15) != 0 || (a.ldres % 8) != 0)) return cudaErrorInvalidValue;
   p.kblocks = L.K / kBK;
   p.ksplit = tc_ksplit(L, a.M);

@@ -31,7 +31,8 @@ struct LinearArgs {
   // later ones' flags once its own stream dependency is met; 2 = later sibling number sib_index (0-based), whose
   // activation loads wait for that flag instead of for the kernel in front of it
   int sib_role, sib_index, sib_count;
-  int act_bf16;              // x, x_mul, residual, y are bfloat16 (b200q_fusion.act_dtype); only the integer-path decode kernel takes it
+  int act_bf16;              // b200q_fusion.act_dtype == bf16: integer-path decode kernel: x, x_mul, residual, y are bfloat16; tcgen05 GEMM:
+                             // y and residual are (x arrives as an fp16 copy)
 };
 
 static constexpr int kMaxPeers = 8;

@@ -436,7 +436,7 @@ def test_bf16_forward_equals_reference_casts(layout, bits, gs, M):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("M", [1, 2, 6, 128])
+@pytest.mark.parametrize("M", [1, 2, 6, 40, 128, 600])
 def test_bf16_fused_mlp_and_residual(M):
     """b200q_linear_ex in bf16: silu(gate) * up and the residual add rounded as the model's bf16 torch ops round them."""
     import torch.nn.functional as F
