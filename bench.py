@@ -338,7 +338,8 @@ class FusedShardedStep:
 
     def run(self, stream):
         from qllm_b200.sharding import sharded_group_forward
-        from qllm_b200._lib import PEER_X_TAGGED, PEER_Y_TAGGED
+        from qllm_b200._lib import PEER_NODE_EPOCH, PEER_X_TAGGED, PEER_Y_TAGGED
+        node = PEER_NODE_EPOCH if os.environ.get("B200Q_BENCH_NO_NODE_EPOCH") is None else 0
         A, M = self.arena, self.M
         A.advance(stream)
         x_name, wait_slot, wait_count = None, -1, 0
@@ -351,7 +352,7 @@ class FusedShardedStep:
                 layers = [b[n] for n in names]
                 offs, fulls, col0s = [self.off[n] for n in names], [self.full[n] for n in names], [l.col0 for l in layers]
                 if self.tagged:
-                    flags = PEER_Y_TAGGED | (PEER_X_TAGGED if x_name is not None else 0)
+                    flags = PEER_Y_TAGGED | (PEER_X_TAGGED if x_name is not None else 0) | node
                     sync = A.sync_desc(flags=flags, tag_stride=stride, y_seq=slot, x_seq=slot - 1)
                 else:
                     sync = A.sync_desc(wait_slot, wait_count, slot)

@@ -214,6 +214,16 @@ typedef struct b200q_peer_sync {
  */
 #define B200Q_PEER_Y_TAGGED 1u
 #define B200Q_PEER_X_TAGGED 2u
+/*
+ * B200Q_PEER_NODE_EPOCH (with B200Q_PEER_Y_TAGGED): `epoch` points at 1 + tag_stride words; word 0 is the step number as
+ * before, word 1 + y_seq counts the completed executions of call y_seq and is maintained by that call's own kernel (its last
+ * storing CTA).  The kernel derives the step from ITS OWN word (a call runs once per step, and a step starts after the
+ * previous one has ended, so the word is stable and current when the kernel starts), which removes the one thing its
+ * x-load stage needed the kernel boundary for: with tagged x it no longer executes griddepcontrol.wait before reading
+ * activations (the tags order the data) -- only ahead of its stores, where the wait has long been satisfied.  Every call of
+ * the step must run exactly once per step (a replayed CUDA graph), words start at zero.
+ */
+#define B200Q_PEER_NODE_EPOCH 4u
 int b200q_peer_untag(const void* tagged, int64_t ld_tagged, void* y, int64_t ldy, int64_t M, int64_t N,
                      const b200q_peer_sync* sync, b200q_stream_t stream);
 int b200q_linear_group_sharded(const b200q_layer* const* layers, int32_t n_layers, const void* x, int64_t M, int64_t ldx,

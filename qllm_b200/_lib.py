@@ -9,6 +9,7 @@ B200Q_OK = 0
 LAYOUT_GPTQ, LAYOUT_AWQ_GEMM, LAYOUT_MARLIN, LAYOUT_HQQ, LAYOUT_AWQ_GEMV, LAYOUT_ORT = 0, 1, 2, 3, 4, 5
 KERNEL_GEMV, KERNEL_GEMM, KERNEL_GENERIC = 1, 2, 3
 PEER_Y_TAGGED, PEER_X_TAGGED = 1, 2
+PEER_NODE_EPOCH = 4
 
 
 class Layer(ctypes.Structure):

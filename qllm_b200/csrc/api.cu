@@ -509,6 +509,8 @@ int b200q_linear_group_sharded(const b200q_layer* const* layers, int32_t n_layer
   ps.y_tagged = (sync->flags & B200Q_PEER_Y_TAGGED) ? 1 : 0;
   ps.x_tagged = (sync->flags & B200Q_PEER_X_TAGGED) ? 1 : 0;
   ps.tag_stride = sync->tag_stride; ps.y_seq = sync->y_seq; ps.x_seq = sync->x_seq;
+  ps.node_epoch = (sync->flags & B200Q_PEER_NODE_EPOCH) ? 1 : 0;
+  if (ps.node_epoch && (!ps.y_tagged || sync->y_seq >= sync->tag_stride)) return B200Q_ERR_UNSUPPORTED;
   if ((ps.y_tagged || ps.x_tagged) && !sync->epoch) return B200Q_ERR_NULL;
   if (ps.x_tagged && ((uintptr_t)x & 15)) return B200Q_ERR_ALIGNMENT;
   if ((ps.y_tagged || ps.x_tagged) && (!sync->counters || !sync->counters[sync->self])) return B200Q_ERR_NULL;   // slot 0: time-out poison

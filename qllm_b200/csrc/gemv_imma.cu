@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
 
   // ---- activations: wait for the upstream kernel, then split this warp's k-range into digits ----
   // parts: <= 128 k (4 sub-steps of 32 k), never across a group boundary; part table (per warp): {2^-E, sum(x)} per token
-  pdl_wait();
+  // tagged x in node-epoch mode: the tags order the data and the step comes from this call's own word, so the load stage
+  // does not wait for the kernel in front of it (st_reduce_store waits ahead of the stores instead)
+  if (!(PEER && p.sync.node_epoch && p.sync.x_tagged)) pdl_wait();
   if (PEER) {
     ST_STAMP(3);                                                         // local upstream done; stamp 2 follows the peers' posts
     st_sync_wait(p, lane);
@@ -522,6 +524,7 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers, c
     p.store_ctas = pl.ctas / pl.cluster;
     p.sync_flags = decode_sync_flags();
     if (sync->n_peers > 1 && sync->post_slot >= 0 && (!a[0].workspace || a[0].workspace_bytes < kCounterBytes)) return cudaErrorInvalidValue;
+    if (sync->node_epoch && (!a[0].workspace || a[0].workspace_bytes < kCounterBytes)) return cudaErrorInvalidValue;
   }
   p.layout = L.layout; p.bits = L.bits; p.group = L.group; p.K = L.K; p.G = L.G; p.zero_bias = L.zero_bias;
   p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M; p.xperm = L.x_perm;

@@ -99,6 +99,7 @@ __device__ __forceinline__ uint2 st_load_tagged4(const StParams& p, const uint32
   for (;;) {
     asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(w) : "memory");
     if (((a >> 16) == tag) & ((b >> 16) == tag) & ((c >> 16) == tag) & ((d >> 16) == tag)) break;
+    if (p.sync.node_epoch) __nanosleep(96);                 // this launch may have started long before its producer ends: poll gently
     if ((++spins & 1023u) == 0) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -108,8 +109,13 @@ __device__ __forceinline__ uint2 st_load_tagged4(const StParams& p, const uint32
   }
   return make_uint2((a & 0xffffu) | (b << 16), (c & 0xffffu) | (d << 16));
 }
+// step number of this launch: the step word, or (node-epoch mode) one more than the completed executions of this call
+__device__ __forceinline__ uint32_t st_step(const StParams& p) {
+  const volatile unsigned long long* e = reinterpret_cast<const volatile unsigned long long*>(p.sync.epoch);
+  return p.sync.node_epoch ? (uint32_t)e[1 + p.sync.y_seq] + 1u : (uint32_t)e[0];
+}
 __device__ __forceinline__ uint32_t st_step_tag(const StParams& p, uint32_t seq) {
-  return ((uint32_t)(*reinterpret_cast<const volatile unsigned long long*>(p.sync.epoch)) * p.sync.tag_stride + seq) & 0xffffu;
+  return (st_step(p) * p.sync.tag_stride + seq) & 0xffffu;
 }
 
 // Producer side: called by every thread of a storing CTA after its stores to the peers' buffers.  The storing CTAs
@@ -194,6 +200,9 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
     }
   }
   const uint32_t ytag = (PEER && p.sync.y_tagged) ? st_step_tag(p, p.sync.y_seq) << 16 : 0u;
+  // node-epoch mode skipped the kernel-boundary wait ahead of the tagged x loads: the stores still follow the previous
+  // kernel's last reads (and keep "kernel i ends after kernel i - 1" for everything downstream)
+  if (PEER && p.sync.node_epoch && p.sync.x_tagged) pdl_wait();
 #pragma unroll
   for (int r = 0; r < NV; ++r) {
     const int idx = tid + r * kRpThreads;
@@ -220,6 +229,16 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
     }
   }
   if (PEER) st_sync_post(p, tid);
+  if (PEER && p.sync.node_epoch) {                          // the last storing CTA records that this call has run once more
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int* arr = p.arrive + 2 + (p.sync.y_seq & 1u);   // neighbouring calls overlap: alternate words (self-cleaning)
+      if (atomicAdd(arr, 1u) == (unsigned int)p.store_ctas - 1u) {
+        *arr = 0u;
+        const_cast<unsigned long long*>(p.sync.epoch)[1 + p.sync.y_seq] = (unsigned long long)st_step(p);
+      }
+    }
+  }
   ST_STAMP(6);
 }
 

@@ -56,6 +56,7 @@ struct PeerSync {
   // step: a buffer rewritten several times per step (once per decoder block) never shows a stale word with the awaited tag.
   int y_tagged, x_tagged;
   unsigned int tag_stride, y_seq, x_seq;
+  int node_epoch;                          // B200Q_PEER_NODE_EPOCH: the step comes from epoch[1 + y_seq] + 1, no kernel-boundary wait ahead of tagged x
 };
 
 int decode_sync_flags();        // diagnostic switch (B200Q_SYNC_FLAGS / "sync_flags")

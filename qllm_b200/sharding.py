@@ -137,7 +137,8 @@ class PeerArena:
         torch.cuda.synchronize()
         dist.barrier(self.group)
         self._cursor = self.counter_bytes
-        self.epoch = torch.zeros(1, dtype=torch.int64, device=self.device)          # local step number
+        # word 0: local step number; words 1..: per-call execution counts (B200Q_PEER_NODE_EPOCH, maintained by the kernels)
+        self.epoch = torch.zeros(4096, dtype=torch.int64, device=self.device)
         self._counters = (ctypes.c_void_p * self.world)(*self.base)                 # counters sit at offset 0
 
     def carve(self, nbytes: int) -> int:

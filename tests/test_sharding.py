@@ -104,7 +104,7 @@ class _VirtualArena:
         from qllm_b200._lib import PeerSync
         self.world = world
         self.bufs = [torch.zeros(2048 + payload, dtype=torch.uint8, device="cuda") for _ in range(world)]
-        self.epochs = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        self.epochs = [torch.zeros(16, dtype=torch.int64, device="cuda") for _ in range(world)]
         self._ctr = (ctypes.c_void_p * world)(*[b.data_ptr() for b in self.bufs])
         self._ct, self._PS = ctypes, PeerSync
 
@@ -193,8 +193,9 @@ def test_peer_wait_times_out_instead_of_hanging():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("node_epoch", [0, 4])          # 4 = B200Q_PEER_NODE_EPOCH: the step comes from the call's own word
 @pytest.mark.parametrize("layout,M", [("GPTQ", 1), ("GEMM", 2)])
-def test_tagged_activation_chain_virtual_ranks(layout, M):
+def test_tagged_activation_chain_virtual_ranks(layout, M, node_epoch):
     """Flag-in-data hand-off: layer A's shards are written as tagged words (fp16 | step tag << 16) into every replica,
     layer B reads the tagged replica as its x, b200q_peer_untag returns plain fp16.  Two steps: the tag follows the
     epoch.  Checked against the oracle of the two-layer chain (x_B = fp16(y_A))."""
@@ -218,10 +219,10 @@ def test_tagged_activation_chain_virtual_ranks(layout, M):
         yp = (ctypes.c_void_p * world)(*[A.bufs[q].data_ptr() + off for q in range(world)])
         ld, no = (ctypes.c_int64 * 1)(N), (ctypes.c_int64 * 1)(shard.col0)
         s = A.sync(r, -1, 0, -1)
-        s.flags, s.tag_stride, s.y_seq, s.x_seq = flags, 3, y_seq, x_seq
+        s.flags, s.tag_stride, s.y_seq, s.x_seq = flags | node_epoch, 3, y_seq, x_seq
         check(lib.b200q_linear_group_sharded(arr, 1, x_ptr, M, ldx, yp, ld, no, ctypes.byref(s), ws.data_ptr(), ws.numel(), st))
 
-    for step in (1, 2):
+    for step in (1, 2, 3):
         x = rng.standard_normal((M, K)).astype(np.float16)
         xd = torch.from_numpy(x).cuda()
         for r in range(world):
@@ -246,6 +247,9 @@ def test_tagged_activation_chain_virtual_ranks(layout, M):
         assert torch.equal(outs[0], outs[1])
         assert rel_err(outs[0].float().cpu().numpy(), ref) < 1e-3
         assert A.counter(0, 0) == 0 and A.counter(1, 0) == 0
+        if node_epoch:                      # each call's own word follows the step; the arrival words are back at zero
+            assert [int(v) for v in A.epochs[0][:4].cpu()] == [step, 0, step, step]
+            assert int(ws[4000:4016].view(torch.int32).abs().sum().item()) == 0
 
 
 @pytest.mark.gpu
