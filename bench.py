@@ -312,20 +312,23 @@ class FusedShardedStep:
         import torch
         import torch.distributed as dist
         import qllm_b200
-        from qllm_b200.sharding import PeerArena, sharded_group_posts
+        from qllm_b200.sharding import LocalArena, PeerArena, sharded_group_posts
         self.lib, self.blocks, self.M, self.world, self.rank, self.torch = qllm_b200.lib, blocks, M, world, rank, torch
-        self.tagged = os.environ.get("B200Q_BENCH_COUNTERS") is None
+        self.tagged = os.environ.get("B200Q_BENCH_COUNTERS") is None or world == 1
         esz = 4 if self.tagged else 2
         full = {n: N for n, _, N in SHAPES}
-        self.arena = PeerArena(sum(((M * N * esz + 255) & ~255) for N in full.values()), n_slots=8 + 4 * len(blocks))
+        payload = sum(((M * N * esz + 255) & ~255) for N in full.values())
+        self.arena = PeerArena(payload, n_slots=8 + 4 * len(blocks)) if world > 1 else LocalArena(payload, n_slots=8 + 4 * len(blocks), device=dev)
         self.off = {n: self.arena.carve(M * N * esz) for n, N in full.items()}
         self.bufs = {n: self.arena.local_view(self.off[n], (M, N), torch.int32 if self.tagged else torch.float16) for n, N in full.items()}
         self.full = full
         self.h = torch.zeros(M, HIDDEN, dtype=torch.float16, device=dev)
         self.out = torch.zeros(M, HIDDEN, dtype=torch.float16, device=dev)
         mine = [sharded_group_posts([blocks[0][n] for n in names], M) for names in self.CALLS]
-        every = [None] * world
-        dist.all_gather_object(every, mine)
+        every = [mine]
+        if world > 1:
+            every = [None] * world
+            dist.all_gather_object(every, mine)
         self.wait_counts = [sum(every[r][j] for r in range(world) if r != rank) for j in range(len(self.CALLS))]
         need = max(self.lib.b200q_workspace_bytes(ctypes.byref(l._decode_descriptor(M)), M) for l in blocks[0].values())
         self.ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=dev)
@@ -334,7 +337,8 @@ class FusedShardedStep:
         for l in blocks[0].values():
             l(torch.zeros(M, l.infeatures, dtype=torch.float16, device=dev))
         torch.cuda.synchronize()
-        dist.barrier()
+        if world > 1:
+            dist.barrier()
 
     def run(self, stream):
         from qllm_b200.sharding import sharded_group_forward
@@ -395,6 +399,12 @@ def run_b200q(args, rank, world, local_rank):
         if ok.item() == 0:
             step = None
     fused_sharded = step is not None
+    tagged_n1 = False
+    if world == 1 and args.handoff == "tagged" and LAYOUT != "GPTQ_ACT" and args.chain == 0:
+        # single GPU, same kernels as the N > 1 path with one peer: activations travel between the QuantLinears as tagged words
+        # and a consumer's load stage follows the data instead of the kernel boundary (B200Q_PEER_NODE_EPOCH)
+        step = FusedShardedStep(blocks, dev, M, 0, 1)
+        tagged_n1 = True
     chain_span = 0
     if step is None and world == 1 and args.chain > 0:
         step = ChainDecodeStep(blocks, dev, M, args.chain)
@@ -453,6 +463,15 @@ def run_b200q(args, rank, world, local_rank):
     tok_s = 1e3 / ms_per_step
     finite = bool(torch.isfinite(out.float()).all().item())
     replicas_equal, timeouts = None, None
+    matches_plain = None
+    if tagged_n1:                                         # the tagged chain against the kernel-boundary chain on the same weights
+        plain = DecodeStep(blocks, dev, M, rank, world)
+        plain.h.copy_(step.h)
+        with torch.cuda.stream(s):
+            ref_out = plain.run(s.cuda_stream)
+        s.synchronize()
+        matches_plain = bool(torch.equal(ref_out, out))
+        timeouts = bool(step.arena.poisoned())
     if world > 1:
         allout = [torch.empty_like(out) for _ in range(world)]
         dist.all_gather(allout, out.contiguous())
@@ -485,6 +504,10 @@ def run_b200q(args, rank, world, local_rank):
                    "M": M, "layers": n_layers, "parallelism": (f"column-shard x{world}, all-gather + hand-off fused into the decode kernels (NVLink peer stores, "
                                     + ("tagged activations" if getattr(step, "tagged", False) else "counter post/wait") + ")" if fused_sharded
                                    else f"column-shard x{world} + NCCL all-gather per layer") if world > 1 else "single GPU",
+                   "handoff": ("tagged activations between the QuantLinears (fp16 | step tag << 16): a consumer's load stage follows the data, "
+                               "no kernel-boundary wait ahead of x" if (tagged_n1 or (fused_sharded and getattr(step, "tagged", False)))
+                               else "kernel boundary (programmatic dependent launch)"),
+                   "matches_kernel_boundary_path": matches_plain,
                    "fused_sharded_error": fused_err, "replicas_equal": replicas_equal, "peer_wait_timeouts": timeouts,
                    "l2_policy": "inputs (3.4 GB packed weights) larger than L2", "cuda_graph": True, "pdl": True,
                    "outputs_finite": finite},
@@ -499,12 +522,39 @@ def run_b200q(args, rank, world, local_rank):
         t_block = C.time_block(M=1, repeats=3, hidden=HIDDEN, inter=INTER)
         result["cpu_baseline"] = {"value": 1.0 / (t_block * BLOCKS), "unit": "tokens/s", "cores": torch.get_num_threads(),
                                   "kind": "port", "sample": f"1 of {BLOCKS} decoder blocks (7 QuantLinears, M=1, fp16 torch-CPU dequant+matmul), best of 3, x{BLOCKS}"}
+    if world == 1 and not tagged_n1 and chain_span == 0 and args.config == "decode7b" and not args.no_prefill:
+        # beside the headline (plain fp16 between the layers, what an unmodified model sees): the same chain with the N > 1 path's
+        # tagged hand-off on one GPU (--handoff tagged) -- applies wherever one QuantLinear feeds the next directly
+        try:
+            result["tagged_handoff"] = tagged_chain_extra(blocks, dev, M, s, steps, warm, out, step.h, total_bytes, P)
+        except Exception as e:
+            result["tagged_handoff"] = {"error": str(e)[:200]}
     if world == 1 and not args.no_prefill and args.config == "decode7b":
         try:
             result["prefill"] = prefill_tflops(dev, P)
         except Exception as e:                       # the decode metric stands on its own
             result["prefill"] = {"error": str(e)[:200]}
     print(json.dumps(result), flush=True)
+
+
+def tagged_chain_extra(blocks, dev, M, s, steps, warm, ref_out, h, total_bytes, P):
+    """The decode step with tagged activations between the QuantLinears on one GPU (FusedShardedStep, world 1), timed like
+    the headline; must reproduce the headline path's hidden state bit for bit."""
+    import torch
+    step = FusedShardedStep(blocks, dev, M, 0, 1)
+    step.h.copy_(h)
+    with torch.cuda.stream(s):
+        step.run(s.cuda_stream)
+        s.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            out = step.run(torch.cuda.current_stream().cuda_stream)
+        ms = _timed(graph.replay, steps, warm + 50, torch.cuda.synchronize) 
+    equal = bool(torch.equal(out, ref_out))
+    return {"value": 1e3 / ms, "unit": "tokens/s", "ms_per_step": ms, "roofline_frac": total_bytes / (ms * 1e-3) / 1e9 / P["hbm_gbs"],
+            "matches_headline_path": equal, "peer_wait_timeouts": bool(step.arena.poisoned()),
+            "what": "bench.py --handoff tagged: activations between the QuantLinears as fp16 | step tag << 16 words, a consumer's load stage "
+                    "follows the data instead of the kernel boundary (B200Q_PEER_NODE_EPOCH)"}
 
 
 def prefill_tflops(dev, P, M=512, iters=8):
@@ -762,6 +812,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200q", choices=["b200q", "reference"])
+    ap.add_argument("--handoff", default="kernel", choices=["kernel", "tagged"],
+                    help="N = 1 decode: how consecutive QuantLinears hand activations over (kernel = plain fp16 + kernel-boundary order; "
+                         "tagged = tagged words, data-flow per lane)")
     ap.add_argument("--chain", type=int, default=0,
                     help="decoder blocks per decode-chain launch (b200q_chain_run); 0 = one launch per sibling group (b200q_linear_group)")
     ap.add_argument("--config", default="decode7b", choices=sorted(CONFIGS),

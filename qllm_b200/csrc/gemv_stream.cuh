@@ -99,7 +99,7 @@ __device__ __forceinline__ uint2 st_load_tagged4(const StParams& p, const uint32
   for (;;) {
     asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(w) : "memory");
     if (((a >> 16) == tag) & ((b >> 16) == tag) & ((c >> 16) == tag) & ((d >> 16) == tag)) break;
-    if (p.sync.node_epoch) __nanosleep(96);                 // this launch may have started long before its producer ends: poll gently
+    if (p.sync.node_epoch && !(p.sync_flags & 32)) __nanosleep((p.sync_flags & 64) ? 32 : 96);   // this launch may have started long before its producer ends: poll gently
     if ((++spins & 1023u) == 0) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));

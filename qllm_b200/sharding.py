@@ -199,6 +199,23 @@ def sharded_group_posts(local_layers, M: int) -> int:
     return n
 
 
+class LocalArena(PeerArena):
+    """The same arena on ONE GPU (world 1, plain device memory, no process group): lets a chain of QuantLinears hand its
+    activations over as tagged words on a single device -- the consumer kernel's load stage then follows the data, not
+    the kernel boundary (B200Q_PEER_NODE_EPOCH)."""
+
+    def __init__(self, payload_bytes: int, n_slots: int = 1024, device=None):
+        self.group, self.rank, self.world = None, 0, 1
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.counter_bytes = (n_slots * self.COUNTER_BYTES + 255) & ~255
+        self.nbytes = self.counter_bytes + ((payload_bytes + 255) & ~255)
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
+        self.base = [self.buf.data_ptr()]
+        self._cursor = self.counter_bytes
+        self.epoch = torch.zeros(4096, dtype=torch.int64, device=self.device)
+        self._counters = (ctypes.c_void_p * 1)(*self.base)
+
+
 def sharded_group_forward(arena: PeerArena, local_layers, x, out_offsets, full_ns, col0s, sync: PeerSync, ws, stream=None,
                           x_ptr=None, M=None, ldx=None):
     """One launch: this rank's column shards of sibling layers `local_layers` (shared x [M, K]) stored at column
