@@ -307,6 +307,9 @@ class FusedShardedStep:
     + 128 launches + the final untag / wait) is one CUDA graph."""
     CALLS = (("q", "k", "v"), ("o",), ("gate", "up"), ("down",))
     X_OF = (None, "v", "o", "gate")          # input of call j (None: the block input = previous block's down / h)
+    # act-order layers carry their own x_perm, so siblings do not share a launch: one call per layer
+    CALLS_ACT = (("q",), ("k",), ("v",), ("o",), ("gate",), ("up",), ("down",))
+    X_OF_ACT = (None, None, None, "v", "o", "o", "gate")
 
     def __init__(self, blocks, dev, M, rank, world):
         import torch
@@ -314,11 +317,13 @@ class FusedShardedStep:
         import qllm_b200
         from qllm_b200.sharding import LocalArena, PeerArena, sharded_group_posts
         self.lib, self.blocks, self.M, self.world, self.rank, self.torch = qllm_b200.lib, blocks, M, world, rank, torch
+        if LAYOUT == "GPTQ_ACT":
+            self.CALLS, self.X_OF = self.CALLS_ACT, self.X_OF_ACT
         self.tagged = os.environ.get("B200Q_BENCH_COUNTERS") is None or world == 1
         esz = 4 if self.tagged else 2
         full = {n: N for n, _, N in SHAPES}
         payload = sum(((M * N * esz + 255) & ~255) for N in full.values())
-        self.arena = PeerArena(payload, n_slots=8 + 4 * len(blocks)) if world > 1 else LocalArena(payload, n_slots=8 + 4 * len(blocks), device=dev)
+        self.arena = PeerArena(payload, n_slots=8 + 7 * len(blocks)) if world > 1 else LocalArena(payload, n_slots=8 + 7 * len(blocks), device=dev)
         self.off = {n: self.arena.carve(M * N * esz) for n, N in full.items()}
         self.bufs = {n: self.arena.local_view(self.off[n], (M, N), torch.int32 if self.tagged else torch.float16) for n, N in full.items()}
         self.full = full
@@ -347,17 +352,19 @@ class FusedShardedStep:
         A, M = self.arena, self.M
         A.advance(stream)
         x_name, wait_slot, wait_count = None, -1, 0
-        stride = 4 * len(self.blocks) + 1
+        nc = len(self.CALLS)
+        stride = nc * len(self.blocks) + 1
+        seq_of = {}                                   # buffer name -> index of the call that wrote it last
+        block_in = None                               # the block's input: h, then the previous block's down
         for i, b in enumerate(self.blocks):
             for j, names in enumerate(self.CALLS):
-                slot = 1 + 4 * i + j
-                if self.X_OF[j] is not None:
-                    x_name = self.X_OF[j]
+                slot = 1 + nc * i + j
+                x_name = self.X_OF[j] if self.X_OF[j] is not None else block_in
                 layers = [b[n] for n in names]
                 offs, fulls, col0s = [self.off[n] for n in names], [self.full[n] for n in names], [l.col0 for l in layers]
                 if self.tagged:
                     flags = PEER_Y_TAGGED | (PEER_X_TAGGED if x_name is not None else 0) | node
-                    sync = A.sync_desc(flags=flags, tag_stride=stride, y_seq=slot, x_seq=slot - 1)
+                    sync = A.sync_desc(flags=flags, tag_stride=stride, y_seq=slot, x_seq=seq_of.get(x_name, 0))
                 else:
                     sync = A.sync_desc(wait_slot, wait_count, slot)
                 if x_name is None:
@@ -367,10 +374,12 @@ class FusedShardedStep:
                     sharded_group_forward(A, layers, None, offs, fulls, col0s, sync, self.ws, stream,
                                           x_ptr=xb.data_ptr(), M=M, ldx=xb.stride(0))
                 wait_slot, wait_count = slot, self.wait_counts[j]
-            x_name = "down"
+                for n in names:
+                    seq_of[n] = slot
+            block_in = "down"
         # the host (or lm_head) reads the complete hidden state as plain fp16
         if self.tagged:
-            A.untag(self.off["down"], M, HIDDEN, self.out, stride, 4 * len(self.blocks), stream)
+            A.untag(self.off["down"], M, HIDDEN, self.out, stride, seq_of["down"], stream)
         else:
             A.wait(wait_slot, wait_count, stream)
             self.out.copy_(self.bufs["down"])
@@ -389,7 +398,9 @@ def run_b200q(args, rank, world, local_rank):
     M = 1
     fused_err = None
     step = None
-    if world > 1 and os.environ.get("B200Q_BENCH_NCCL") is None and LAYOUT != "GPTQ_ACT":   # x_perm layers cannot read tagged activations yet
+    # act-order layers can read tagged activations (gathered word by word through x_perm) but that load stage is slow
+    # (N = 1: 140 vs 368 tokens/s): their N > 1 default stays the NCCL all-gather per layer, B200Q_BENCH_ACT_FUSED=1 selects the fused path
+    if world > 1 and os.environ.get("B200Q_BENCH_NCCL") is None and (LAYOUT != "GPTQ_ACT" or os.environ.get("B200Q_BENCH_ACT_FUSED")):
         try:
             step = FusedShardedStep(blocks, dev, M, rank, world)
         except Exception as e:                            # symmetric memory unavailable: NCCL all-gather per layer
@@ -400,7 +411,7 @@ def run_b200q(args, rank, world, local_rank):
             step = None
     fused_sharded = step is not None
     tagged_n1 = False
-    if world == 1 and args.handoff == "tagged" and LAYOUT != "GPTQ_ACT" and args.chain == 0:
+    if world == 1 and args.handoff == "tagged" and args.chain == 0:
         # single GPU, same kernels as the N > 1 path with one peer: activations travel between the QuantLinears as tagged words
         # and a consumer's load stage follows the data instead of the kernel boundary (B200Q_PEER_NODE_EPOCH)
         step = FusedShardedStep(blocks, dev, M, 0, 1)

@@ -176,7 +176,10 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
         if (4 * lane < len) {
           const size_t xo = (size_t)m * p.ldx + (size_t)ks * 32 + 4 * lane;
           uint2 raw;
-          if (PEER && p.sync.x_tagged) {
+          if (PEER && p.sync.x_tagged && p.xperm) {                      // act-order layer behind a tagged producer: gather the four words
+            const int4 pi = *reinterpret_cast<const int4*>(p.xperm + (size_t)ks * 32 + 4 * lane);
+            raw = st_gather_tagged4(p, reinterpret_cast<const uint32_t*>(p.x) + (size_t)m * p.ldx, pi, xtag);
+          } else if (PEER && p.sync.x_tagged) {
             raw = st_load_tagged4(p, reinterpret_cast<const uint32_t*>(p.x) + xo, xtag);
           } else if (p.xperm) {                                          // act-order re-layout: packed row j multiplies x[x_perm[j]]
             const int4 pi = *reinterpret_cast<const int4*>(p.xperm + (size_t)ks * 32 + 4 * lane);
@@ -529,7 +532,6 @@ cudaError_t launch_gemv_imma(const LinearArgs* a, int n, const PeerOut* peers, c
   p.layout = L.layout; p.bits = L.bits; p.group = L.group; p.K = L.K; p.G = L.G; p.zero_bias = L.zero_bias;
   p.x = a[0].x; p.ldx = a[0].ldx; p.M = a[0].M; p.xperm = L.x_perm;
   if ((a[0].x_mul || a[0].act_bf16) && sync) return cudaErrorInvalidValue;     // tagged activations carry no second operand
-  if (L.x_perm && sync && sync->x_tagged) return cudaErrorInvalidValue;    // gather through x_perm reads plain fp16 activations
   p.cluster = pl.cluster; p.tpc = pl.tpc; p.depth = pl.depth; p.steps_total = pl.steps_total; p.group_shift = pl.group_shift;
   p.gcap = pl.gcap; p.split_q = pl.split_q; p.split_r = pl.split_r; p.part_cap = pl.part_cap;
   p.x_stride = 0; p.red_stride = pl.tpc * kINT * a[0].M;

@@ -110,6 +110,26 @@ __device__ __forceinline__ uint2 st_load_tagged4(const StParams& p, const uint32
   return make_uint2((a & 0xffffu) | (b << 16), (c & 0xffffu) | (d << 16));
 }
 // step number of this launch: the step word, or (node-epoch mode) one more than the completed executions of this call
+// ... the same for an act-order layer: the four words sit at x_perm[j .. j + 3]
+__device__ __forceinline__ uint2 st_gather_tagged4(const StParams& p, const uint32_t* row, int4 idx, uint32_t tag) {
+  uint32_t a, b, c, d, spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(a) : "l"(row + idx.x) : "memory");
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(b) : "l"(row + idx.y) : "memory");
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(c) : "l"(row + idx.z) : "memory");
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(d) : "l"(row + idx.w) : "memory");
+    if (((a >> 16) == tag) & ((b >> 16) == tag) & ((c >> 16) == tag) & ((d >> 16) == tag)) break;
+    if (p.sync.node_epoch && !(p.sync_flags & 32)) __nanosleep((p.sync_flags & 64) ? 32 : 96);
+    if ((++spins & 1023u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) { p.sync.counters[p.sync.self][0] = ~0ull; break; }
+    }
+  }
+  return make_uint2((a & 0xffffu) | (b << 16), (c & 0xffffu) | (d << 16));
+}
 __device__ __forceinline__ uint32_t st_step(const StParams& p) {
   const volatile unsigned long long* e = reinterpret_cast<const volatile unsigned long long*>(p.sync.epoch);
   return p.sync.node_epoch ? (uint32_t)e[1 + p.sync.y_seq] + 1u : (uint32_t)e[0];

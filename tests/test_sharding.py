@@ -194,8 +194,8 @@ def test_peer_wait_times_out_instead_of_hanging():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("node_epoch", [0, 4])          # 4 = B200Q_PEER_NODE_EPOCH: the step comes from the call's own word
-@pytest.mark.parametrize("layout,M", [("GPTQ", 1), ("GEMM", 2)])
-def test_tagged_activation_chain_virtual_ranks(layout, M, node_epoch):
+@pytest.mark.parametrize("layout,M,act", [("GPTQ", 1, False), ("GEMM", 2, False), ("GPTQ", 1, True), ("GPTQ", 2, True)])
+def test_tagged_activation_chain_virtual_ranks(layout, M, act, node_epoch):
     """Flag-in-data hand-off: layer A's shards are written as tagged words (fp16 | step tag << 16) into every replica,
     layer B reads the tagged replica as its x, b200q_peer_untag returns plain fp16.  Two steps: the tag follows the
     epoch.  Checked against the oracle of the two-layer chain (x_B = fp16(y_A))."""
@@ -203,7 +203,8 @@ def test_tagged_activation_chain_virtual_ranks(layout, M, node_epoch):
     from qllm_b200 import Layer, check, lib
     from qllm_b200._lib import PEER_X_TAGGED, PEER_Y_TAGGED
     K, NA, NB, gs, world = 512, 1024, 512, 128, 2
-    LA, LB = O.make_layer(layout, 4, gs, K, NA, seed=41), O.make_layer(layout, 4, gs, NA, NB, seed=42)
+    # act: the consumer is a desc_act layer -- it gathers its tagged words through x_perm
+    LA, LB = O.make_layer(layout, 4, gs, K, NA, seed=41), O.make_layer(layout, 4, gs, NA, NB, seed=42, act_order=act)
     fA, fB = layer_from_dict(LA, device="cpu"), layer_from_dict(LB, device="cpu")
     sA = [sharding.shard_layer(fA, r, world).cuda() for r in range(world)]
     sB = [sharding.shard_layer(fB, r, world).cuda() for r in range(world)]
