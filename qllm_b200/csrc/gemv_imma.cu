@@ -85,6 +85,10 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
 
   ST_STAMP(0);
   pdl_launch_dependents();
+  // node-epoch mode: this call's step word is stable from the moment the kernel starts -- read it now, behind the weight
+  // prefetch, instead of as an L2 round trip in front of the tagged x loads and another in front of the stores
+  uint32_t step_early = 0;
+  if (PEER && p.sync.node_epoch) step_early = st_step(p);
   if (cs > 1) {
     if (rank == 0 && tid == 0) {
       mbar_init(rbar, 1);
@@ -160,7 +164,8 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
     st_sync_wait(p, lane);
   }
   ST_STAMP(2);
-  const uint32_t xtag = (PEER && p.sync.x_tagged) ? st_step_tag(p, p.sync.x_seq) : 0u;
+  const uint32_t step_now = (PEER && (p.sync.x_tagged || p.sync.y_tagged)) ? (p.sync.node_epoch ? step_early : st_step(p)) : 0u;
+  const uint32_t xtag = (step_now * p.sync.tag_stride + p.sync.x_seq) & 0xffffu;
   char* xq = smem + p.off_x + (size_t)(s_begin - cta_s0) * (2 * XQ_SUB);   // this warp's digit sub-steps
   float2* part = reinterpret_cast<float2*>(smem + p.off_part) + (size_t)warp * (p.part_cap * MTOK);
   const int part_sub = min(4, p.group >> 5);                             // sub-steps per full part (2 or 4: group >= 64)
@@ -362,7 +367,7 @@ __global__ void __launch_bounds__(kRpThreads, 3) gemv_imma_kernel(const __grid_c
     for (int idx = lane; idx < nt * NT * ms; idx += 32) redw[idx] = 0.f;
   }
   ST_STAMP(4);
-  st_reduce_store<MC, 256, PEER, FUSED>(p, SL, red, rbuf, rbar, nt * NT, ncols_cta, n0, cs, rank, tid);
+  st_reduce_store<MC, 256, PEER, FUSED>(p, SL, red, rbuf, rbar, nt * NT, ncols_cta, n0, cs, rank, tid, step_now);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -183,7 +183,8 @@ __device__ __forceinline__ void cp_async_wait_ring(int depth) {
 // FUSED: the residual epilogue of b200q_linear_ex is compiled in (the plain instantiations carry none of it)
 template <int MC, int MAXCOLS, bool PEER = false, bool FUSED = false>
 __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer& SL, const float* red, float* rbuf, uint64_t* rbar,
-                                                int ncols_alloc, int ncols_cta, int n0, int cs, int rank, int tid) {
+                                                int ncols_alloc, int ncols_cta, int n0, int cs, int rank, int tid,
+                                                uint32_t step_now = 0) {
   __syncthreads();
   const int totalv = ncols_alloc * p.M;
   const int wstride = p.red_stride;                         // floats between two warps' partial vectors
@@ -219,7 +220,7 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
         for (int q = 0; q < cs - 1; ++q) v[r] += rbuf[(size_t)q * totalv + idx];
     }
   }
-  const uint32_t ytag = (PEER && p.sync.y_tagged) ? st_step_tag(p, p.sync.y_seq) << 16 : 0u;
+  const uint32_t ytag = (PEER && p.sync.y_tagged) ? ((step_now * p.sync.tag_stride + p.sync.y_seq) & 0xffffu) << 16 : 0u;
   // node-epoch mode skipped the kernel-boundary wait ahead of the tagged x loads: the stores still follow the previous
   // kernel's last reads (and keep "kernel i ends after kernel i - 1" for everything downstream)
   if (PEER && p.sync.node_epoch && p.sync.x_tagged) pdl_wait();
@@ -255,7 +256,7 @@ __device__ __forceinline__ void st_reduce_store(const StParams& p, const StLayer
       unsigned int* arr = p.arrive + 2 + (p.sync.y_seq & 1u);   // neighbouring calls overlap: alternate words (self-cleaning)
       if (atomicAdd(arr, 1u) == (unsigned int)p.store_ctas - 1u) {
         *arr = 0u;
-        const_cast<unsigned long long*>(p.sync.epoch)[1 + p.sync.y_seq] = (unsigned long long)st_step(p);
+        const_cast<unsigned long long*>(p.sync.epoch)[1 + p.sync.y_seq] = (unsigned long long)step_now;
       }
     }
   }
