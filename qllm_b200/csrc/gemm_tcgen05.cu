@@ -89,8 +89,12 @@ __device__ __forceinline__ uint32_t tc_mapa(uint32_t local_smem, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void tc_st_cluster_f32(uint32_t addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+// one fp32 into the peer's shared memory, counted in bytes on the peer's mbarrier (the receiver waits on its own barrier:
+// the pattern the decode kernels' cluster reduction uses)
+__device__ __forceinline__ void tc_st_async_f32(uint32_t remote_addr, uint32_t remote_bar, float v) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(__float_as_uint(v)),
+               "r"(remote_bar)
+               : "memory");
 }
 // stamps (SM cycles): [kb][0..3] lead warp of the dequant team that owns kb (packed words landed, ALU done, A stage
 // free, TMEM store retired + signalled), [kb][4..7] MMA thread (X landed, A landed, MMAs issued, commits issued)
@@ -206,6 +210,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   uint64_t* a_empty = a_full + kNA;
   uint64_t* acc_full = a_empty + kNA;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* part_bar = acc_full + 2;                                // cluster split-K: counts the bytes of the peer's half-tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * kBN;
@@ -224,6 +229,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     for (int s = 0; s < kNSWMax; ++s) { mbar_init(&full_w[s], 1); mbar_init(&empty_w[s], kDqWarps); }
     for (int s = 0; s < kNA; ++s) { mbar_init(&a_full[s], kDqWarps); mbar_init(&a_empty[s], 1); }
     mbar_init(acc_full, TT <= 128 ? 2 : 1);
+    mbar_init(part_bar, 1);
     fence_mbar_init();
   }
   if (warp == kWAlloc) {
@@ -234,6 +240,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
   __syncthreads();                         // barriers initialised, TMEM allocated: the TMA producers start right away
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (TT >= 128 && p.csplit == 2 && tid == 0) mbar_expect_tx(part_bar, (uint32_t)((TT / 2) * kBN * 4));   // armed long before the peer sends
   if (tid == 0) TC_STAMP(p.kblocks, 1);                                                        // barriers + TMEM ready
   constexpr int P = 32 / BITS;                     // k values per packed word (3-bit: 32 values straddle three words)
   constexpr int RS = kBK * BITS / 32;              // packed rows per stage
@@ -505,18 +512,20 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     if (TT >= 128 && p.csplit == 2) {
       const uint32_t crank = tc_cluster_rank();
       tc_cluster_sync();                          // both CTAs' MMAs have completed: stage memory is free on either side
-      const uint32_t remote = tc_mapa(smem_u32(part), crank ^ 1u);
+      const uint32_t remote = tc_mapa(smem_u32(part), crank ^ 1u), remote_bar = tc_mapa(smem_u32(part_bar), crank ^ 1u);
       const int pbase = (int)(crank ^ 1u) * (TT / 2);
 #pragma unroll 1
       for (int j = eidx; j < TT / 64; j += 2 * kDqPar) {
         uint32_t v[32];
         load_acc(pbase + 32 * j, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) tc_st_cluster_f32(remote + (uint32_t)(((32 * j + i) * kBN + n) * 4), __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) tc_st_async_f32(remote + (uint32_t)(((32 * j + i) * kBN + n) * 4), remote_bar, __uint_as_float(v[i]));
       }
-      tc_cluster_sync();                          // the peer's half-tile has landed here (release / acquire at cluster scope)
       c_begin = (int)crank * (TT / 2);
       c_end = c_begin + TT / 2;
+      // the peer's half-tile has landed when its bytes are counted on this CTA's barrier.  Every epilogue thread waits (not
+      // only the finalising ones): the CTA must not leave while stores into its shared memory are in flight
+      mbar_wait_bounded(part_bar, 0, p.err, 8);
     }
 #pragma unroll 1
     for (int c0 = c_begin + eidx * 32; c0 < c_end && ok; c0 += 64 * kDqPar) {
@@ -635,10 +644,7 @@ gemm_tc_gptq_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_const
     }
     tc_fence_before();
   }
-  if (TT >= 128 && p.csplit == 2 && warp >= kDqWarps * kDqPar) {      // producer / issuer warps: the pair's two barriers count every thread
-    tc_cluster_sync();
-    tc_cluster_sync();
-  }
+  if (TT >= 128 && p.csplit == 2 && warp >= kDqWarps * kDqPar) tc_cluster_sync();   // producer / issuer warps: the pair's barrier counts every thread
   __syncthreads();
   if (tid == 0) TC_STAMP(p.kblocks, 4);                                                        // epilogue stored
   if (warp == kWAlloc) {

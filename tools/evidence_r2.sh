@@ -8,6 +8,7 @@ echo "== bench reference arm"; timeout 600 python bench.py --impl reference --st
 for c in prefill7b act13b mixtral; do echo "== bench $c"; timeout 900 python bench.py --config $c --steps 20 > $O/bench_$c.json 2> $O/bench_$c.err; tail -c 600 $O/bench_$c.json; done
 echo "== bench prefill7b M=2048"; timeout 900 python bench.py --config prefill7b --m 2048 --steps 5 > $O/bench_prefill7b_m2048.json 2>/dev/null; tail -c 500 $O/bench_prefill7b_m2048.json
 echo "== bench prefill7b, per-layer calls"; B200Q_BENCH_NO_GROUP=1 timeout 900 python bench.py --config prefill7b --steps 20 --no-cpu 2>/dev/null | tail -1 > $O/bench_prefill7b_nogroup.json; cut -c1-200 $O/bench_prefill7b_nogroup.json
+echo "== bench decode, tagged hand-off on one GPU"; timeout 600 python bench.py --handoff tagged --no-cpu --no-prefill --steps 100 2>/dev/null | tail -1 > $O/bench_tagged_n1.json; cut -c1-200 $O/bench_tagged_n1.json
 echo "== bench decode chain"; for c in 32; do timeout 600 python bench.py --chain $c --no-cpu --no-prefill --steps 100 2>/dev/null | tail -1 > $O/bench_chain$c.json; cut -c1-200 $O/bench_chain$c.json; done
 echo "== ncu launch list of the bench command"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemv|gemm_tc" -s 1024 -c 128 --csv --log-file $O/launches_bench.csv python bench.py --no-cpu --no-prefill --steps 2 --warmup 3 > $O/bench_under_ncu.log 2>&1
