@@ -149,6 +149,11 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / steps
     tok_s = blocks_per_step / (dt * BLOCKS)
     cores = torch.get_num_threads()
+    ref_cuda = None
+    try:                                               # labelled extra, not the arm's value: the reference's own CUDA kernel on this GPU
+        ref_cuda = reference_cuda_chain()
+    except Exception as e:
+        ref_cuda = {"error": f"{type(e).__name__}: {e}"[:200]}
     sample = (f"{blocks_per_step} of {BLOCKS} decoder blocks ({7 * blocks_per_step} QuantLinears, M=1, fp16) timed per step"
               + ("" if blocks_per_step == BLOCKS else f", x{BLOCKS / blocks_per_step:.2f} extrapolated"))
     print(json.dumps({
@@ -159,7 +164,59 @@ def run_reference(args, rank, world):
                    "layers": 7 * BLOCKS, "blocks_timed_per_step": blocks_per_step, "extrapolated": blocks_per_step != BLOCKS},
         "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_cuda_kernels": ref_cuda,
     }), flush=True)
+
+
+def reference_cuda_chain(steps=5):
+    """Extra beside the CPU arm: the same 224-layer decode chain through the reference's OWN CUDA kernel --
+    awq_inference_engine.gemm_forward_cuda (quant_linear_awq.py:142-148, split_k_iters = 8) compiled unmodified for sm_100 into
+    oracle/_ref -- on random AWQ-format buffers, one CUDA graph, CUDA events.  None when there is no GPU or no oracle/_ref."""
+    import glob
+    import torch
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not torch.cuda.is_available() or not glob.glob(os.path.join(ref, "awq_inference_engine*.so")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import awq_inference_engine as awq
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    ri = lambda *sh: torch.randint(-2 ** 31, 2 ** 31 - 1, sh, dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+    blocks = [{name: (ri(K, N // 8), ((torch.rand(K // GROUP, N, device=dev, generator=g) * 0.4 + 0.8) / (6.5 * K ** 0.5)).to(torch.float16),
+                      ri(K // GROUP, N // 8)) for name, K, N in SHAPES} for _ in range(BLOCKS)]
+    x0 = torch.randn(1, HIDDEN, device=dev, dtype=torch.float16)
+    f = lambda x, t: awq.gemm_forward_cuda(x, t[0], t[1], t[2], 8)
+
+    def token():
+        x = x0
+        for b in blocks:
+            q, k, v = f(x, b["q"]), f(x, b["k"]), f(x, b["v"])
+            o = f(v, b["o"])
+            gt, up = f(o, b["gate"]), f(o, b["up"])
+            x = f(gt, b["down"])
+        return x
+
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        token()
+        s.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            out = token()
+        for _ in range(2):
+            graph.replay()
+        s.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            graph.replay()
+        e1.record()
+        s.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": 1e3 / ms, "unit": "tokens/s", "ms_per_step": ms, "kernel": "awq_inference_engine.gemm_forward_cuda (reference csrc/awq_cuda, sm_100 build)",
+            "layers": len(SHAPES) * BLOCKS, "outputs_finite": bool(torch.isfinite(out.float()).all().item()),
+            "what": "the reference's own CUDA AWQ kernel over the same chain on this GPU (CUDA graph, inputs resident); the arm's value stays the CPU path"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -494,7 +551,7 @@ def run_b200q(args, rank, world, local_rank):
         return
     total_bytes = BLOCKS * sum(alg_bytes(K, N, M) + (K * 4 if LAYOUT == "GPTQ_ACT" else 0) for _, K, N in SHAPES)
     n_layers = BLOCKS * len(SHAPES)
-    achieved = total_bytes * world / world / (ms_per_step * 1e-3) / 1e9      # whole-job algorithmic GB/s
+    achieved = total_bytes / (ms_per_step * 1e-3) / 1e9                      # whole-job algorithmic GB/s
     roofline = {"bound": "hbm", "achieved": achieved / world, "peak": P["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / world / P["hbm_gbs"], "traffic": None, "peak_source": P["source"],
                 "kernel": ("decode_chain_kernel (persistent, TMA ring + IMMA.16832)" if chain_span else "gemv_imma_kernel (decode, IMMA.16832 on the K-packed re-layout)"), "bytes_per_launch": total_bytes / launches_per_step,
