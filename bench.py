@@ -356,6 +356,23 @@ class ChainDecodeStep:
         return self.out
 
 
+def handoff_schedule(calls, x_of, n_blocks):
+    """Call sequence of the fused sharded step: [(block, names, x_name, y_seq, x_seq)], tag_stride.  y_seq numbers the calls of
+    a token from 1; x_name is None for the first block's input (plain fp16 h), else the buffer the call reads; x_seq is the
+    y_seq of the call that wrote that buffer last -- what the consumer's awaited tag is built from."""
+    nc = len(calls)
+    seq_of, block_in, out = {}, None, []
+    for i in range(n_blocks):
+        for j, names in enumerate(calls):
+            slot = 1 + nc * i + j
+            x_name = x_of[j] if x_of[j] is not None else block_in
+            out.append((i, names, x_name, slot, seq_of.get(x_name, 0)))
+            for n in names:
+                seq_of[n] = slot
+        block_in = "down"
+    return out, nc * n_blocks + 1
+
+
 class FusedShardedStep:
     """N > 1: every call is one b200q_linear_group_sharded launch -- this rank's column shards, stored into every
     rank's replica over NVLink, with the cross-GPU hand-off inside the kernels: tagged activations (flag-in-data:
@@ -410,33 +427,26 @@ class FusedShardedStep:
         A.advance(stream)
         x_name, wait_slot, wait_count = None, -1, 0
         nc = len(self.CALLS)
-        stride = nc * len(self.blocks) + 1
-        seq_of = {}                                   # buffer name -> index of the call that wrote it last
-        block_in = None                               # the block's input: h, then the previous block's down
-        for i, b in enumerate(self.blocks):
-            for j, names in enumerate(self.CALLS):
-                slot = 1 + nc * i + j
-                x_name = self.X_OF[j] if self.X_OF[j] is not None else block_in
-                layers = [b[n] for n in names]
-                offs, fulls, col0s = [self.off[n] for n in names], [self.full[n] for n in names], [l.col0 for l in layers]
-                if self.tagged:
-                    flags = PEER_Y_TAGGED | (PEER_X_TAGGED if x_name is not None else 0) | node
-                    sync = A.sync_desc(flags=flags, tag_stride=stride, y_seq=slot, x_seq=seq_of.get(x_name, 0))
-                else:
-                    sync = A.sync_desc(wait_slot, wait_count, slot)
-                if x_name is None:
-                    sharded_group_forward(A, layers, self.h, offs, fulls, col0s, sync, self.ws, stream)
-                else:
-                    xb = self.bufs[x_name]
-                    sharded_group_forward(A, layers, None, offs, fulls, col0s, sync, self.ws, stream,
-                                          x_ptr=xb.data_ptr(), M=M, ldx=xb.stride(0))
-                wait_slot, wait_count = slot, self.wait_counts[j]
-                for n in names:
-                    seq_of[n] = slot
-            block_in = "down"
+        schedule, stride = handoff_schedule(self.CALLS, self.X_OF, len(self.blocks))
+        for i, names, x_name, slot, x_seq in schedule:
+            b, j = self.blocks[i], (slot - 1) % nc
+            layers = [b[n] for n in names]
+            offs, fulls, col0s = [self.off[n] for n in names], [self.full[n] for n in names], [l.col0 for l in layers]
+            if self.tagged:
+                flags = PEER_Y_TAGGED | (PEER_X_TAGGED if x_name is not None else 0) | node
+                sync = A.sync_desc(flags=flags, tag_stride=stride, y_seq=slot, x_seq=x_seq)
+            else:
+                sync = A.sync_desc(wait_slot, wait_count, slot)
+            if x_name is None:
+                sharded_group_forward(A, layers, self.h, offs, fulls, col0s, sync, self.ws, stream)
+            else:
+                xb = self.bufs[x_name]
+                sharded_group_forward(A, layers, None, offs, fulls, col0s, sync, self.ws, stream,
+                                      x_ptr=xb.data_ptr(), M=M, ldx=xb.stride(0))
+            wait_slot, wait_count = slot, self.wait_counts[j]
         # the host (or lm_head) reads the complete hidden state as plain fp16
         if self.tagged:
-            A.untag(self.off["down"], M, HIDDEN, self.out, stride, seq_of["down"], stream)
+            A.untag(self.off["down"], M, HIDDEN, self.out, stride, schedule[-1][3], stream)
         else:
             A.wait(wait_slot, wait_count, stream)
             self.out.copy_(self.bufs["down"])

@@ -150,3 +150,30 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
                     "-L", libdir, "-lb200q", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_bench_handoff_schedule():
+    """bench.py's fused-step call sequence: unique y_seq below the tag stride, and every consumer awaits the tag of the call
+    that wrote its input last (sibling groups and the one-call-per-layer form of act-order models)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    F = bench.FusedShardedStep
+    for calls, x_of in ((F.CALLS, F.X_OF), (F.CALLS_ACT, F.X_OF_ACT)):
+        sched, stride = bench.handoff_schedule(calls, x_of, 3)
+        seqs = [c[3] for c in sched]
+        assert seqs == list(range(1, len(calls) * 3 + 1)) and stride == len(calls) * 3 + 1
+        last_writer = {}
+        for blk, names, x_name, y_seq, x_seq in sched:
+            if x_name is None:
+                assert blk == 0 and x_seq == 0               # the token's input is plain fp16
+            else:
+                assert x_seq == last_writer[x_name] and 0 < x_seq < y_seq
+            for n in names:
+                last_writer[n] = y_seq
+        assert sched[-1][1] == ("down",)
+        # every block after the first reads the previous block's down
+        firsts = [c for c in sched if c[0] == 1 and x_of[(c[3] - 1) % len(calls)] is None]
+        assert firsts and all(c[2] == "down" and c[4] == len(calls) for c in firsts)
