@@ -800,7 +800,7 @@ static cudaError_t tc_launch(const LinearArgs& a, const PeerOut* peers) {
   if (!cached_tmap_2d(enc, &wmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, L.qw, (uint64_t)L.N, (uint64_t)(L.K * BITS / 32), (uint64_t)L.N * 4,
                       (uint32_t)kBN, (uint32_t)(kBK * BITS / 32), CU_TENSOR_MAP_SWIZZLE_NONE))
     return cudaErrorInvalidValue;
-  TcParams p;
+  TcParams p = {};
   p.L = L; p.M = a.M;
   if (peers) p.out = *peers; else { p.out.n = 1; p.out.y[0] = a.y; }
   p.ldy = a.ldy; p.n_offset = a.n_offset;
