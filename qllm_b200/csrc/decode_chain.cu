@@ -805,7 +805,7 @@ cudaError_t launch_decode_chain(const void* plan_host, const void* plan_dev, voi
     if (e != cudaSuccess) return e;
     attr_done[dev & 63][mi] = true;
   }
-  ChParams p;
+  ChParams p = {};
   p.plan = (const char*)plan_dev; p.ws = (char*)ws; p.h = *H; p.dbg = g_ch_dbg;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(H->n_cta);

@@ -657,7 +657,7 @@ cudaError_t launch_gemv_mma(const LinearArgs& a, const PeerOut* peers) {
   Plan pl;
   if (!make_plan(a.L, a.M, pl)) return cudaErrorInvalidValue;
   if (pl.n_tiles * 4 > (int)kCounterBytes) return cudaErrorInvalidValue;
-  GemvParams p;
+  GemvParams p = {};
   p.L = a.L; p.x = a.x; p.ldx = a.ldx; p.M = a.M;
   if (peers) p.out = *peers; else { p.out.n = 1; p.out.y[0] = a.y; }
   p.ldy = a.ldy; p.n_offset = a.n_offset;
