@@ -75,9 +75,10 @@ def test_ort_gemv(M):
     assert _rel(y, ref) < 2e-3           # the reference accumulates 8-term partial sums in fp16 (dq_gemv.cu:120-129)
 
 
-# NOTE (round 1): the reference's Marlin kernel (csrc/awq_cuda/quantization/marlin_cuda_kernel.cu, compiled
-# unmodified for compute_100/sm_100) raises cudaErrorIllegalInstruction on B200 for every shape tried
-# (M = 1, 16, 200; grouped and per-channel), which poisons the CUDA context of the whole pytest process.
-# There is therefore no reference-CUDA comparison for pack_mode=MARLIN; Marlin parity rests on the numpy
-# oracle (tests/test_gpu_parity.py) whose pack/unpack is pinned bit-exactly to the reference's own
-# QuantLinearMarlin.pack (tests/golden/marlin.npz).
+# NOTE: the reference's Marlin kernel (csrc/awq_cuda/quantization/marlin_cuda_kernel.cu, compiled unmodified for
+# compute_100 / sm_100) is not usable as a second oracle on B200.  tools/marlin_ref_probe.py runs it in one subprocess per
+# shape (profiles/r2_marlin_ref_probe_sm100.txt): cudaErrorIllegalInstruction -- which poisons the CUDA context of the
+# calling process -- at M = 1 and 16 and for per-channel scales at every size tried; correct at M = 200, 1024 x 512
+# (rel 7e-4 against this engine's Marlin path); wrong numbers at M = 512, 4096 x 4096 (rel 0.09-0.13 against both this
+# engine and the float64 oracle).  Marlin parity therefore rests on the numpy oracle (tests/test_gpu_parity.py), whose
+# pack / unpack is pinned bit-exactly to the reference's own QuantLinearMarlin.pack (tests/golden/marlin.npz).
